@@ -43,7 +43,7 @@ int oracle_ransac_replay(const int *valid, const int *count, int n_cand, int n_p
         if (count[c] > best_count) {
             best_count = count[c]; best = c;
             double w = best_count * one_over;
-            double p_no = 1.0 - pow(w, (double)sample_size);
+            double p_no = sample_size == 3 ? 1.0 - w * w * w : 1.0 - pow(w, (double)sample_size);
             if (p_no < eps) p_no = eps;
             if (p_no > 1.0 - eps) p_no = 1.0 - eps;
             k = log_prob / log(p_no);

@@ -1,0 +1,236 @@
+"""ctypes binding of libslam3d_b200.so (include/slam3d_b200.h).  No fallbacks: a missing library or a
+missing GPU is an error."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import numpy as np
+
+from . import _abi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+class LibraryMissing(RuntimeError):
+    pass
+
+
+class S3DError(RuntimeError):
+    pass
+
+
+def library_path() -> str:
+    return os.path.join(_HERE, "libslam3d_b200.so")
+
+
+# every symbol include/slam3d_b200.h declares (tests check that the .so exports all of them)
+EXPORTS = [
+    "s3d_abi_version", "s3d_create", "s3d_destroy", "s3d_last_error", "s3d_set_stream", "s3d_device_sm_count",
+    "s3d_launch_count", "s3d_cloud_upload", "s3d_cloud_from_device", "s3d_cloud_from_depth", "s3d_cloud_set_normals",
+    "s3d_cloud_set_normals_device", "s3d_cloud_size", "s3d_cloud_has_normals", "s3d_cloud_download",
+    "s3d_cloud_drop_index", "s3d_cloud_free", "s3d_segment_planes", "s3d_register_batch", "s3d_register_pair",
+    "s3d_last_correspondences", "s3d_last_timing", "s3d_icp_params_default", "s3d_plane_params_default",
+    "s3d_planar_keypoints", "s3d_gather_results",
+]
+
+
+def load_library():
+    """dlopen the CUDA library.  Raises LibraryMissing if it was not built (run __graft_entry__.build())."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = library_path()
+    if not os.path.exists(path):
+        raise LibraryMissing(f"{path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                             "(there is no CPU fallback)")
+    lib = C.CDLL(path)
+    vp, ci = C.c_void_p, C.c_int
+    lib.s3d_abi_version.restype = ci
+    lib.s3d_create.argtypes = [C.POINTER(vp), ci]
+    lib.s3d_destroy.argtypes = [vp]
+    lib.s3d_destroy.restype = None
+    lib.s3d_last_error.argtypes = [vp]
+    lib.s3d_last_error.restype = C.c_char_p
+    lib.s3d_set_stream.argtypes = [vp, vp]
+    lib.s3d_device_sm_count.argtypes = [vp]
+    lib.s3d_launch_count.argtypes = [vp]
+    lib.s3d_launch_count.restype = C.c_int64
+    lib.s3d_cloud_upload.argtypes = [vp, vp, ci, ci, C.POINTER(vp)]
+    lib.s3d_cloud_from_device.argtypes = [vp, vp, ci, C.POINTER(vp)]
+    lib.s3d_cloud_from_depth.argtypes = [vp, vp, ci, ci, C.POINTER(_abi.CameraC), C.c_float, C.POINTER(vp)]
+    lib.s3d_cloud_set_normals.argtypes = [vp, vp, vp, ci, ci]
+    lib.s3d_cloud_set_normals_device.argtypes = [vp, vp, vp, ci]
+    lib.s3d_cloud_size.argtypes = [vp]
+    lib.s3d_cloud_has_normals.argtypes = [vp]
+    lib.s3d_cloud_download.argtypes = [vp, vp, vp, vp, vp]
+    lib.s3d_cloud_drop_index.argtypes = [vp, vp]
+    lib.s3d_cloud_free.argtypes = [vp, vp]
+    lib.s3d_cloud_free.restype = None
+    lib.s3d_segment_planes.argtypes = [vp, vp, C.POINTER(_abi.PlaneParams), C.POINTER(_abi.Plane), C.POINTER(ci)]
+    lib.s3d_register_batch.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), vp, ci, C.POINTER(_abi.IcpParams),
+                                       C.POINTER(_abi.Result)]
+    lib.s3d_register_pair.argtypes = [vp, vp, vp, vp, C.POINTER(_abi.IcpParams), C.POINTER(_abi.Result)]
+    lib.s3d_last_correspondences.argtypes = [vp, vp, ci]
+    lib.s3d_last_timing.argtypes = [vp, C.POINTER(_abi.Timing)]
+    lib.s3d_icp_params_default.argtypes = [C.POINTER(_abi.IcpParams)]
+    lib.s3d_icp_params_default.restype = None
+    lib.s3d_plane_params_default.argtypes = [C.POINTER(_abi.PlaneParams)]
+    lib.s3d_plane_params_default.restype = None
+    lib.s3d_planar_keypoints.argtypes = [vp, vp, ci, ci, C.POINTER(_abi.CameraC), vp, ci, C.c_float, ci, C.c_uint64, vp]
+    lib.s3d_gather_results.argtypes = [vp, vp, C.POINTER(_abi.Result), ci, ci, C.POINTER(_abi.Result)]
+    _LIB = lib
+    return lib
+
+
+class Cloud:
+    """Device-resident cloud handle (s3d_cloud*)."""
+
+    def __init__(self, ctx: "Context", handle):
+        self.ctx, self.handle = ctx, handle
+
+    def __len__(self):
+        return self.ctx.lib.s3d_cloud_size(self.handle)
+
+    @property
+    def has_normals(self) -> bool:
+        return bool(self.ctx.lib.s3d_cloud_has_normals(self.handle))
+
+    def set_normals(self, normals: np.ndarray):
+        a = np.ascontiguousarray(normals, dtype=np.float32)
+        assert a.ndim == 2 and a.shape[1] >= 3 and a.shape[0] == len(self)
+        self.ctx._check(self.ctx.lib.s3d_cloud_set_normals(self.ctx.h, self.handle, a.ctypes.data, a.shape[1], a.shape[0]))
+
+    def set_normals_device(self, dptr: int, n: int):
+        self.ctx._check(self.ctx.lib.s3d_cloud_set_normals_device(self.ctx.h, self.handle, C.c_void_p(dptr), n))
+
+    def download(self, xyz=True, normals=False, labels=False):
+        n = len(self)
+        out = {}
+        ax = np.empty((n, 3), np.float32) if xyz else None
+        an = np.empty((n, 3), np.float32) if normals else None
+        al = np.empty(n, np.int32) if labels else None
+        self.ctx._check(self.ctx.lib.s3d_cloud_download(self.ctx.h, self.handle, ax.ctypes.data if xyz else None,
+                                                        an.ctypes.data if normals else None,
+                                                        al.ctypes.data if labels else None))
+        if xyz:
+            out["xyz"] = ax
+        if normals:
+            out["normals"] = an
+        if labels:
+            out["labels"] = al
+        return out
+
+    def segment_planes(self, params: _abi.PlaneParams | None = None):
+        """GraphicEnd::extractPlanesAndGenerateImage (reference src/GraphicEnd.cpp:353-430) on the device."""
+        params = params or _abi.plane_params()
+        planes = (_abi.Plane * max(1, params.max_planes))()
+        k = C.c_int(0)
+        self.ctx._check(self.ctx.lib.s3d_segment_planes(self.ctx.h, self.handle, C.byref(params), planes, C.byref(k)))
+        return [dict(coef=np.array(list(planes[i].coef), np.float32), inliers=planes[i].inliers,
+                     hypotheses=planes[i].hypotheses) for i in range(k.value)]
+
+    def drop_index(self):
+        self.ctx.lib.s3d_cloud_drop_index(self.ctx.h, self.handle)
+
+    def free(self):
+        if self.handle is not None:
+            self.ctx.lib.s3d_cloud_free(self.ctx.h, self.handle)
+            self.handle = None
+
+
+class Context:
+    """Per-GPU context (s3d_ctx*)."""
+
+    def __init__(self, device: int = 0):
+        self.lib = load_library()
+        h = C.c_void_p()
+        rc = self.lib.s3d_create(C.byref(h), device)
+        if rc != 0:
+            raise S3DError(f"s3d_create(device={device}) failed rc={rc}: a CUDA device is required (no CPU fallback)")
+        self.h = h
+
+    def _check(self, rc: int):
+        if rc != 0:
+            raise S3DError(f"rc={rc}: {self.lib.s3d_last_error(self.h).decode()}")
+
+    def close(self):
+        if self.h is not None:
+            self.lib.s3d_destroy(self.h)
+            self.h = None
+
+    def set_stream(self, cuda_stream: int):
+        self._check(self.lib.s3d_set_stream(self.h, C.c_void_p(cuda_stream)))
+
+    @property
+    def sm_count(self) -> int:
+        return self.lib.s3d_device_sm_count(self.h)
+
+    @property
+    def launch_count(self) -> int:
+        return self.lib.s3d_launch_count(self.h)
+
+    def upload(self, xyz: np.ndarray, normals: np.ndarray | None = None) -> Cloud:
+        a = np.ascontiguousarray(xyz, dtype=np.float32)
+        assert a.ndim == 2 and a.shape[1] >= 3
+        h = C.c_void_p()
+        self._check(self.lib.s3d_cloud_upload(self.h, a.ctypes.data, a.shape[1], a.shape[0], C.byref(h)))
+        c = Cloud(self, h)
+        if normals is not None:
+            c.set_normals(normals)
+        return c
+
+    def from_device(self, dptr: int, n: int) -> Cloud:
+        h = C.c_void_p()
+        self._check(self.lib.s3d_cloud_from_device(self.h, C.c_void_p(dptr), n, C.byref(h)))
+        return Cloud(self, h)
+
+    def from_depth(self, depth: np.ndarray, cam, z_max: float = 0.0) -> Cloud:
+        d = np.ascontiguousarray(depth, dtype=np.uint16)
+        camc = _abi.camera_c(cam)
+        h = C.c_void_p()
+        self._check(self.lib.s3d_cloud_from_depth(self.h, d.ctypes.data, d.shape[1], d.shape[0], C.byref(camc),
+                                                  C.c_float(z_max), C.byref(h)))
+        return Cloud(self, h)
+
+    def register_batch(self, srcs, tgts, guess=None, params: _abi.IcpParams | None = None, raw: bool = False):
+        """Batched GraphicEnd::multiPnP (reference src/GraphicEnd.cpp:557-659): one result per (src, tgt)."""
+        params = params or _abi.icp_params()
+        n = len(srcs)
+        assert n == len(tgts) and n > 0
+        sa = (C.c_void_p * n)(*[s.handle for s in srcs])
+        ta = (C.c_void_p * n)(*[t.handle for t in tgts])
+        g = None
+        if guess is not None:
+            g = np.ascontiguousarray(guess, dtype=np.float64).reshape(n, 16)
+        res = (_abi.Result * n)()
+        self._check(self.lib.s3d_register_batch(self.h, sa, ta, g.ctypes.data if g is not None else None, n,
+                                                C.byref(params), res))
+        if raw:
+            return res
+        return [_abi.result_to_dict(res[i]) for i in range(n)]
+
+    def register(self, src: Cloud, tgt: Cloud, guess=None, params: _abi.IcpParams | None = None) -> dict:
+        return self.register_batch([src], [tgt], None if guess is None else [guess], params)[0]
+
+    def last_correspondences(self, n: int) -> np.ndarray:
+        out = np.empty(n, np.int32)
+        self._check(self.lib.s3d_last_correspondences(self.h, out.ctypes.data, n))
+        return out
+
+    def last_timing(self) -> dict:
+        t = _abi.Timing()
+        self.lib.s3d_last_timing(self.h, C.byref(t))
+        return dict(index_ms=t.index_ms, iterate_ms=t.iterate_ms, iter_launches=t.iter_launches,
+                    total_launches=t.total_launches)
+
+    def planar_keypoints(self, depth: np.ndarray, cam, uv: np.ndarray, threshold=0.01, min_inliers=40, seed=12345):
+        """isPlanar (reference src/planarFeatures.cpp:88-136) for a batch of keypoints."""
+        d = np.ascontiguousarray(depth, dtype=np.uint16)
+        uv = np.ascontiguousarray(uv, dtype=np.int32).reshape(-1, 2)
+        flags = np.zeros(len(uv), np.uint8)
+        camc = _abi.camera_c(cam)
+        self._check(self.lib.s3d_planar_keypoints(self.h, d.ctypes.data, d.shape[1], d.shape[0], C.byref(camc),
+                                                  uv.ctypes.data, len(uv), C.c_float(threshold), int(min_inliers),
+                                                  C.c_uint64(seed), flags.ctypes.data))
+        return flags

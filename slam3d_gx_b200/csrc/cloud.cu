@@ -1,0 +1,310 @@
+// cloud.cu -- context and device-resident clouds of libslam3d_b200.
+//
+// A cloud is stored as float4 (x,y,z,1) so that every point is one coalesced 16-byte load, plus an
+// optional float4 normal (nx,ny,nz,valid) and an int32 plane label per point.  It replaces the
+// pcl::PointCloud<PointXYZRGBA>::Ptr members of the reference front end (src/GraphicEnd.h:181-183).
+#include <cstdio>
+#include <cstring>
+#include <cmath>
+#include "context.h"
+#include "compact.cuh"
+
+int s3d_fail(s3d_ctx *ctx, int code, const char *what, cudaError_t e)
+{
+    if (ctx) {
+        ctx->err = what ? what : "";
+        if (e != cudaSuccess) { ctx->err += ": "; ctx->err += cudaGetErrorString(e); }
+    }
+    return code;
+}
+
+void *s3d_pinned(s3d_ctx *ctx, size_t bytes)
+{
+    if (bytes > ctx->cap_pinned) {
+        if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+        ctx->h_pinned = nullptr; ctx->cap_pinned = 0;
+        size_t cap = bytes + bytes / 2 + 4096;
+        if (cudaMallocHost(&ctx->h_pinned, cap) != cudaSuccess) { ctx->h_pinned = nullptr; return nullptr; }
+        ctx->cap_pinned = cap;
+    }
+    return ctx->h_pinned;
+}
+
+extern "C" int s3d_abi_version(void) { return S3D_ABI_VERSION; }
+
+extern "C" int s3d_create(s3d_ctx **out, int device_id)
+{
+    if (!out) return S3D_E_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0 || device_id < 0 || device_id >= ndev) {
+        // No CPU fallback by design: the product path requires a CUDA device.
+        fprintf(stderr, "slam3d_b200: no usable CUDA device %d (%s)\n", device_id,
+                e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0 or id out of range");
+        return S3D_E_CUDA;
+    }
+    s3d_ctx *ctx = new s3d_ctx();
+    ctx->device = device_id;
+    if (cudaSetDevice(device_id) != cudaSuccess) { delete ctx; return S3D_E_CUDA; }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device_id) != cudaSuccess) { delete ctx; return S3D_E_CUDA; }
+    ctx->sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return S3D_E_CUDA; }
+    ctx->stream = ctx->own_stream;
+    for (int i = 0; i < 4; ++i) cudaEventCreate(&ctx->ev[i]);
+    *out = ctx;
+    return S3D_OK;
+}
+
+extern "C" void s3d_destroy(s3d_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (auto &kv : ctx->graphs) cudaGraphExecDestroy(kv.second);
+    cudaFree(ctx->d_desc); cudaFreeHost(ctx->h_desc);
+    cudaFree(ctx->d_state); cudaFreeHost(ctx->h_state);
+    cudaFree(ctx->d_partials); cudaFree(ctx->d_nn_idx); cudaFree(ctx->d_nn_d2); cudaFree(ctx->d_last_nn);
+    cudaFree(ctx->d_seg);
+    if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+    for (int i = 0; i < 4; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+}
+
+extern "C" const char *s3d_last_error(const s3d_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+extern "C" int s3d_set_stream(s3d_ctx *ctx, void *cuda_stream)
+{
+    if (!ctx) return S3D_E_ARG;
+    cudaStreamSynchronize(ctx->stream);
+    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    // graphs were captured on the previous stream's topology only; they stay valid for launch on any stream
+    return S3D_OK;
+}
+
+extern "C" int s3d_device_sm_count(const s3d_ctx *ctx) { return ctx ? ctx->sm_count : 0; }
+extern "C" int64_t s3d_launch_count(const s3d_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+// ------------------------------------------------------------------------------------------------
+
+static int cloud_alloc(s3d_ctx *ctx, int n, s3d_cloud **out)
+{
+    s3d_cloud *c = new s3d_cloud();
+    c->n = n;
+    cudaError_t e = cudaMalloc(&c->d_pts, sizeof(float4) * (size_t)(n > 0 ? n : 1));
+    if (e != cudaSuccess) { delete c; return s3d_fail(ctx, S3D_E_CUDA, "cudaMalloc cloud", e); }
+    *out = c;
+    return S3D_OK;
+}
+
+__global__ void pack_xyz_kernel(const float *in, int stride, int n, float4 *out) /* may run in place (stride 4) */
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float *p = in + (size_t)i * stride;
+    out[i] = make_float4(p[0], p[1], p[2], 1.0f);
+}
+
+__global__ void pack_normals_kernel(const float *__restrict__ in, int stride, int n, float4 *__restrict__ out)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float *p = in + (size_t)i * stride;
+    float x = p[0], y = p[1], z = p[2];
+    bool ok = isfinite(x) && isfinite(y) && isfinite(z) && (x != 0.f || y != 0.f || z != 0.f);
+    out[i] = ok ? make_float4(x, y, z, 1.0f) : make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+extern "C" int s3d_cloud_upload(s3d_ctx *ctx, const float *xyz, int stride_floats, int n, s3d_cloud **out)
+{
+    if (!ctx || !out || n < 0 || stride_floats < 3 || (n > 0 && !xyz)) return s3d_fail(ctx, S3D_E_ARG, "s3d_cloud_upload: bad argument");
+    cudaSetDevice(ctx->device);
+    s3d_cloud *c = nullptr;
+    int rc = cloud_alloc(ctx, n, &c);
+    if (rc) return rc;
+    if (n > 0) {
+        size_t bytes = sizeof(float) * (size_t)n * stride_floats;
+        if (stride_floats == 4) {
+            // PCD rows "x y z rgba" are already float4-shaped: copy straight, then normalise w on device
+            S3D_CUDA(ctx, cudaMemcpyAsync(c->d_pts, xyz, bytes, cudaMemcpyHostToDevice, ctx->stream));
+            pack_xyz_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>((const float *)c->d_pts, 4, n, c->d_pts);
+            S3D_LAUNCHED(ctx);
+        } else {
+            float *tmp = nullptr;
+            S3D_CUDA(ctx, cudaMalloc(&tmp, bytes));
+            S3D_CUDA(ctx, cudaMemcpyAsync(tmp, xyz, bytes, cudaMemcpyHostToDevice, ctx->stream));
+            pack_xyz_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(tmp, stride_floats, n, c->d_pts);
+            S3D_LAUNCHED(ctx);
+            S3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            cudaFree(tmp);
+        }
+        S3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    *out = c;
+    return S3D_OK;
+}
+
+extern "C" int s3d_cloud_from_device(s3d_ctx *ctx, const void *d_xyzw, int n, s3d_cloud **out)
+{
+    if (!ctx || !out || n < 0 || (n > 0 && !d_xyzw)) return s3d_fail(ctx, S3D_E_ARG, "s3d_cloud_from_device: bad argument");
+    cudaSetDevice(ctx->device);
+    s3d_cloud *c = nullptr;
+    int rc = cloud_alloc(ctx, n, &c);
+    if (rc) return rc;
+    if (n > 0) {
+        pack_xyz_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>((const float *)d_xyzw, 4, n, c->d_pts);
+        S3D_LAUNCHED(ctx);
+    }
+    *out = c;
+    return S3D_OK;
+}
+
+// ---- depth image -> cloud ----------------------------------------------------------------------
+// x=(u-cx)z/fx, y=(v-cy)z/fy, z=d/factor evaluated in double and stored as float, exactly like
+// reference src/convert2PCD.cpp:64-68 (IEEE double mul/div/sub are bit-reproducible on the device).
+struct DepthPred {
+    const uint16_t *depth; double inv_unused; double factor; float z_max;
+    __device__ bool operator()(int i) const
+    {
+        uint16_t d = depth[i];
+        if (d == 0) return false;
+        if (z_max > 0.f) { float fz = (float)__ddiv_rn((double)d, factor); return fz >= 0.f && fz <= z_max; }
+        return true;
+    }
+};
+struct DepthEmit {
+    const uint16_t *depth; int width; double fx, fy, cx, cy, factor; float4 *out;
+    __device__ void operator()(int i, uint32_t pos) const
+    {
+        int m = i / width, n = i - m * width;
+        double z = __ddiv_rn((double)depth[i], factor);
+        double x = __ddiv_rn(__dmul_rn(__dsub_rn((double)n, cx), z), fx);
+        double y = __ddiv_rn(__dmul_rn(__dsub_rn((double)m, cy), z), fy);
+        out[pos] = make_float4((float)x, (float)y, (float)z, 1.0f);
+    }
+};
+struct NoDrop { __device__ void operator()(int) const {} };
+
+extern "C" int s3d_cloud_from_depth(s3d_ctx *ctx, const uint16_t *depth, int width, int height,
+                                    const s3d_camera *cam, float z_max, s3d_cloud **out)
+{
+    if (!ctx || !out || !depth || !cam || width <= 0 || height <= 0) return s3d_fail(ctx, S3D_E_ARG, "s3d_cloud_from_depth: bad argument");
+    cudaSetDevice(ctx->device);
+    int npx = width * height;
+    int nblocks = (npx + S3D_COMPACT_BLOCK - 1) / S3D_COMPACT_BLOCK;
+    uint16_t *d_depth = nullptr; uint32_t *d_counts = nullptr; float4 *d_tmp = nullptr;
+    S3D_CUDA(ctx, cudaMalloc(&d_depth, sizeof(uint16_t) * (size_t)npx));
+    S3D_CUDA(ctx, cudaMalloc(&d_counts, sizeof(uint32_t) * (size_t)(nblocks + 1)));
+    S3D_CUDA(ctx, cudaMalloc(&d_tmp, sizeof(float4) * (size_t)npx));
+    S3D_CUDA(ctx, cudaMemcpyAsync(d_depth, depth, sizeof(uint16_t) * (size_t)npx, cudaMemcpyHostToDevice, ctx->stream));
+    DepthPred pred{d_depth, 0.0, cam->factor, z_max};
+    DepthEmit emit{d_depth, width, cam->fx, cam->fy, cam->cx, cam->cy, cam->factor, d_tmp};
+    compact_count_kernel<<<nblocks, S3D_COMPACT_BLOCK, 0, ctx->stream>>>(npx, pred, d_counts);
+    S3D_LAUNCHED(ctx);
+    compact_scan_kernel<<<1, 1024, 0, ctx->stream>>>(d_counts, nblocks, d_counts + nblocks);
+    S3D_LAUNCHED(ctx);
+    compact_write_kernel<<<nblocks, S3D_COMPACT_BLOCK, 0, ctx->stream>>>(npx, pred, emit, NoDrop(), d_counts);
+    S3D_LAUNCHED(ctx);
+    uint32_t total = 0;
+    S3D_CUDA(ctx, cudaMemcpyAsync(&total, d_counts + nblocks, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    S3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    s3d_cloud *c = nullptr;
+    int rc = cloud_alloc(ctx, (int)total, &c);
+    if (rc == S3D_OK && total > 0)
+        rc = cudaMemcpyAsync(c->d_pts, d_tmp, sizeof(float4) * (size_t)total, cudaMemcpyDeviceToDevice, ctx->stream) == cudaSuccess
+                 ? S3D_OK : s3d_fail(ctx, S3D_E_CUDA, "copy compacted cloud");
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_depth); cudaFree(d_counts); cudaFree(d_tmp);
+    if (rc) { if (c) { cudaFree(c->d_pts); delete c; } return rc; }
+    *out = c;
+    return S3D_OK;
+}
+
+// ---- normals / download ------------------------------------------------------------------------
+
+static int ensure_normals(s3d_ctx *ctx, s3d_cloud *c)
+{
+    if (!c->d_nrm) S3D_CUDA(ctx, cudaMalloc(&c->d_nrm, sizeof(float4) * (size_t)(c->n > 0 ? c->n : 1)));
+    return S3D_OK;
+}
+
+extern "C" int s3d_cloud_set_normals(s3d_ctx *ctx, s3d_cloud *cloud, const float *nrm, int stride_floats, int n)
+{
+    if (!ctx || !cloud || !nrm || stride_floats < 3 || n != cloud->n) return s3d_fail(ctx, S3D_E_ARG, "s3d_cloud_set_normals: bad argument");
+    cudaSetDevice(ctx->device);
+    int rc = ensure_normals(ctx, cloud);
+    if (rc) return rc;
+    if (n > 0) {
+        float *tmp = nullptr;
+        size_t bytes = sizeof(float) * (size_t)n * stride_floats;
+        S3D_CUDA(ctx, cudaMalloc(&tmp, bytes));
+        S3D_CUDA(ctx, cudaMemcpyAsync(tmp, nrm, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        pack_normals_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(tmp, stride_floats, n, cloud->d_nrm);
+        S3D_LAUNCHED(ctx);
+        S3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        cudaFree(tmp);
+    }
+    cloud->grid.valid = false; // sorted normals are stale
+    return S3D_OK;
+}
+
+extern "C" int s3d_cloud_set_normals_device(s3d_ctx *ctx, s3d_cloud *cloud, const void *d_nrm, int n)
+{
+    if (!ctx || !cloud || !d_nrm || n != cloud->n) return s3d_fail(ctx, S3D_E_ARG, "s3d_cloud_set_normals_device: bad argument");
+    cudaSetDevice(ctx->device);
+    int rc = ensure_normals(ctx, cloud);
+    if (rc) return rc;
+    if (n > 0) {
+        pack_normals_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>((const float *)d_nrm, 4, n, cloud->d_nrm);
+        S3D_LAUNCHED(ctx);
+    }
+    cloud->grid.valid = false;
+    return S3D_OK;
+}
+
+extern "C" int s3d_cloud_size(const s3d_cloud *cloud) { return cloud ? cloud->n : 0; }
+extern "C" int s3d_cloud_has_normals(const s3d_cloud *cloud) { return cloud && cloud->d_nrm ? 1 : 0; }
+
+extern "C" int s3d_cloud_download(s3d_ctx *ctx, const s3d_cloud *cloud, float *xyz, float *normals, int32_t *labels)
+{
+    if (!ctx || !cloud) return s3d_fail(ctx, S3D_E_ARG, "s3d_cloud_download: bad argument");
+    cudaSetDevice(ctx->device);
+    int n = cloud->n;
+    if (n == 0) return S3D_OK;
+    std::vector<float4> tmp((size_t)n);
+    if (xyz) {
+        S3D_CUDA(ctx, cudaMemcpyAsync(tmp.data(), cloud->d_pts, sizeof(float4) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+        S3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        for (int i = 0; i < n; ++i) { xyz[3 * i] = tmp[i].x; xyz[3 * i + 1] = tmp[i].y; xyz[3 * i + 2] = tmp[i].z; }
+    }
+    if (normals) {
+        if (!cloud->d_nrm) return s3d_fail(ctx, S3D_E_STATE, "cloud has no normals");
+        S3D_CUDA(ctx, cudaMemcpyAsync(tmp.data(), cloud->d_nrm, sizeof(float4) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+        S3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        for (int i = 0; i < n; ++i) { normals[3 * i] = tmp[i].x; normals[3 * i + 1] = tmp[i].y; normals[3 * i + 2] = tmp[i].z; }
+    }
+    if (labels) {
+        if (!cloud->d_labels) return s3d_fail(ctx, S3D_E_STATE, "cloud has no labels");
+        S3D_CUDA(ctx, cudaMemcpyAsync(labels, cloud->d_labels, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+        S3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return S3D_OK;
+}
+
+extern "C" int s3d_cloud_drop_index(s3d_ctx *ctx, s3d_cloud *cloud)
+{
+    if (!ctx || !cloud) return S3D_E_ARG;
+    cloud->grid.valid = false;
+    return S3D_OK;
+}
+
+extern "C" void s3d_cloud_free(s3d_ctx *ctx, s3d_cloud *cloud)
+{
+    if (!cloud) return;
+    if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
+    s3d_grid_free(cloud->grid);
+    cudaFree(cloud->d_pts); cudaFree(cloud->d_nrm); cudaFree(cloud->d_labels);
+    delete cloud;
+}

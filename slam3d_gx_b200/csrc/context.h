@@ -1,0 +1,95 @@
+// context.h -- internal objects behind the opaque handles of include/slam3d_b200.h
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include <map>
+#include "../../include/slam3d_b200.h"
+
+#define S3D_GRID_MAX_CELLS (1u << 23)   // dense cell-start array budget per target (32 MiB)
+#define S3D_GRID_MAX_DIM 2040           // per-axis cap: keeps the float cell coordinate error < 1e-3 cells
+
+// Device-resident description of a target's search grid; written by grid_setup_kernel, read by
+// every kernel that searches (no host round trip between build and use).
+struct GridParams {
+    float ox, oy, oz;      // origin (bbox min)
+    float inv_cell, cell;
+    int nx, ny, nz;
+    int ncells;
+    int n_points;
+};
+
+struct GridIndex {
+    bool valid = false;
+    bool has_normals = false;
+    float requested_cell = 0.f;
+    GridParams *d_params = nullptr;   // 1
+    uint32_t *d_cell_start = nullptr; // S3D_GRID_MAX_CELLS + 1
+    float4 *d_sorted_pts = nullptr;   // n : (x,y,z, original index bits)
+    float4 *d_sorted_nrm = nullptr;   // n : (nx,ny,nz,valid) in sorted order
+    uint32_t *d_rank = nullptr;       // n : rank of the point inside its cell
+    uint32_t *d_bbox = nullptr;       // 6 ordered-uint min/max
+    uint32_t *d_block_sums = nullptr; // scan scratch
+};
+
+struct s3d_cloud {
+    int n = 0;
+    float4 *d_pts = nullptr;      // (x,y,z,1)
+    float4 *d_nrm = nullptr;      // (nx,ny,nz,valid) or null
+    int32_t *d_labels = nullptr;  // plane id or -1, or null
+    GridIndex grid;
+};
+
+// one registration unit as the kernels see it
+struct PairDesc {
+    const float4 *src; int n_src;
+    const float4 *tgt; const float4 *tgt_nrm; int n_tgt;            // original order (brute force)
+    const float4 *sorted_pts; const float4 *sorted_nrm;             // grid order
+    const uint32_t *cell_start; const GridParams *grid;
+};
+
+struct PairState {
+    double T[12];
+    float Tf[12];
+    double fitness;
+    int inliers;
+    int iterations;
+    int status;
+    unsigned ticket;
+};
+
+struct s3d_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    int64_t launches = 0;
+    // batch scratch (grown on demand)
+    int cap_pairs = 0, cap_ctas = 0;
+    PairDesc *d_desc = nullptr; PairDesc *h_desc = nullptr;
+    PairState *d_state = nullptr; PairState *h_state = nullptr;
+    double *d_partials = nullptr;     // [pairs][ctas][S3D_NACC]
+    // brute-force scratch + last-correspondence buffer
+    int cap_nn = 0;
+    int32_t *d_nn_idx = nullptr; float *d_nn_d2 = nullptr;
+    int last_nn_n = 0; int32_t *d_last_nn = nullptr; int cap_last_nn = 0;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    s3d_timing timing = {0, 0, 0, 0};
+    // plane segmentation scratch
+    size_t cap_seg = 0;
+    void *d_seg = nullptr;
+    void *h_pinned = nullptr; size_t cap_pinned = 0;
+    std::map<uint64_t, cudaGraphExec_t> graphs;
+};
+
+int s3d_fail(s3d_ctx *ctx, int code, const char *what, cudaError_t e = cudaSuccess);
+#define S3D_CUDA(ctx, call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return s3d_fail(ctx, S3D_E_CUDA, #call, e__); } while (0)
+#define S3D_LAUNCHED(ctx) do { (ctx)->launches++; cudaError_t e__ = cudaGetLastError(); if (e__ != cudaSuccess) return s3d_fail(ctx, S3D_E_CUDA, "kernel launch", e__); } while (0)
+
+// grid.cu
+int s3d_grid_build(s3d_ctx *ctx, s3d_cloud *cloud, float cell);
+void s3d_grid_free(GridIndex &g);
+// pinned staging
+void *s3d_pinned(s3d_ctx *ctx, size_t bytes);

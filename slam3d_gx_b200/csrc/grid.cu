@@ -1,0 +1,230 @@
+// grid.cu -- device-built uniform grid over a target cloud: the exact-NN search index.
+//
+// Plays the role of the FLANN KD-tree behind pcl::search::KdTree in PCL-1.7
+// CorrespondenceEstimation (the "PCL KD-tree calls" of the north star), re-designed for the GPU:
+// a counting sort of the target points by cell (x fastest), so that any run of cells along x is
+// one contiguous, coalescible range of float4 points.  Everything, including the choice of the
+// cell size, happens on the device: there is no host round trip between build and first query.
+//
+//   bbox reduce -> grid_setup (1 thread) -> zero counts -> count (atomic rank) -> exclusive scan
+//   -> scatter (points + normals into cell order, original index kept in .w)
+#include "context.h"
+#include "common.cuh"
+#include "grid.cuh"
+#include "compact.cuh"
+#include <cstdlib>
+
+#define SCAN_ITEMS 8
+#define SCAN_BLOCK 1024
+#define SCAN_TILE (SCAN_ITEMS * SCAN_BLOCK)
+
+__global__ void bbox_init_kernel(uint32_t *bbox)
+{
+    if (threadIdx.x < 3) bbox[threadIdx.x] = 0xFFFFFFFFu;
+    else if (threadIdx.x < 6) bbox[threadIdx.x] = 0u;
+}
+
+__global__ void __launch_bounds__(256) bbox_kernel(const float4 *__restrict__ pts, int n, uint32_t *__restrict__ bbox)
+{
+    float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        float4 p = pts[i];
+        mn[0] = fminf(mn[0], p.x); mx[0] = fmaxf(mx[0], p.x);
+        mn[1] = fminf(mn[1], p.y); mx[1] = fmaxf(mx[1], p.y);
+        mn[2] = fminf(mn[2], p.z); mx[2] = fmaxf(mx[2], p.z);
+    }
+    #pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        #pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            mn[a] = fminf(mn[a], __shfl_xor_sync(0xffffffffu, mn[a], o));
+            mx[a] = fmaxf(mx[a], __shfl_xor_sync(0xffffffffu, mx[a], o));
+        }
+    }
+    if ((threadIdx.x & 31) == 0) {
+        #pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            if (mn[a] <= mx[a]) { atomicMin(&bbox[a], f2ord(mn[a])); atomicMax(&bbox[3 + a], f2ord(mx[a])); }
+        }
+    }
+}
+
+__global__ void grid_setup_kernel(const uint32_t *__restrict__ bbox, int n, float requested_cell, float auto_scale,
+                                  GridParams *__restrict__ gp)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    float mn[3], ex[3];
+    for (int a = 0; a < 3; ++a) {
+        mn[a] = n > 0 ? ord2f(bbox[a]) : 0.f;
+        float mxv = n > 0 ? ord2f(bbox[3 + a]) : 0.f;
+        ex[a] = fmaxf(mxv - mn[a], 1e-6f);
+    }
+    float h = requested_cell;
+    if (!(h > 0.f)) {
+        // surfaces, not volumes: spacing ~ sqrt(area / n); area estimated from the bbox faces
+        float area = ex[0] * ex[1] + ex[1] * ex[2] + ex[0] * ex[2];
+        h = auto_scale * sqrtf(area / (float)(n > 0 ? n : 1));
+    }
+    h = fmaxf(h, 1e-4f);
+    int nx, ny, nz;
+    for (;;) {
+        nx = (int)fminf((float)S3D_GRID_MAX_DIM, floorf(ex[0] / h) + 1.f);
+        ny = (int)fminf((float)S3D_GRID_MAX_DIM, floorf(ex[1] / h) + 1.f);
+        nz = (int)fminf((float)S3D_GRID_MAX_DIM, floorf(ex[2] / h) + 1.f);
+        bool capped = (floorf(ex[0] / h) + 1.f > S3D_GRID_MAX_DIM) || (floorf(ex[1] / h) + 1.f > S3D_GRID_MAX_DIM) ||
+                      (floorf(ex[2] / h) + 1.f > S3D_GRID_MAX_DIM);
+        if (!capped && (double)nx * ny * nz <= (double)S3D_GRID_MAX_CELLS) break;
+        h *= 1.25992105f;
+    }
+    gp->ox = mn[0]; gp->oy = mn[1]; gp->oz = mn[2];
+    gp->cell = h; gp->inv_cell = 1.0f / h;
+    gp->nx = nx; gp->ny = ny; gp->nz = nz; gp->ncells = nx * ny * nz; gp->n_points = n;
+}
+
+__global__ void __launch_bounds__(256) grid_zero_kernel(uint32_t *__restrict__ cell_start, const GridParams *__restrict__ gp)
+{
+    int n = gp->ncells + 1;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) cell_start[i] = 0u;
+}
+
+__global__ void __launch_bounds__(256) grid_count_kernel(const float4 *__restrict__ pts, int n, const GridParams *__restrict__ gpp,
+                                                         uint32_t *__restrict__ cell_start, uint32_t *__restrict__ rank)
+{
+    GridParams gp = *gpp;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        float4 p = pts[i];
+        rank[i] = atomicAdd(&cell_start[grid_cell_index(gp, p.x, p.y, p.z)], 1u);
+    }
+}
+
+__global__ void __launch_bounds__(SCAN_BLOCK) grid_scan_reduce_kernel(const uint32_t *__restrict__ data, const GridParams *__restrict__ gp,
+                                                                      uint32_t *__restrict__ block_sums)
+{
+    __shared__ uint32_t ws[32];
+    int n = gp->ncells + 1;
+    int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+    uint32_t s = 0;
+    if (base + SCAN_ITEMS <= n) {
+        uint4 a = *reinterpret_cast<const uint4 *>(data + base), b = *reinterpret_cast<const uint4 *>(data + base + 4);
+        s = a.x + a.y + a.z + a.w + b.x + b.y + b.z + b.w;
+    } else {
+        for (int k = 0; k < SCAN_ITEMS; ++k) if (base + k < n) s += data[base + k];
+    }
+    s = (uint32_t)warp_sum_i((int)s);
+    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        uint32_t v = (uint32_t)warp_sum_i((int)ws[threadIdx.x]);
+        if (threadIdx.x == 0) block_sums[blockIdx.x] = v;
+    }
+}
+
+__global__ void __launch_bounds__(SCAN_BLOCK) grid_scan_apply_kernel(uint32_t *__restrict__ data, const GridParams *__restrict__ gp,
+                                                                     const uint32_t *__restrict__ block_offsets)
+{
+    __shared__ uint32_t ws[32];
+    int n = gp->ncells + 1;
+    int tile = blockIdx.x * SCAN_TILE;
+    if (tile >= n) return;
+    int base = tile + threadIdx.x * SCAN_ITEMS;
+    uint32_t v[SCAN_ITEMS];
+    bool full = base + SCAN_ITEMS <= n;
+    if (full) {
+        uint4 a = *reinterpret_cast<const uint4 *>(data + base), b = *reinterpret_cast<const uint4 *>(data + base + 4);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
+        for (int k = 0; k < SCAN_ITEMS; ++k) v[k] = (base + k < n) ? data[base + k] : 0u;
+    }
+    uint32_t tot = 0;
+    #pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) { uint32_t t = v[k]; v[k] = tot; tot += t; }
+    uint32_t incl = tot;
+    #pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if ((threadIdx.x & 31) >= o) incl += t;
+    }
+    if ((threadIdx.x & 31) == 31) ws[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        uint32_t w = ws[threadIdx.x], wi = w;
+        #pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, wi, o);
+            if (threadIdx.x >= o) wi += t;
+        }
+        ws[threadIdx.x] = wi - w;
+    }
+    __syncthreads();
+    uint32_t off = block_offsets[blockIdx.x] + ws[threadIdx.x >> 5] + incl - tot;
+    if (full) {
+        uint4 a = make_uint4(v[0] + off, v[1] + off, v[2] + off, v[3] + off);
+        uint4 b = make_uint4(v[4] + off, v[5] + off, v[6] + off, v[7] + off);
+        *reinterpret_cast<uint4 *>(data + base) = a; *reinterpret_cast<uint4 *>(data + base + 4) = b;
+    } else {
+        for (int k = 0; k < SCAN_ITEMS; ++k) if (base + k < n) data[base + k] = v[k] + off;
+    }
+}
+
+__global__ void __launch_bounds__(256) grid_scatter_kernel(const float4 *__restrict__ pts, const float4 *__restrict__ nrm, int n,
+                                                           const GridParams *__restrict__ gpp, const uint32_t *__restrict__ cell_start,
+                                                           const uint32_t *__restrict__ rank, float4 *__restrict__ sorted_pts,
+                                                           float4 *__restrict__ sorted_nrm)
+{
+    GridParams gp = *gpp;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        float4 p = pts[i];
+        uint32_t pos = cell_start[grid_cell_index(gp, p.x, p.y, p.z)] + rank[i];
+        sorted_pts[pos] = make_float4(p.x, p.y, p.z, __int_as_float(i));
+        if (nrm) sorted_nrm[pos] = nrm[i];
+    }
+}
+
+void s3d_grid_free(GridIndex &g)
+{
+    cudaFree(g.d_params); cudaFree(g.d_cell_start); cudaFree(g.d_sorted_pts); cudaFree(g.d_sorted_nrm);
+    cudaFree(g.d_rank); cudaFree(g.d_bbox); cudaFree(g.d_block_sums);
+    g = GridIndex();
+}
+
+static float auto_scale_from_env()
+{
+    const char *e = getenv("S3D_GRID_CELL_SCALE");
+    float v = e ? (float)atof(e) : 0.f;
+    return v > 0.f ? v : 1.5f;
+}
+
+int s3d_grid_build(s3d_ctx *ctx, s3d_cloud *c, float cell)
+{
+    GridIndex &g = c->grid;
+    int n = c->n;
+    size_t np = (size_t)(n > 0 ? n : 1);
+    if (!g.d_params) {
+        S3D_CUDA(ctx, cudaMalloc(&g.d_params, sizeof(GridParams)));
+        S3D_CUDA(ctx, cudaMalloc(&g.d_cell_start, sizeof(uint32_t) * ((size_t)S3D_GRID_MAX_CELLS + 16)));
+        S3D_CUDA(ctx, cudaMalloc(&g.d_sorted_pts, sizeof(float4) * np));
+        S3D_CUDA(ctx, cudaMalloc(&g.d_rank, sizeof(uint32_t) * np));
+        S3D_CUDA(ctx, cudaMalloc(&g.d_bbox, sizeof(uint32_t) * 8));
+        S3D_CUDA(ctx, cudaMalloc(&g.d_block_sums, sizeof(uint32_t) * (S3D_GRID_MAX_CELLS / SCAN_TILE + 8)));
+    }
+    if (c->d_nrm && !g.d_sorted_nrm) S3D_CUDA(ctx, cudaMalloc(&g.d_sorted_nrm, sizeof(float4) * np));
+    cudaStream_t st = ctx->stream;
+    const int wide = ctx->sm_count * 8;
+    const int scan_blocks = S3D_GRID_MAX_CELLS / SCAN_TILE + 1;
+    static const float scale = auto_scale_from_env();
+    bbox_init_kernel<<<1, 32, 0, st>>>(g.d_bbox); S3D_LAUNCHED(ctx);
+    if (n > 0) { bbox_kernel<<<wide, 256, 0, st>>>(c->d_pts, n, g.d_bbox); S3D_LAUNCHED(ctx); }
+    grid_setup_kernel<<<1, 32, 0, st>>>(g.d_bbox, n, cell, scale, g.d_params); S3D_LAUNCHED(ctx);
+    grid_zero_kernel<<<wide, 256, 0, st>>>(g.d_cell_start, g.d_params); S3D_LAUNCHED(ctx);
+    if (n > 0) { grid_count_kernel<<<wide, 256, 0, st>>>(c->d_pts, n, g.d_params, g.d_cell_start, g.d_rank); S3D_LAUNCHED(ctx); }
+    grid_scan_reduce_kernel<<<scan_blocks, SCAN_BLOCK, 0, st>>>(g.d_cell_start, g.d_params, g.d_block_sums); S3D_LAUNCHED(ctx);
+    compact_scan_kernel<<<1, 1024, 0, st>>>(g.d_block_sums, scan_blocks, g.d_block_sums + scan_blocks); S3D_LAUNCHED(ctx);
+    grid_scan_apply_kernel<<<scan_blocks, SCAN_BLOCK, 0, st>>>(g.d_cell_start, g.d_params, g.d_block_sums); S3D_LAUNCHED(ctx);
+    if (n > 0) {
+        grid_scatter_kernel<<<wide, 256, 0, st>>>(c->d_pts, c->d_nrm, n, g.d_params, g.d_cell_start, g.d_rank,
+                                                  g.d_sorted_pts, c->d_nrm ? g.d_sorted_nrm : nullptr);
+        S3D_LAUNCHED(ctx);
+    }
+    g.valid = true; g.has_normals = c->d_nrm != nullptr; g.requested_cell = cell;
+    return S3D_OK;
+}

@@ -1,0 +1,635 @@
+// icp.cu -- the registration hot path: exact nearest-neighbour correspondence + fused
+// point-to-plane (or point-to-point) accumulation + on-device 6x6 / Kabsch solve.
+//
+// Replaces GraphicEnd::multiPnP (reference src/GraphicEnd.cpp:557-659) with the PCL-1.7
+// IterativeClosestPoint semantics restated in oracle/icp_oracle.c:
+//   per iteration   X = T*src ; j(i) = argmin_j |X_i - Q_j|^2 (exact, lowest index on ties)
+//                   reject d^2 > max_corr_dist^2 (and, point-to-plane, targets without a normal)
+//                   A += J^T J, g += J^T r  with J = [X x n ; n], r = n.(Q - X)     (LLS)
+//                   or  sums for Kabsch                                            (SVD)
+//                   T <- dT * T
+// One kernel launch per iteration: every CTA reduces its 29 accumulators (warp shuffles, then
+// double precision across warps), writes one partial row, and the last CTA to finish (atomic
+// ticket) sums the rows in a fixed order, solves in double and publishes the new pose, so the
+// iteration loop never returns to the host.  Two exact search back ends share that epilogue:
+//   S3D_SEARCH_GRID   ring search on the uniform grid of grid.cu (O(1) candidates per query)
+//   S3D_SEARCH_BRUTE  all targets streamed through shared memory by TMA bulk copies
+//                     (cp.async.bulk + mbarrier), 4 sources per thread in registers
+#include <cstdio>
+#include <cstring>
+#include <cmath>
+#include <algorithm>
+#include "context.h"
+#include "common.cuh"
+#include "grid.cuh"
+
+#define ICP_BLOCK 256
+#define GRID_MARGIN 1e-3f     // cell-coordinate rounding allowance (see DESIGN.md "exactness of the ring search")
+
+// ------------------------------------------------------------------------------------------------
+// exact NN on the grid
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float axis_gap(float t, int d)
+{
+    float g = d > 0 ? ((float)d - t) : (d < 0 ? (t - (float)d - 1.0f) : 0.0f);
+    return fmaxf(g - GRID_MARGIN, 0.0f);
+}
+
+__device__ __forceinline__ void scan_range(const float4 *__restrict__ sp, uint32_t s, uint32_t e, float px, float py, float pz,
+                                           float &bd, int &bpos, int &bidx)
+{
+    for (uint32_t k = s; k < e; ++k) {
+        float4 q = __ldg(&sp[k]);
+        float d2 = s3d_dist2(px, py, pz, q.x, q.y, q.z);
+        int qi = __float_as_int(q.w);
+        if (d2 < bd || (d2 == bd && qi < bidx)) { bd = d2; bpos = (int)k; bidx = qi; }
+    }
+}
+
+// Returns position of the nearest target in the sorted array (-1 if the target is empty).
+__device__ __forceinline__ void grid_nn(const GridParams &gp, const uint32_t *__restrict__ cs, const float4 *__restrict__ sp,
+                                        float px, float py, float pz, float &bd, int &bpos)
+{
+    const float fx = grid_fcoord(px, gp.ox, gp.inv_cell), fy = grid_fcoord(py, gp.oy, gp.inv_cell), fz = grid_fcoord(pz, gp.oz, gp.inv_cell);
+    const int cx = grid_clampi(fx, gp.nx), cy = grid_clampi(fy, gp.ny), cz = grid_clampi(fz, gp.nz);
+    const float tx = fx - (float)cx, ty = fy - (float)cy, tz = fz - (float)cz;
+    const float cell2 = gp.cell * gp.cell;
+    bd = INFINITY; bpos = -1;
+    int bidx = 0x7fffffff;
+    if (gp.n_points == 0) return;
+    for (int r = 0;; ++r) {
+        const int z0 = max(cz - r, 0), z1 = min(cz + r, gp.nz - 1);
+        const int y0 = max(cy - r, 0), y1 = min(cy + r, gp.ny - 1);
+        for (int z = z0; z <= z1; ++z) {
+            const float gz = axis_gap(tz, z - cz);
+            const bool zedge = (z - cz == r) || (cz - z == r);
+            for (int y = y0; y <= y1; ++y) {
+                const float gy = axis_gap(ty, y - cy);
+                const float row2 = gy * gy + gz * gz;
+                if (row2 * cell2 >= bd) continue;
+                // cells of this row that can still hold a closer point: |x - tx| < sqrt(bd/cell^2 - row2)
+                int xa = cx - r, xb = cx + r;
+                if (bd < INFINITY) {
+                    float ext = sqrtf(fmaxf(bd / cell2 - row2, 0.f)) + GRID_MARGIN;
+                    xa = max(xa, cx + __float2int_rd(tx - ext));
+                    xb = min(xb, cx + __float2int_rd(tx + ext));
+                }
+                xa = max(xa, 0); xb = min(xb, gp.nx - 1);
+                const int row = (z * gp.ny + y) * gp.nx;
+                const bool edge = zedge || (y - cy == r) || (cy - y == r);
+                if (edge) {
+                    if (xa <= xb) scan_range(sp, cs[row + xa], cs[row + xb + 1], px, py, pz, bd, bpos, bidx);
+                } else {
+                    // interior row of the shell: only the two end cells are new
+                    const int xl = cx - r, xh = cx + r;
+                    if (xl >= xa && xl <= xb) scan_range(sp, cs[row + xl], cs[row + xl + 1], px, py, pz, bd, bpos, bidx);
+                    if (xh >= xa && xh <= xb && xh != xl) scan_range(sp, cs[row + xh], cs[row + xh + 1], px, py, pz, bd, bpos, bidx);
+                }
+            }
+        }
+        // distance from p to the nearest unexplored cell (cube of radius r around the home cell)
+        float gap = INFINITY;
+        bool covered = true;
+        if (cx - r > 0) { gap = fminf(gap, tx + (float)r); covered = false; }
+        if (cx + r < gp.nx - 1) { gap = fminf(gap, (float)(r + 1) - tx); covered = false; }
+        if (cy - r > 0) { gap = fminf(gap, ty + (float)r); covered = false; }
+        if (cy + r < gp.ny - 1) { gap = fminf(gap, (float)(r + 1) - ty); covered = false; }
+        if (cz - r > 0) { gap = fminf(gap, tz + (float)r); covered = false; }
+        if (cz + r < gp.nz - 1) { gap = fminf(gap, (float)(r + 1) - tz); covered = false; }
+        if (covered) break;
+        gap = fmaxf(gap - GRID_MARGIN, 0.f);
+        if (bd < gap * gap * cell2) break;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// brute-force exact NN: target tiles staged in shared memory by TMA bulk copies
+// ------------------------------------------------------------------------------------------------
+#define BF_SRC_PER_THREAD 4
+#define BF_TILE 1024          // target points per tile (16 KiB)
+#define BF_STAGES 4
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t ok = 0;
+    while (!ok) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    }
+}
+
+__global__ void __launch_bounds__(ICP_BLOCK) nn_brute_tma_kernel(const PairDesc *__restrict__ descs, const PairState *__restrict__ states,
+                                                                 int32_t *__restrict__ nn_idx, float *__restrict__ nn_d2, int nn_stride)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float4 *tiles = reinterpret_cast<float4 *>(smem_raw);
+    __shared__ __align__(8) uint64_t full[BF_STAGES];
+    const int pair = blockIdx.y;
+    const PairDesc d = descs[pair];
+    if (states[pair].status != 0) return;
+    const int base = blockIdx.x * (ICP_BLOCK * BF_SRC_PER_THREAD);
+    if (base >= d.n_src) return;
+    float T[12];
+    #pragma unroll
+    for (int k = 0; k < 12; ++k) T[k] = states[pair].Tf[k];
+    float px[BF_SRC_PER_THREAD], py[BF_SRC_PER_THREAD], pz[BF_SRC_PER_THREAD], bd[BF_SRC_PER_THREAD];
+    int bi[BF_SRC_PER_THREAD];
+    #pragma unroll
+    for (int s = 0; s < BF_SRC_PER_THREAD; ++s) {
+        int i = base + s * ICP_BLOCK + threadIdx.x;
+        float4 p = i < d.n_src ? d.src[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+        float3 x = s3d_xform(T, p.x, p.y, p.z);
+        px[s] = x.x; py[s] = x.y; pz[s] = x.z; bd[s] = INFINITY; bi[s] = -1;
+    }
+    const int m = d.n_tgt;
+    const int ntiles = (m + BF_TILE - 1) / BF_TILE;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < BF_STAGES; ++s) mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int t = 0; t < BF_STAGES && t < ntiles; ++t) {
+            uint32_t cnt = (uint32_t)min(BF_TILE, m - t * BF_TILE);
+            mbar_expect_tx(&full[t], cnt * 16u);
+            tma_bulk_g2s(tiles + t * BF_TILE, d.tgt + (size_t)t * BF_TILE, cnt * 16u, &full[t]);
+        }
+    }
+    for (int t = 0; t < ntiles; ++t) {
+        const int stage = t % BF_STAGES;
+        mbar_wait(&full[stage], (uint32_t)((t / BF_STAGES) & 1));
+        const int cnt = min(BF_TILE, m - t * BF_TILE);
+        const float4 *tile = tiles + stage * BF_TILE;
+        const int jbase = t * BF_TILE;
+        #pragma unroll 4
+        for (int k = 0; k < cnt; ++k) {
+            float4 q = tile[k]; // same address for all lanes: shared-memory broadcast
+            #pragma unroll
+            for (int s = 0; s < BF_SRC_PER_THREAD; ++s) {
+                float d2 = s3d_dist2(px[s], py[s], pz[s], q.x, q.y, q.z);
+                if (d2 < bd[s]) { bd[s] = d2; bi[s] = jbase + k; } // ascending j + strict '<' = lowest index on ties
+            }
+        }
+        __syncthreads(); // every thread is done reading this stage
+        if (threadIdx.x == 0 && t + BF_STAGES < ntiles) {
+            int tn = t + BF_STAGES;
+            uint32_t c2 = (uint32_t)min(BF_TILE, m - tn * BF_TILE);
+            mbar_expect_tx(&full[stage], c2 * 16u);
+            tma_bulk_g2s(tiles + stage * BF_TILE, d.tgt + (size_t)tn * BF_TILE, c2 * 16u, &full[stage]);
+        }
+    }
+    #pragma unroll
+    for (int s = 0; s < BF_SRC_PER_THREAD; ++s) {
+        int i = base + s * ICP_BLOCK + threadIdx.x;
+        if (i < d.n_src) { nn_idx[(size_t)pair * nn_stride + i] = bi[s]; nn_d2[(size_t)pair * nn_stride + i] = bd[s]; }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// small dense solvers (double, one thread) -- same algorithms as oracle/icp_oracle.c
+// ------------------------------------------------------------------------------------------------
+__device__ int chol6_solve(const double A[6][6], const double g[6], double pivot_eps, double x[6])
+{
+    double L[6][6];
+    for (int i = 0; i < 6; ++i) for (int j = 0; j < 6; ++j) L[i][j] = 0.0;
+    for (int j = 0; j < 6; ++j) {
+        double s = A[j][j];
+        for (int k = 0; k < j; ++k) s -= L[j][k] * L[j][k];
+        if (!(s > pivot_eps * A[j][j]) || !(A[j][j] > 0.0)) return 1;
+        L[j][j] = sqrt(s);
+        for (int i = j + 1; i < 6; ++i) {
+            double v = A[i][j];
+            for (int k = 0; k < j; ++k) v -= L[i][k] * L[j][k];
+            L[i][j] = v / L[j][j];
+        }
+    }
+    double y[6];
+    for (int i = 0; i < 6; ++i) { double v = g[i]; for (int k = 0; k < i; ++k) v -= L[i][k] * y[k]; y[i] = v / L[i][i]; }
+    for (int i = 5; i >= 0; --i) { double v = y[i]; for (int k = i + 1; k < 6; ++k) v -= L[k][i] * x[k]; x[i] = v / L[i][i]; }
+    return 0;
+}
+
+__device__ void euler_to_T(const double x[6], double D[12])
+{
+    double sa, ca, sb, cb, sg, cg;
+    sincos(x[0], &sa, &ca); sincos(x[1], &sb, &cb); sincos(x[2], &sg, &cg);
+    D[0] = cg * cb; D[1] = -sg * ca + cg * sb * sa; D[2] = sg * sa + cg * sb * ca;  D[3] = x[3];
+    D[4] = sg * cb; D[5] = cg * ca + sg * sb * sa;  D[6] = -cg * sa + sg * sb * ca; D[7] = x[4];
+    D[8] = -sb;     D[9] = cb * sa;                 D[10] = cb * ca;                D[11] = x[5];
+}
+
+__device__ void kabsch_rotation(double H[3][3], double R[3][3])
+{
+    double HtH[3][3], V[3][3], w[3];
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) {
+        double s = 0; for (int k = 0; k < 3; ++k) s += H[k][i] * H[k][j];
+        HtH[i][j] = s;
+    }
+    s3d_jacobi3(HtH, V, w);
+    int ord[3] = {0, 1, 2};
+    for (int a = 0; a < 2; ++a) for (int b = a + 1; b < 3; ++b) if (w[ord[b]] > w[ord[a]]) { int t = ord[a]; ord[a] = ord[b]; ord[b] = t; }
+    double Vs[3][3], U[3][3];
+    for (int c = 0; c < 3; ++c) for (int r = 0; r < 3; ++r) Vs[r][c] = V[r][ord[c]];
+    for (int c = 0; c < 2; ++c) {
+        double u[3] = {0, 0, 0};
+        for (int r = 0; r < 3; ++r) for (int k = 0; k < 3; ++k) u[r] += H[r][k] * Vs[k][c];
+        double n = sqrt(u[0] * u[0] + u[1] * u[1] + u[2] * u[2]);
+        if (n < 1e-300) n = 1;
+        for (int r = 0; r < 3; ++r) U[r][c] = u[r] / n;
+    }
+    {
+        double d = U[0][0] * U[0][1] + U[1][0] * U[1][1] + U[2][0] * U[2][1];
+        for (int r = 0; r < 3; ++r) U[r][1] -= d * U[r][0];
+        double n = sqrt(U[0][1] * U[0][1] + U[1][1] * U[1][1] + U[2][1] * U[2][1]);
+        if (n < 1e-300) n = 1;
+        for (int r = 0; r < 3; ++r) U[r][1] /= n;
+    }
+    U[0][2] = U[1][0] * U[2][1] - U[2][0] * U[1][1];
+    U[1][2] = U[2][0] * U[0][1] - U[0][0] * U[2][1];
+    U[2][2] = U[0][0] * U[1][1] - U[1][0] * U[0][1];
+    Vs[0][2] = Vs[1][0] * Vs[2][1] - Vs[2][0] * Vs[1][1];
+    Vs[1][2] = Vs[2][0] * Vs[0][1] - Vs[0][0] * Vs[2][1];
+    Vs[2][2] = Vs[0][0] * Vs[1][1] - Vs[1][0] * Vs[0][1];
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) {
+        double s = 0; for (int k = 0; k < 3; ++k) s += Vs[i][k] * U[j][k];
+        R[i][j] = s;
+    }
+}
+
+// consumes the summed accumulators of one pair, updates its state (runs in one thread)
+template <int EST>
+__device__ void solve_and_update(const double *acc, PairState *st, int min_corr, double pivot_eps)
+{
+    const double cnt_d = acc[S3D_ACC_COUNT];
+    const int cnt = (int)(cnt_d + 0.5);
+    st->inliers = cnt;
+    st->fitness = cnt > 0 ? acc[S3D_ACC_SUMD2] / cnt_d : 0.0;
+    if (cnt < min_corr) { st->status = S3D_PAIR_FEW_CORRESPONDENCES; return; }
+    double D[12];
+    if (EST == S3D_ESTIMATOR_POINT_TO_PLANE) {
+        double A[6][6], g[6], x[6];
+        int k = 0;
+        for (int a = 0; a < 6; ++a) for (int b = a; b < 6; ++b) { A[a][b] = acc[k]; A[b][a] = acc[k]; ++k; }
+        for (int a = 0; a < 6; ++a) g[a] = acc[21 + a];
+        if (chol6_solve(A, g, pivot_eps, x)) { st->status = S3D_PAIR_DEGENERATE; return; }
+        euler_to_T(x, D);
+    } else {
+        double H[3][3], R[3][3], pb[3], qb[3];
+        for (int a = 0; a < 3; ++a) { pb[a] = acc[a] / cnt_d; qb[a] = acc[3 + a] / cnt_d; }
+        for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) H[a][b] = acc[6 + 3 * a + b] - cnt_d * pb[a] * qb[b];
+        kabsch_rotation(H, R);
+        for (int a = 0; a < 3; ++a) {
+            for (int b = 0; b < 3; ++b) D[4 * a + b] = R[a][b];
+            D[4 * a + 3] = qb[a] - (R[a][0] * pb[0] + R[a][1] * pb[1] + R[a][2] * pb[2]);
+        }
+    }
+    bool finite = true;
+    for (int k = 0; k < 12; ++k) finite = finite && isfinite(D[k]);
+    if (!finite) { st->status = S3D_PAIR_NONFINITE; return; }
+    double T[12], O[12];
+    for (int k = 0; k < 12; ++k) T[k] = st->T[k];
+    for (int r = 0; r < 3; ++r) {
+        for (int c = 0; c < 3; ++c) O[4 * r + c] = D[4 * r] * T[c] + D[4 * r + 1] * T[4 + c] + D[4 * r + 2] * T[8 + c];
+        O[4 * r + 3] = D[4 * r] * T[3] + D[4 * r + 1] * T[7] + D[4 * r + 2] * T[11] + D[4 * r + 3];
+    }
+    for (int k = 0; k < 12; ++k) { st->T[k] = O[k]; st->Tf[k] = (float)O[k]; }
+    st->iterations += 1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// the fused iteration kernel
+// ------------------------------------------------------------------------------------------------
+template <int EST>
+__device__ __forceinline__ void accumulate(float *acc, float px, float py, float pz, float4 q, float4 nv, float d2)
+{
+    if (EST == S3D_ESTIMATOR_POINT_TO_PLANE) {
+        float J[6];
+        J[0] = __fmaf_rn(nv.z, py, -__fmul_rn(nv.y, pz));
+        J[1] = __fmaf_rn(nv.x, pz, -__fmul_rn(nv.z, px));
+        J[2] = __fmaf_rn(nv.y, px, -__fmul_rn(nv.x, py));
+        J[3] = nv.x; J[4] = nv.y; J[5] = nv.z;
+        float ex = __fsub_rn(q.x, px), ey = __fsub_rn(q.y, py), ez = __fsub_rn(q.z, pz);
+        float r = __fmaf_rn(nv.z, ez, __fmaf_rn(nv.y, ey, __fmul_rn(nv.x, ex)));
+        int k = 0;
+        #pragma unroll
+        for (int a = 0; a < 6; ++a) {
+            #pragma unroll
+            for (int b = a; b < 6; ++b) { acc[k] = fmaf(J[a], J[b], acc[k]); ++k; }
+        }
+        #pragma unroll
+        for (int a = 0; a < 6; ++a) acc[21 + a] = fmaf(J[a], r, acc[21 + a]);
+    } else {
+        float p[3] = {px, py, pz}, qq[3] = {q.x, q.y, q.z};
+        #pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            acc[a] += p[a]; acc[3 + a] += qq[a];
+            #pragma unroll
+            for (int b = 0; b < 3; ++b) acc[6 + 3 * a + b] = fmaf(p[a], qq[b], acc[6 + 3 * a + b]);
+        }
+    }
+    acc[S3D_ACC_SUMD2] += d2;
+    acc[S3D_ACC_COUNT] += 1.0f;
+}
+
+template <int EST, int SEARCH>
+__global__ void __launch_bounds__(ICP_BLOCK, 2) icp_iter_kernel(const PairDesc *__restrict__ descs, PairState *__restrict__ states,
+                                                             double *__restrict__ partials, const int32_t *__restrict__ nn_idx,
+                                                             const float *__restrict__ nn_d2, int nn_stride, float max_d2,
+                                                             int min_corr, double pivot_eps, int32_t *__restrict__ nn_out)
+{
+    __shared__ double wsum[ICP_BLOCK / 32][S3D_NACC];
+    __shared__ double tail[8][S3D_NACC];
+    __shared__ bool is_last;
+    const int pair = blockIdx.y;
+    PairState *st = states + pair;
+    if (st->status != 0) return;   // failed pairs stay failed; every CTA of the pair takes this exit together
+    const PairDesc d = descs[pair];
+    float T[12];
+    #pragma unroll
+    for (int k = 0; k < 12; ++k) T[k] = st->Tf[k];
+    GridParams gp;
+    if (SEARCH == S3D_SEARCH_GRID) gp = *d.grid;
+
+    float acc[29];
+    #pragma unroll
+    for (int k = 0; k < 29; ++k) acc[k] = 0.f;
+
+    for (int i = blockIdx.x * ICP_BLOCK + threadIdx.x; i < d.n_src; i += gridDim.x * ICP_BLOCK) {
+        const float4 p = d.src[i];
+        const float3 x = s3d_xform(T, p.x, p.y, p.z);
+        float bd; int j = -1; float4 q, nv = make_float4(0.f, 0.f, 0.f, 1.f);
+        if (SEARCH == S3D_SEARCH_GRID) {
+            int bpos;
+            grid_nn(gp, d.cell_start, d.sorted_pts, x.x, x.y, x.z, bd, bpos);
+            if (bpos >= 0) {
+                q = __ldg(&d.sorted_pts[bpos]);
+                j = __float_as_int(q.w);
+                if (EST == S3D_ESTIMATOR_POINT_TO_PLANE) nv = __ldg(&d.sorted_nrm[bpos]);
+            }
+        } else {
+            j = nn_idx[(size_t)pair * nn_stride + i];
+            bd = nn_d2[(size_t)pair * nn_stride + i];
+            if (j >= 0) {
+                q = __ldg(&d.tgt[j]);
+                if (EST == S3D_ESTIMATOR_POINT_TO_PLANE) nv = __ldg(&d.tgt_nrm[j]);
+            }
+        }
+        bool ok = (j >= 0) && (bd <= max_d2) && (nv.w != 0.f);
+        if (ok) accumulate<EST>(acc, x.x, x.y, x.z, q, nv, bd);
+        if (nn_out) nn_out[i] = ok ? j : -1;
+    }
+
+    // CTA reduction: shuffles inside the warp (float), double across warps
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    #pragma unroll
+    for (int k = 0; k < 29; ++k) {
+        float v = warp_sum(acc[k]);
+        if (lane == 0) wsum[warp][k] = (double)v;
+    }
+    __syncthreads();
+    double *row = partials + ((size_t)pair * gridDim.x + blockIdx.x) * S3D_NACC;
+    if (threadIdx.x < 29) {
+        double s = 0.0;
+        #pragma unroll
+        for (int w = 0; w < ICP_BLOCK / 32; ++w) s += wsum[w][threadIdx.x];
+        __stcg(&row[threadIdx.x], s);
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned t = atomicAdd(&st->ticket, 1u);
+        is_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    // last CTA of the pair: fixed-order sum of all partial rows, then solve
+    {
+        const int slot = threadIdx.x & 31, part = threadIdx.x >> 5; // 8 parts
+        double s = 0.0;
+        if (slot < 29) {
+            const double *base = partials + (size_t)pair * gridDim.x * S3D_NACC;
+            for (int c = part; c < (int)gridDim.x; c += 8) s += __ldcg(&base[(size_t)c * S3D_NACC + slot]);
+        }
+        tail[part][slot] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        double s = 0.0;
+        #pragma unroll
+        for (int p8 = 0; p8 < 8; ++p8) s += tail[p8][threadIdx.x];
+        tail[0][threadIdx.x] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        solve_and_update<EST>(tail[0], st, min_corr, pivot_eps);
+        st->ticket = 0u;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+extern "C" void s3d_icp_params_default(s3d_icp_params *p)
+{
+    if (!p) return;
+    memset(p, 0, sizeof(*p));
+    p->max_iterations = 10; p->max_corr_dist = 0.f; p->estimator = S3D_ESTIMATOR_POINT_TO_PLANE;
+    p->search = S3D_SEARCH_GRID; p->grid_cell = 0.f; p->min_correspondences = 3; p->pivot_eps = 1e-9; p->reuse_index = 1;
+}
+
+static double pose_norm(const double *T)
+{
+    // |min(theta, 2pi-theta)| + 0.9 |t|   (reference src/GraphicEnd.cpp:618)
+    double sx = T[9] - T[6], sy = T[2] - T[8], sz = T[4] - T[1];
+    double s = 0.5 * sqrt(sx * sx + sy * sy + sz * sz);
+    double c = 0.5 * (T[0] + T[5] + T[10] - 1.0);
+    double theta = atan2(s, c), alt = 2.0 * M_PI - theta;
+    double th = fabs(theta < alt ? theta : alt);
+    return th + 0.9 * sqrt(T[3] * T[3] + T[7] * T[7] + T[11] * T[11]);
+}
+
+static int ensure_batch(s3d_ctx *ctx, int n_pairs, int ctas)
+{
+    if (n_pairs > ctx->cap_pairs) {
+        cudaFree(ctx->d_desc); cudaFreeHost(ctx->h_desc); cudaFree(ctx->d_state); cudaFreeHost(ctx->h_state);
+        ctx->d_desc = nullptr; ctx->h_desc = nullptr; ctx->d_state = nullptr; ctx->h_state = nullptr; ctx->cap_pairs = 0;
+        int cap = std::max(n_pairs, 64);
+        S3D_CUDA(ctx, cudaMalloc(&ctx->d_desc, sizeof(PairDesc) * cap));
+        S3D_CUDA(ctx, cudaMallocHost(&ctx->h_desc, sizeof(PairDesc) * cap));
+        S3D_CUDA(ctx, cudaMalloc(&ctx->d_state, sizeof(PairState) * cap));
+        S3D_CUDA(ctx, cudaMallocHost(&ctx->h_state, sizeof(PairState) * cap));
+        ctx->cap_pairs = cap;
+        cudaFree(ctx->d_partials); ctx->d_partials = nullptr; ctx->cap_ctas = 0;
+    }
+    if ((size_t)ctx->cap_pairs * ctas > (size_t)ctx->cap_ctas) {
+        cudaFree(ctx->d_partials); ctx->d_partials = nullptr;
+        size_t rows = (size_t)ctx->cap_pairs * ctas;
+        S3D_CUDA(ctx, cudaMalloc(&ctx->d_partials, sizeof(double) * S3D_NACC * rows));
+        ctx->cap_ctas = (int)std::min<size_t>(rows, 0x7fffffff);
+    }
+    return S3D_OK;
+}
+
+template <int EST, int SEARCH>
+static void launch_iter(s3d_ctx *ctx, dim3 grid, int nn_stride, float max_d2, int min_corr, double pivot_eps, int32_t *nn_out)
+{
+    icp_iter_kernel<EST, SEARCH><<<grid, ICP_BLOCK, 0, ctx->stream>>>(ctx->d_desc, ctx->d_state, ctx->d_partials, ctx->d_nn_idx,
+                                                                      ctx->d_nn_d2, nn_stride, max_d2, min_corr, pivot_eps, nn_out);
+}
+
+extern "C" int s3d_register_batch(s3d_ctx *ctx, const s3d_cloud *const *src, const s3d_cloud *const *tgt,
+                                  const double *guess, int n_pairs, const s3d_icp_params *prm, s3d_result *out)
+{
+    if (!ctx || !src || !tgt || !prm || !out || n_pairs <= 0) return s3d_fail(ctx, S3D_E_ARG, "s3d_register_batch: bad argument");
+    if (prm->estimator != S3D_ESTIMATOR_POINT_TO_PLANE && prm->estimator != S3D_ESTIMATOR_SVD) return s3d_fail(ctx, S3D_E_ARG, "unknown estimator");
+    if (prm->search != S3D_SEARCH_GRID && prm->search != S3D_SEARCH_BRUTE) return s3d_fail(ctx, S3D_E_ARG, "unknown search mode");
+    if (prm->max_iterations < 0) return s3d_fail(ctx, S3D_E_ARG, "max_iterations < 0");
+    cudaSetDevice(ctx->device);
+    const bool plane = prm->estimator == S3D_ESTIMATOR_POINT_TO_PLANE;
+    const bool use_grid = prm->search == S3D_SEARCH_GRID;
+    int n_max = 0;
+    for (int i = 0; i < n_pairs; ++i) {
+        if (!src[i] || !tgt[i]) return s3d_fail(ctx, S3D_E_ARG, "null cloud in batch");
+        if (plane && !tgt[i]->d_nrm) return s3d_fail(ctx, S3D_E_STATE, "point-to-plane needs target normals: call s3d_segment_planes or s3d_cloud_set_normals on the target first");
+        n_max = std::max(n_max, src[i]->n);
+    }
+    const int64_t launches0 = ctx->launches;
+    // launch geometry: ~4 sources per thread for a lone pair, more per thread when the batch fills the GPU
+    int ctas = std::max(1, std::min((n_max + ICP_BLOCK * 4 - 1) / (ICP_BLOCK * 4), (ctx->sm_count * 16 + n_pairs - 1) / n_pairs));
+    int rc = ensure_batch(ctx, n_pairs, ctas);
+    if (rc) return rc;
+
+    cudaEventRecord(ctx->ev[0], ctx->stream);
+    bool built = false;
+    if (use_grid) {
+        for (int i = 0; i < n_pairs; ++i) {
+            s3d_cloud *t = const_cast<s3d_cloud *>(tgt[i]);
+            bool seen = false;
+            for (int k = 0; k < i && !seen; ++k) seen = (tgt[k] == tgt[i]);
+            if (seen) continue;
+            bool stale = !t->grid.valid || t->grid.requested_cell != prm->grid_cell || (plane && !t->grid.has_normals) || !prm->reuse_index;
+            if (stale) { rc = s3d_grid_build(ctx, t, prm->grid_cell); if (rc) return rc; built = true; }
+        }
+    }
+    cudaEventRecord(ctx->ev[1], ctx->stream);
+
+    if (!use_grid) {
+        size_t need = (size_t)n_pairs * n_max;
+        if (need > (size_t)ctx->cap_nn) {
+            cudaFree(ctx->d_nn_idx); cudaFree(ctx->d_nn_d2); ctx->d_nn_idx = nullptr; ctx->d_nn_d2 = nullptr;
+            S3D_CUDA(ctx, cudaMalloc(&ctx->d_nn_idx, sizeof(int32_t) * std::max<size_t>(need, 1)));
+            S3D_CUDA(ctx, cudaMalloc(&ctx->d_nn_d2, sizeof(float) * std::max<size_t>(need, 1)));
+            ctx->cap_nn = (int)need;
+        }
+    }
+    int32_t *nn_out = nullptr;
+    if (n_pairs == 1) {
+        if (src[0]->n > ctx->cap_last_nn) {
+            cudaFree(ctx->d_last_nn); ctx->d_last_nn = nullptr;
+            S3D_CUDA(ctx, cudaMalloc(&ctx->d_last_nn, sizeof(int32_t) * (size_t)std::max(src[0]->n, 1)));
+            ctx->cap_last_nn = src[0]->n;
+        }
+        nn_out = ctx->d_last_nn; ctx->last_nn_n = src[0]->n;
+    } else ctx->last_nn_n = 0;
+
+    for (int i = 0; i < n_pairs; ++i) {
+        PairDesc &d = ctx->h_desc[i];
+        d.src = src[i]->d_pts; d.n_src = src[i]->n;
+        d.tgt = tgt[i]->d_pts; d.tgt_nrm = tgt[i]->d_nrm; d.n_tgt = tgt[i]->n;
+        d.sorted_pts = tgt[i]->grid.d_sorted_pts; d.sorted_nrm = tgt[i]->grid.d_sorted_nrm;
+        d.cell_start = tgt[i]->grid.d_cell_start; d.grid = tgt[i]->grid.d_params;
+        PairState &s = ctx->h_state[i];
+        memset(&s, 0, sizeof(s));
+        static const double I12[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
+        const double *g = guess ? guess + 16 * (size_t)i : I12;
+        for (int k = 0; k < 12; ++k) { s.T[k] = g[k]; s.Tf[k] = (float)g[k]; }
+    }
+    S3D_CUDA(ctx, cudaMemcpyAsync(ctx->d_desc, ctx->h_desc, sizeof(PairDesc) * n_pairs, cudaMemcpyHostToDevice, ctx->stream));
+    S3D_CUDA(ctx, cudaMemcpyAsync(ctx->d_state, ctx->h_state, sizeof(PairState) * n_pairs, cudaMemcpyHostToDevice, ctx->stream));
+
+    const float max_d2 = prm->max_corr_dist > 0.f ? prm->max_corr_dist * prm->max_corr_dist : INFINITY;
+    const int min_corr = prm->min_correspondences > 0 ? prm->min_correspondences : 3;
+    const double pivot_eps = prm->pivot_eps > 0 ? prm->pivot_eps : 1e-9;
+    const dim3 grid(ctas, n_pairs);
+    int iter_launches = 0;
+    for (int it = 0; it < prm->max_iterations; ++it) {
+        int32_t *no = (it == prm->max_iterations - 1) ? nn_out : nullptr;
+        if (!use_grid) {
+            dim3 g2((n_max + ICP_BLOCK * BF_SRC_PER_THREAD - 1) / (ICP_BLOCK * BF_SRC_PER_THREAD), n_pairs);
+            size_t smem = sizeof(float4) * BF_TILE * BF_STAGES;
+            static bool attr_done = false;
+            if (!attr_done) { cudaFuncSetAttribute(nn_brute_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_done = true; }
+            nn_brute_tma_kernel<<<g2, ICP_BLOCK, smem, ctx->stream>>>(ctx->d_desc, ctx->d_state, ctx->d_nn_idx, ctx->d_nn_d2, n_max);
+            S3D_LAUNCHED(ctx); ++iter_launches;
+            if (plane) launch_iter<S3D_ESTIMATOR_POINT_TO_PLANE, S3D_SEARCH_BRUTE>(ctx, grid, n_max, max_d2, min_corr, pivot_eps, no);
+            else launch_iter<S3D_ESTIMATOR_SVD, S3D_SEARCH_BRUTE>(ctx, grid, n_max, max_d2, min_corr, pivot_eps, no);
+        } else {
+            if (plane) launch_iter<S3D_ESTIMATOR_POINT_TO_PLANE, S3D_SEARCH_GRID>(ctx, grid, n_max, max_d2, min_corr, pivot_eps, no);
+            else launch_iter<S3D_ESTIMATOR_SVD, S3D_SEARCH_GRID>(ctx, grid, n_max, max_d2, min_corr, pivot_eps, no);
+        }
+        S3D_LAUNCHED(ctx); ++iter_launches;
+    }
+    cudaEventRecord(ctx->ev[2], ctx->stream);
+    S3D_CUDA(ctx, cudaMemcpyAsync(ctx->h_state, ctx->d_state, sizeof(PairState) * n_pairs, cudaMemcpyDeviceToHost, ctx->stream));
+    S3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+
+    for (int i = 0; i < n_pairs; ++i) {
+        const PairState &s = ctx->h_state[i];
+        s3d_result &r = out[i];
+        memset(&r, 0, sizeof(r));
+        r.inliers = s.inliers; r.iterations = s.iterations; r.status = s.status; r.fitness = s.fitness;
+        if (s.status == S3D_PAIR_OK) {
+            memcpy(r.T, s.T, sizeof(double) * 12);
+            r.T[15] = 1.0;
+            r.norm = pose_norm(r.T);
+        } else {
+            r.T[0] = r.T[5] = r.T[10] = r.T[15] = 1.0; // the reference's failure convention: T == Identity
+        }
+    }
+    float ms_index = 0.f, ms_iter = 0.f;
+    cudaEventElapsedTime(&ms_index, ctx->ev[0], ctx->ev[1]);
+    cudaEventElapsedTime(&ms_iter, ctx->ev[1], ctx->ev[2]);
+    ctx->timing.index_ms = built ? ms_index : 0.f;
+    ctx->timing.iterate_ms = ms_iter;
+    ctx->timing.iter_launches = iter_launches;
+    ctx->timing.total_launches = (int)(ctx->launches - launches0);
+    return S3D_OK;
+}
+
+extern "C" int s3d_register_pair(s3d_ctx *ctx, const s3d_cloud *src, const s3d_cloud *tgt, const double *guess,
+                                 const s3d_icp_params *params, s3d_result *result_out)
+{
+    const s3d_cloud *s[1] = {src}, *t[1] = {tgt};
+    return s3d_register_batch(ctx, s, t, guess, 1, params, result_out);
+}
+
+extern "C" int s3d_last_correspondences(s3d_ctx *ctx, int32_t *idx_out, int n)
+{
+    if (!ctx || !idx_out || n != ctx->last_nn_n || n <= 0) return s3d_fail(ctx, S3D_E_ARG, "s3d_last_correspondences: size mismatch or no single-pair call before");
+    cudaSetDevice(ctx->device);
+    S3D_CUDA(ctx, cudaMemcpyAsync(idx_out, ctx->d_last_nn, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    S3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return S3D_OK;
+}
+
+extern "C" int s3d_last_timing(const s3d_ctx *ctx, s3d_timing *out)
+{
+    if (!ctx || !out) return S3D_E_ARG;
+    *out = ctx->timing;
+    return S3D_OK;
+}

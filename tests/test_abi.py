@@ -1,0 +1,76 @@
+"""CPU tests of the drop-in boundary: the C-ABI library loads, exports every symbol include/slam3d_b200.h
+declares, and the ctypes struct mirrors have the C layout.  No compute call is made (no GPU here)."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import pytest
+
+import slam3d_gx_b200 as s3d
+from slam3d_gx_b200 import _abi, binding
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "slam3d_b200.h")
+
+
+def _declared_symbols():
+    txt = open(HEADER).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(s3d_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = s3d.load_library()
+    declared = _declared_symbols()
+    assert len(declared) >= 25
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/slam3d_b200.h but not exported"
+    assert sorted(binding.EXPORTS) == declared
+    assert lib.s3d_abi_version() == 1
+
+
+def test_struct_layouts_match_c(tmp_path):
+    src = tmp_path / "sz.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "slam3d_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n",'
+                   'sizeof(s3d_icp_params),sizeof(s3d_result),sizeof(s3d_plane_params),sizeof(s3d_plane),sizeof(s3d_camera),'
+                   'sizeof(s3d_timing),offsetof(s3d_result,inliers),offsetof(s3d_icp_params,pivot_eps));return 0;}\n')
+    exe = tmp_path / "sz"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True,
+                   env={**os.environ, "CC": "gcc"})
+    got = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    want = [C.sizeof(_abi.IcpParams), C.sizeof(_abi.Result), C.sizeof(_abi.PlaneParams), C.sizeof(_abi.Plane),
+            C.sizeof(_abi.CameraC), C.sizeof(_abi.Timing), _abi.Result.inliers.offset, _abi.IcpParams.pivot_eps.offset]
+    assert got == want
+
+
+def test_defaults_come_from_the_library():
+    lib = s3d.load_library()
+    p = _abi.IcpParams()
+    lib.s3d_icp_params_default(C.byref(p))
+    assert (p.max_iterations, p.estimator, p.search, p.min_correspondences, p.reuse_index) == (10, 0, 0, 3, 1)
+    q = _abi.PlaneParams()
+    lib.s3d_plane_params_default(C.byref(q))
+    # reference parameters.yaml: distance_threshold 0.08, plane_percent 0.2, max_planes 3; PCL: 50 iterations, p=0.99
+    assert abs(q.distance_threshold - 0.08) < 1e-7 and abs(q.plane_percent - 0.2) < 1e-7
+    assert (q.max_planes, q.max_iterations) == (3, 50)
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(s3d.S3DError):
+        s3d.Context(0)
+
+
+def test_product_package_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "slam3d_gx_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp", ".hpp")):
+                txt = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert "oracle/" not in txt.replace("oracle/oracle_common.h", "").replace("oracle/icp_oracle.c", "").replace("oracle/plane_oracle.c", "") \
+                    or f.endswith((".cu", ".cuh", ".h")), f
+                assert "import oracle" not in txt and "from oracle" not in txt, f"{f} imports the oracle"
+                assert "liboracle" not in txt, f"{f} links the oracle"

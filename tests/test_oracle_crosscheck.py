@@ -1,0 +1,165 @@
+"""CPU tests: the C oracle against an independent scipy/numpy float64 implementation (tests/ref_numpy.py)
+and against analytic ground truth.  The reference ships no golden vectors for this path, so
+this cross-check is what pins the oracle ("parity unpinned" by the reference itself)."""
+import numpy as np
+import pytest
+from scipy.spatial import cKDTree
+
+from slam3d_gx_b200 import synth, _abi
+from oracle import oracle
+from ref_numpy import icp_numpy
+from conftest import pose_close
+
+
+def test_nn_kdtree_equals_brute_and_scipy(small_pair):
+    src, tgt = small_pair["src"], small_pair["tgt"]
+    T = small_pair["T_gt"]
+    i_kd, d_kd = oracle.nn(src, tgt, T)
+    i_bf, d_bf = oracle.nn(src[:3000], tgt, T, brute=True)
+    assert np.array_equal(i_kd[:3000], i_bf) and np.array_equal(d_kd[:3000], d_bf)
+    X = src[:, :3].astype(np.float64) @ T[:3, :3].T + T[:3, 3]
+    d_sp, i_sp = cKDTree(tgt[:, :3].astype(np.float64)).query(X)
+    assert (i_sp == i_kd).mean() > 0.999          # float32 vs float64 near-ties may differ
+    assert np.allclose(d_sp ** 2, d_kd, rtol=1e-3, atol=1e-9)
+
+
+def test_nn_duplicate_points_lowest_index():
+    tgt = np.zeros((10, 4), np.float32)
+    tgt[:, 0] = [0, 1, 1, 2, 2, 2, 3, 3, 3, 3]
+    src = np.array([[1, 0, 0, 1], [2.1, 0, 0, 1], [3, 0, 0, 1], [1.5, 0, 0, 1]], np.float32)
+    idx, d2 = oracle.nn(src, tgt)
+    assert idx.tolist() == [1, 3, 6, 1]
+
+
+@pytest.mark.parametrize("est,name,tol", [(_abi.ESTIMATOR_POINT_TO_PLANE, "plane", 1e-6), (_abi.ESTIMATOR_SVD, "svd", 2e-5)])
+def test_icp_matches_numpy_reference(small_pair, est, name, tol):
+    p = small_pair
+    r = oracle.icp(p["src"], p["tgt"], p["tgt_normals"], params=_abi.icp_params(10, estimator=est))
+    rn = icp_numpy(p["src"], p["tgt"], p["tgt_normals"], 10, name)
+    assert r["status"] == _abi.PAIR_OK and r["iterations"] == 10
+    assert r["inliers"] == rn["inliers"]
+    ok, err = pose_close(r["T"], rn["T"], tol, tol)
+    assert ok, err
+    assert abs(r["fitness"] - rn["fitness"]) < 1e-6 * max(1.0, rn["fitness"]) + 1e-9
+
+
+def test_icp_with_guess_and_gate(small_pair):
+    p = small_pair
+    prm = _abi.icp_params(5, max_corr_dist=0.05)
+    r = oracle.icp(p["src"], p["tgt"], p["tgt_normals"], guess=p["T_gt"], params=prm)
+    rn = icp_numpy(p["src"], p["tgt"], p["tgt_normals"], 5, "plane", max_corr_dist=0.05, guess=p["T_gt"])
+    ok, err = pose_close(r["T"], rn["T"], 1e-6, 1e-6)
+    assert ok, err
+    assert r["inliers"] == rn["inliers"]
+
+
+def test_icp_converges_to_ground_truth(small_pair):
+    p = small_pair
+    r = oracle.icp(p["src"], p["tgt"], p["tgt_normals"], params=_abi.icp_params(30))
+    ok, err = pose_close(r["T"], p["T_gt"], 2e-3, 5e-3)   # accuracy vs analytic GT (noise + discretisation limited)
+    assert ok, err
+    # norm formula of reference src/GraphicEnd.cpp:618
+    ang, _ = synth.pose_error(np.eye(4), r["T"])
+    assert abs(r["norm"] - (ang + 0.9 * np.linalg.norm(r["T"][:3, 3]))) < 1e-12
+
+
+def test_icp_degenerate_single_plane_returns_identity(small_cam):
+    p = synth.make_pair(3, cam=small_cam, scene="S0")
+    r = oracle.icp(p["src"], p["tgt"], p["tgt_normals"], params=_abi.icp_params(10))
+    assert r["status"] == _abi.PAIR_DEGENERATE
+    assert np.array_equal(r["T"], np.eye(4))          # reference failure convention (GraphicEnd.cpp:585-600)
+
+
+def test_icp_too_few_correspondences(small_pair):
+    p = small_pair
+    r = oracle.icp(p["src"], p["tgt"], p["tgt_normals"], params=_abi.icp_params(10, max_corr_dist=1e-7))
+    assert r["status"] == _abi.PAIR_FEW and np.array_equal(r["T"], np.eye(4))
+
+
+def test_icp_threads_do_not_change_result(small_pair):
+    p = small_pair
+    a = oracle.icp(p["src"], p["tgt"], p["tgt_normals"], params=_abi.icp_params(5), nthreads=1)
+    b = oracle.icp(p["src"], p["tgt"], p["tgt_normals"], params=_abi.icp_params(5), nthreads=4)
+    assert np.array_equal(a["T"], b["T"])
+
+
+def test_plane_segmentation_recovers_scene_planes(small_cam):
+    p = synth.make_pair(1, cam=small_cam)
+    seg = oracle.segment_planes(p["tgt"], _abi.plane_params())
+    assert len(seg["planes"]) == 3
+    # analytic planes in the target camera frame: n_c = R^T n_w, d_c = n_w.o + d_w
+    C2 = synth.base_pose() @ np.linalg.inv(p["T_gt"])
+    N, d = synth.scene_planes("S1")
+    truth = []
+    for n_w, d_w in zip(N, d):
+        n_c = C2[:3, :3].T @ n_w
+        d_c = n_w @ C2[:3, 3] + d_w
+        if d_c < 0:
+            n_c, d_c = -n_c, -d_c
+        truth.append(np.r_[n_c, d_c])
+    for pl in seg["planes"]:
+        best = min(np.abs(pl["coef"] - t).max() for t in truth)
+        assert best < 2.5e-2, (pl["coef"], truth)   # PCA refit at tau=0.08 m is biased by the neighbouring planes within 8 cm
+        assert pl["coef"][3] >= 0                       # sign convention GraphicEnd.cpp:383-387
+    lab = seg["labels"]
+    assert (lab >= 0).mean() > 0.99
+    assert sum(pl["inliers"] for pl in seg["planes"]) == int((lab >= 0).sum())
+    # every labelled point satisfies its plane within the threshold and carries that plane's normal
+    for k, pl in enumerate(seg["planes"]):
+        pts = p["tgt"][lab == k, :3]
+        assert np.all(np.abs(pts @ pl["coef"][:3] + pl["coef"][3]) < 0.08 + 1e-6)
+        assert np.allclose(seg["normals"][lab == k, :3], pl["coef"][:3])
+
+
+def test_plane_segmentation_edge_cases():
+    prm = _abi.plane_params()
+    assert oracle.segment_planes(np.zeros((0, 4), np.float32), prm)["planes"] == []
+    two = np.array([[0, 0, 1, 1], [1, 0, 1, 1]], np.float32)
+    assert oracle.segment_planes(two, prm)["planes"] == []
+    # a single perfect plane: one plane, everything labelled, loop stops because nothing remains
+    g = np.stack(np.meshgrid(np.linspace(-1, 1, 40), np.linspace(-1, 1, 40)), -1).reshape(-1, 2)
+    pts = np.c_[g, np.full(len(g), 2.0), np.ones(len(g))].astype(np.float32)
+    seg = oracle.segment_planes(pts, prm)
+    assert len(seg["planes"]) == 1 and (seg["labels"] == 0).all()
+    assert np.allclose(np.abs(seg["planes"][0]["coef"]), [0, 0, 1, 2], atol=1e-5)
+
+
+def test_ransac_replay_adaptive_stop():
+    import ctypes as C
+    lib = oracle.lib()
+    valid = (C.c_int * 6)(1, 0, 1, 1, 1, 1)
+    count = (C.c_int * 6)(10, 99, 90, 95, 100, 100)
+    iters = C.c_int(0)
+    # n=100: first valid gives w=.1 -> k huge; candidate 2 (w=.9) -> k = log(.01)/log(1-.729) = 3.53
+    best = lib.oracle_ransac_replay(valid, count, 6, 100, 50, C.c_double(0.99), 3, C.byref(iters))
+    # iterations: c0 ->1, c1 skipped, c2 ->2 (k=3.53), c3 ->3 (95>90, k=log(.01)/log(1-.857)=2.37) -> stop (3 >= 2.37)
+    assert best == 3 and iters.value == 3
+
+
+def test_backproject_matches_numpy(small_cam):
+    p = synth.make_pair(2, cam=small_cam, quantize=True, holes=0.2)
+    a = oracle.backproject(p["tgt_depth"], small_cam)
+    assert np.array_equal(a, p["tgt"])
+    assert len(a) < small_cam.width * small_cam.height     # holes were skipped
+    b = oracle.backproject(p["tgt_depth"], small_cam, z_max=2.5)
+    assert len(b) < len(a) and b[:, 2].max() <= 2.5
+
+
+def test_planar_keypoints_oracle(small_cam):
+    cam = synth.Camera()
+    z, pid = synth.render_depth(synth.base_pose(), cam, "S1", 0.001, 5, 1)
+    depth = synth.quantize_depth(z, cam)
+    depth[100:110, 200:210] = 0
+    # keypoints: interior of a plane (planar), on a hole (reject), at the border (reject), on a plane boundary
+    v, u = np.mgrid[20:460:40, 20:620:40]
+    uv = np.stack([u.ravel(), v.ravel()], 1)
+    extra = np.array([[204, 104], [1, 1], [638, 478]])
+    uv = np.concatenate([uv, extra])
+    flags = oracle.planar_keypoints(depth, cam, uv)
+    assert flags[-3:].tolist() == [0, 0, 0]
+    inner = []
+    for (uu, vv), f in zip(uv[:-3], flags[:-3]):
+        patch = pid[vv - 3:vv + 4, uu - 3:uu + 4]
+        if (patch == patch[0, 0]).all():
+            inner.append(f)
+    assert len(inner) > 50 and np.mean(inner) > 0.95     # single-plane patches are planar (1 mm noise vs 1 cm threshold)
