@@ -1,0 +1,301 @@
+#!/usr/bin/env python
+"""bench.py -- ICP iterations/s of the registration hot path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+One "step" = one pass of the hot path over one frame pair of BASELINE config 2: a synthetic 640x480
+RGB-D pair (307 200 x 307 200 points), 30 point-to-plane ICP iterations, the target's search index rebuilt
+inside the step.  A pool of POOL distinct pairs (> 126 MB of device data, i.e. larger than L2) rotates so no
+step finds its inputs in cache.  With N > 1 (torchrun, one rank per GPU) every rank registers its own pairs
+(frame pairs are independent units: weak scaling, no data-path collective) and the resulting pose records are
+all-gathered over NCCL inside the timed region.
+
+value      = N * K * 30 / t        device-resident inputs, CUDA events on the launching stream, max over ranks
+e2e        = same metric through the C ABI from HOST (pinned) buffers: upload of both clouds, plane extraction
+             of the target (the reference flow extractPlanes -> multiPnP), registration, result read-back
+roofline   = correspondence+reduction kernel: algorithmic bytes (16 N + 32 M per iteration)
+             over its measured launch time, against the measured HBM peak of MEASURED_PEAKS.json
+cpu_baseline = the CPU oracle (PCL-1.7-equivalent restatement; the reference's own PCL path cannot be built
+             here) timed on this box's host cores on a bounded sample
+--impl reference = that same CPU restatement with every host thread, as the reference arm.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ITERS = 30
+POOL = 16
+N_PTS = 307200
+B_ALG = 16 * N_PTS + 32 * N_PTS          # algorithmic bytes per ICP iteration
+METRIC = "ICP iterations/sec on 640x480 RGB-D clouds"
+UNIT = "iterations/s"
+WORKLOAD = ("config2: single synthetic 640x480 RGB-D frame pair (307200 x 307200 pts), 30 point-to-plane ICP "
+            "iterations, exact NN, search index rebuilt every step")
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) > 8 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) > 8 and r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) > 8 for i in range(4) if r[5 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def run_reference(args, rank):
+    """Reference arm: the CPU restatement of the reference's PCL path with all host threads (rank 0 only)."""
+    if rank != 0:
+        return
+    from slam3d_gx_b200 import synth, _abi
+    from oracle import oracle
+    threads = oracle.max_threads()
+    pairs = [synth.make_pair(i) for i in range(min(2, max(1, args.steps)))]
+    prm = _abi.icp_params(ITERS)
+    for w in range(args.warmup):
+        p = pairs[w % len(pairs)]
+        oracle.icp(p["src"], p["tgt"], p["tgt_normals"], params=_abi.icp_params(3), nthreads=threads)
+    t0 = time.perf_counter()
+    for s in range(args.steps):
+        p = pairs[s % len(pairs)]
+        r = oracle.icp(p["src"], p["tgt"], p["tgt_normals"], params=prm, nthreads=threads)
+        assert r["status"] == 0
+    dt = time.perf_counter() - t0
+    value = args.steps * ITERS / dt
+    sample = f"{args.steps} step(s) x 1 pair x {ITERS} iterations (KD-tree build included), OpenMP over source points"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / max(1, args.steps) * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "note": "CPU restatement of the reference's PCL-1.7 ICP (reference cannot be built: no PCL)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=48)
+    ap.add_argument("--warmup", type=int, default=16)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--pool", type=int, default=POOL)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        if args.steps == 48 and args.warmup == 16:      # defaults sized for the GPU arm; keep the CPU arm bounded
+            args.steps, args.warmup = 4, 1
+        run_reference(args, rank)
+        return
+
+    import torch
+    import slam3d_gx_b200 as s3d
+    from slam3d_gx_b200 import synth, _abi
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    ctx = s3d.Context(local_rank)
+    stream = torch.cuda.current_stream()
+    ctx.set_stream(stream.cuda_stream)
+    W = max(3, args.warmup)
+
+    # ---- inputs: every rank owns its own pool of pairs (pair index = rank*pool + k) ---------------------
+    host, src, tgt = [], [], []
+    for k in range(args.pool):
+        p = synth.make_pair(rank * args.pool + k)
+        host.append(p)
+        src.append(ctx.upload(p["src"]))
+        tgt.append(ctx.upload(p["tgt"], p["tgt_normals"]))
+    prm = _abi.icp_params(ITERS, reuse_index=0)
+    rec_bytes = _abi.RESULT_BYTES
+    gather_in = torch.zeros(rec_bytes, dtype=torch.uint8, device="cuda")
+    gather_out = torch.zeros(world * rec_bytes, dtype=torch.uint8, device="cuda") if world > 1 else None
+    pinned_rec = torch.zeros(rec_bytes, dtype=torch.uint8).pin_memory()
+
+    def step(i):
+        k = i % args.pool
+        res = ctx.register_batch([src[k]], [tgt[k]], None, prm, raw=True)
+        if world > 1:   # pose gather: the only collective of the path
+            pinned_rec.numpy()[:] = np.frombuffer(bytes(res[0]), dtype=np.uint8)
+            gather_in.copy_(pinned_rec, non_blocking=True)
+            dist.all_gather_into_tensor(gather_out, gather_in)
+        return res[0]
+
+    for i in range(W):
+        step(i)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = ctx.launch_count
+    iter_ms, index_ms, iter_launches = 0.0, 0.0, 0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    last = None
+    for i in range(args.steps):
+        last = step(W + i)
+        tm = ctx.last_timing()
+        iter_ms += tm["iterate_ms"]; index_ms += tm["index_ms"]; iter_launches += tm["iter_launches"]
+    e1.record(stream)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    elapsed_ms = e0.elapsed_time(e1)
+    launches = ctx.launch_count - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    assert last.status == 0, "registration failed inside the timed region"
+
+    # ---- e2e: host buffers through the C ABI (upload + plane extraction + registration + read-back) ------
+    pin = []
+    for k in range(min(4, args.pool)):
+        a = torch.from_numpy(host[k]["src"].copy()).pin_memory()
+        b = torch.from_numpy(host[k]["tgt"].copy()).pin_memory()
+        pin.append((a, b))
+    plane_prm = _abi.plane_params()
+    e2e_prm = _abi.icp_params(ITERS, reuse_index=0)
+
+    def e2e_step(i):
+        a, b = pin[i % len(pin)]
+        cs = ctx.upload(a.numpy())
+        ct = ctx.upload(b.numpy())
+        planes = ct.segment_planes(plane_prm)
+        r = ctx.register_batch([cs], [ct], None, e2e_prm, raw=True)[0]
+        cs.free(); ct.free()
+        return r, planes
+
+    e2e_steps = max(4, min(args.steps, 16))
+    for i in range(3):
+        e2e_step(i)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        r, planes = e2e_step(3 + i)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    assert r.status == 0 and len(planes) == 3
+    h2d = int(pin[0][0].numel() * 4 + pin[0][1].numel() * 4)
+    d2h = int(rec_bytes + 3 * 24 + 3 * (64 + 4))
+
+    # ---- max over ranks --------------------------------------------------------------------------------
+    t = torch.tensor([elapsed_ms, e2e_s * 1e3, iter_ms], dtype=torch.float64, device="cuda")
+    cnt = torch.tensor([float(launches)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    elapsed_ms, e2e_ms, iter_ms_max = [float(x) for x in t.tolist()]
+    total_launches = int(cnt.item())
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        value = world * args.steps * ITERS / (elapsed_ms * 1e-3)
+        e2e_value = world * e2e_steps * ITERS / (e2e_ms * 1e-3)
+        # dominant kernel: the fused correspondence + reduction + solve launch (one per iteration)
+        per_launch_s = (iter_ms * 1e-3) / max(1, iter_launches)
+        units_per_launch = (args.steps * ITERS) / max(1, iter_launches)
+        achieved = B_ALG * units_per_launch / per_launch_s / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
+            "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "pairs_per_step_per_gpu": 1, "icp_iterations": ITERS, "points": [N_PTS, N_PTS],
+                       "pool_pairs_per_gpu": args.pool, "l2": "inputs larger than L2: a pool of %d pairs (>%d MB) rotates" % (args.pool, args.pool * 40),
+                       "parallelism": "pairs sharded over %d GPU(s), NCCL all_gather of pose records" % world},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": e2e_steps, "includes": "pinned-host upload of both clouds, RANSAC plane extraction of the target, index build, 30 iterations, result read-back"},
+            "gpu_launches": total_launches,
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "kernel": "icp_iter_kernel<point_to_plane, grid>", "peak_source": peak_src,
+                         "algorithmic_bytes_per_iteration": B_ALG, "iterations_per_launch": units_per_launch,
+                         "avg_launch_us": per_launch_s * 1e6,
+                         "note": "latency/ALU-bound gather kernel; data set is L2 resident after the first iteration (SURVEY.md 0.4, 8d)"},
+            "breakdown_ms_per_step": {"index_build": index_ms / args.steps, "iterations": iter_ms / args.steps},
+        }
+        if not args.no_cpu_baseline and world == 1:
+            from oracle import oracle          # checker / baseline only
+            p = host[0]
+            t0 = time.perf_counter()
+            ro = oracle.icp(p["src"], p["tgt"], p["tgt_normals"], params=_abi.icp_params(ITERS), nthreads=1)
+            dt = time.perf_counter() - t0
+            out["cpu_baseline"] = {"value": ITERS / dt, "unit": UNIT, "cores": 1, "kind": "port",
+                                   "sample": "1 pair x 30 iterations (KD-tree build included), single thread, oracle/icp_oracle.c"}
+            T_gpu = np.array(list(last.T)).reshape(4, 4)
+            # last timed step used pair index (W+steps-1) % pool; compare pair 0 separately
+            r0 = ctx.register_batch([src[0]], [tgt[0]], None, prm)[0]
+            rot, trans = synth.pose_error(r0["T"], ro["T"])
+            out["parity_vs_oracle"] = {"rot_rad": rot, "trans_m": trans, "tolerance": 1e-4}
+        else:
+            out["cpu_baseline"] = None
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

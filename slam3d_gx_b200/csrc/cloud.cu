@@ -65,7 +65,7 @@ extern "C" void s3d_destroy(s3d_ctx *ctx)
     for (auto &kv : ctx->graphs) cudaGraphExecDestroy(kv.second);
     cudaFree(ctx->d_desc); cudaFreeHost(ctx->h_desc);
     cudaFree(ctx->d_state); cudaFreeHost(ctx->h_state);
-    cudaFree(ctx->d_partials); cudaFree(ctx->d_nn_idx); cudaFree(ctx->d_nn_d2); cudaFree(ctx->d_last_nn);
+    cudaFree(ctx->d_partials); cudaFree(ctx->d_nn_idx); cudaFree(ctx->d_nn_d2); cudaFree(ctx->d_nn_pos); cudaFree(ctx->d_last_nn);
     cudaFree(ctx->d_seg);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     for (int i = 0; i < 4; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
@@ -305,6 +305,8 @@ extern "C" void s3d_cloud_free(s3d_ctx *ctx, s3d_cloud *cloud)
     if (!cloud) return;
     if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
     s3d_grid_free(cloud->grid);
+    s3d_grid_free(cloud->coarse);
+    cudaFree(cloud->d_coarse_pts);
     cudaFree(cloud->d_pts); cudaFree(cloud->d_nrm); cudaFree(cloud->d_labels);
     delete cloud;
 }

@@ -9,6 +9,9 @@
 
 #define S3D_GRID_MAX_CELLS (1u << 23)   // dense cell-start array budget per target (32 MiB)
 #define S3D_GRID_MAX_DIM 2040           // per-axis cap: keeps the float cell coordinate error < 1e-3 cells
+#define S3D_COARSE_STRIDE 16            // the coarse seeding index holds every 16th target point
+#define S3D_COARSE_MIN_POINTS 4096      // smaller targets are searched without seeds
+#define S3D_COARSE_MAX_CELLS (1u << 20)
 
 // Device-resident description of a target's search grid; written by grid_setup_kernel, read by
 // every kernel that searches (no host round trip between build and use).
@@ -24,6 +27,8 @@ struct GridIndex {
     bool valid = false;
     bool has_normals = false;
     float requested_cell = 0.f;
+    int n = 0, cap_points = -1;
+    uint32_t cap_cells = 0;
     GridParams *d_params = nullptr;   // 1
     uint32_t *d_cell_start = nullptr; // S3D_GRID_MAX_CELLS + 1
     float4 *d_sorted_pts = nullptr;   // n : (x,y,z, original index bits)
@@ -38,7 +43,9 @@ struct s3d_cloud {
     float4 *d_pts = nullptr;      // (x,y,z,1)
     float4 *d_nrm = nullptr;      // (nx,ny,nz,valid) or null
     int32_t *d_labels = nullptr;  // plane id or -1, or null
-    GridIndex grid;
+    GridIndex grid;               // all points: the exact search index
+    GridIndex coarse;             // every 16th point: first-iteration seeds
+    float4 *d_coarse_pts = nullptr; int cap_coarse_pts = 0;
 };
 
 // one registration unit as the kernels see it
@@ -47,6 +54,7 @@ struct PairDesc {
     const float4 *tgt; const float4 *tgt_nrm; int n_tgt;            // original order (brute force)
     const float4 *sorted_pts; const float4 *sorted_nrm;             // grid order
     const uint32_t *cell_start; const GridParams *grid;
+    const float4 *coarse_pts; const uint32_t *coarse_cell_start; const GridParams *coarse_grid;  // null when absent
 };
 
 struct PairState {
@@ -73,7 +81,7 @@ struct s3d_ctx {
     double *d_partials = nullptr;     // [pairs][ctas][S3D_NACC]
     // brute-force scratch + last-correspondence buffer
     int cap_nn = 0;
-    int32_t *d_nn_idx = nullptr; float *d_nn_d2 = nullptr;
+    int32_t *d_nn_idx = nullptr; float *d_nn_d2 = nullptr; int32_t *d_nn_pos = nullptr;
     int last_nn_n = 0; int32_t *d_last_nn = nullptr; int cap_last_nn = 0;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     s3d_timing timing = {0, 0, 0, 0};

@@ -13,6 +13,7 @@
 #include "grid.cuh"
 #include "compact.cuh"
 #include <cstdlib>
+#include <algorithm>
 
 #define SCAN_ITEMS 8
 #define SCAN_BLOCK 1024
@@ -50,7 +51,7 @@ __global__ void __launch_bounds__(256) bbox_kernel(const float4 *__restrict__ pt
 }
 
 __global__ void grid_setup_kernel(const uint32_t *__restrict__ bbox, int n, float requested_cell, float auto_scale,
-                                  GridParams *__restrict__ gp)
+                                  uint32_t max_cells, GridParams *__restrict__ gp)
 {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     float mn[3], ex[3];
@@ -73,7 +74,7 @@ __global__ void grid_setup_kernel(const uint32_t *__restrict__ bbox, int n, floa
         nz = (int)fminf((float)S3D_GRID_MAX_DIM, floorf(ex[2] / h) + 1.f);
         bool capped = (floorf(ex[0] / h) + 1.f > S3D_GRID_MAX_DIM) || (floorf(ex[1] / h) + 1.f > S3D_GRID_MAX_DIM) ||
                       (floorf(ex[2] / h) + 1.f > S3D_GRID_MAX_DIM);
-        if (!capped && (double)nx * ny * nz <= (double)S3D_GRID_MAX_CELLS) break;
+        if (!capped && (double)nx * ny * nz <= (double)max_cells) break;
         h *= 1.25992105f;
     }
     gp->ox = mn[0]; gp->oy = mn[1]; gp->oz = mn[2];
@@ -194,37 +195,68 @@ static float auto_scale_from_env()
     return v > 0.f ? v : 1.5f;
 }
 
-int s3d_grid_build(s3d_ctx *ctx, s3d_cloud *c, float cell)
+// every `stride`-th point of the cloud: the decimated set behind the coarse seeding index
+__global__ void __launch_bounds__(256) decimate_kernel(const float4 *__restrict__ pts, int n_out, int stride, float4 *__restrict__ out)
 {
-    GridIndex &g = c->grid;
-    int n = c->n;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_out; i += gridDim.x * blockDim.x) out[i] = pts[(size_t)i * stride];
+}
+
+// Build (or rebuild) an index over n device points.  max_cells bounds the dense cell array.
+static int grid_build_raw(s3d_ctx *ctx, GridIndex &g, const float4 *d_pts, const float4 *d_nrm, int n, float cell, float scale,
+                          uint32_t max_cells)
+{
     size_t np = (size_t)(n > 0 ? n : 1);
-    if (!g.d_params) {
+    if (g.cap_points < n || g.cap_cells < max_cells || !g.d_params) {
+        bool had_nrm = g.d_sorted_nrm != nullptr;
+        s3d_grid_free(g);
         S3D_CUDA(ctx, cudaMalloc(&g.d_params, sizeof(GridParams)));
-        S3D_CUDA(ctx, cudaMalloc(&g.d_cell_start, sizeof(uint32_t) * ((size_t)S3D_GRID_MAX_CELLS + 16)));
+        S3D_CUDA(ctx, cudaMalloc(&g.d_cell_start, sizeof(uint32_t) * ((size_t)max_cells + 16)));
         S3D_CUDA(ctx, cudaMalloc(&g.d_sorted_pts, sizeof(float4) * np));
         S3D_CUDA(ctx, cudaMalloc(&g.d_rank, sizeof(uint32_t) * np));
         S3D_CUDA(ctx, cudaMalloc(&g.d_bbox, sizeof(uint32_t) * 8));
-        S3D_CUDA(ctx, cudaMalloc(&g.d_block_sums, sizeof(uint32_t) * (S3D_GRID_MAX_CELLS / SCAN_TILE + 8)));
+        S3D_CUDA(ctx, cudaMalloc(&g.d_block_sums, sizeof(uint32_t) * (max_cells / SCAN_TILE + 8)));
+        g.cap_points = n; g.cap_cells = max_cells;
+        (void)had_nrm;
     }
-    if (c->d_nrm && !g.d_sorted_nrm) S3D_CUDA(ctx, cudaMalloc(&g.d_sorted_nrm, sizeof(float4) * np));
+    if (d_nrm && !g.d_sorted_nrm) S3D_CUDA(ctx, cudaMalloc(&g.d_sorted_nrm, sizeof(float4) * (size_t)(g.cap_points > 0 ? g.cap_points : 1)));
     cudaStream_t st = ctx->stream;
     const int wide = ctx->sm_count * 8;
-    const int scan_blocks = S3D_GRID_MAX_CELLS / SCAN_TILE + 1;
-    static const float scale = auto_scale_from_env();
+    const int scan_blocks = (int)(max_cells / SCAN_TILE) + 1;
     bbox_init_kernel<<<1, 32, 0, st>>>(g.d_bbox); S3D_LAUNCHED(ctx);
-    if (n > 0) { bbox_kernel<<<wide, 256, 0, st>>>(c->d_pts, n, g.d_bbox); S3D_LAUNCHED(ctx); }
-    grid_setup_kernel<<<1, 32, 0, st>>>(g.d_bbox, n, cell, scale, g.d_params); S3D_LAUNCHED(ctx);
-    grid_zero_kernel<<<wide, 256, 0, st>>>(g.d_cell_start, g.d_params); S3D_LAUNCHED(ctx);
-    if (n > 0) { grid_count_kernel<<<wide, 256, 0, st>>>(c->d_pts, n, g.d_params, g.d_cell_start, g.d_rank); S3D_LAUNCHED(ctx); }
+    if (n > 0) { bbox_kernel<<<std::min(wide, (n + 255) / 256), 256, 0, st>>>(d_pts, n, g.d_bbox); S3D_LAUNCHED(ctx); }
+    grid_setup_kernel<<<1, 32, 0, st>>>(g.d_bbox, n, cell, scale, max_cells, g.d_params); S3D_LAUNCHED(ctx);
+    grid_zero_kernel<<<std::min(wide, (int)(max_cells / 1024) + 1), 256, 0, st>>>(g.d_cell_start, g.d_params); S3D_LAUNCHED(ctx);
+    if (n > 0) { grid_count_kernel<<<std::min(wide, (n + 255) / 256), 256, 0, st>>>(d_pts, n, g.d_params, g.d_cell_start, g.d_rank); S3D_LAUNCHED(ctx); }
     grid_scan_reduce_kernel<<<scan_blocks, SCAN_BLOCK, 0, st>>>(g.d_cell_start, g.d_params, g.d_block_sums); S3D_LAUNCHED(ctx);
     compact_scan_kernel<<<1, 1024, 0, st>>>(g.d_block_sums, scan_blocks, g.d_block_sums + scan_blocks); S3D_LAUNCHED(ctx);
     grid_scan_apply_kernel<<<scan_blocks, SCAN_BLOCK, 0, st>>>(g.d_cell_start, g.d_params, g.d_block_sums); S3D_LAUNCHED(ctx);
     if (n > 0) {
-        grid_scatter_kernel<<<wide, 256, 0, st>>>(c->d_pts, c->d_nrm, n, g.d_params, g.d_cell_start, g.d_rank,
-                                                  g.d_sorted_pts, c->d_nrm ? g.d_sorted_nrm : nullptr);
+        grid_scatter_kernel<<<std::min(wide, (n + 255) / 256), 256, 0, st>>>(d_pts, d_nrm, n, g.d_params, g.d_cell_start, g.d_rank,
+                                                                           g.d_sorted_pts, d_nrm ? g.d_sorted_nrm : nullptr);
         S3D_LAUNCHED(ctx);
     }
-    g.valid = true; g.has_normals = c->d_nrm != nullptr; g.requested_cell = cell;
+    g.valid = true; g.has_normals = d_nrm != nullptr; g.requested_cell = cell; g.n = n;
+    return S3D_OK;
+}
+
+int s3d_grid_build(s3d_ctx *ctx, s3d_cloud *c, float cell)
+{
+    static const float scale = auto_scale_from_env();
+    int rc = grid_build_raw(ctx, c->grid, c->d_pts, c->d_nrm, c->n, cell, scale, S3D_GRID_MAX_CELLS);
+    if (rc) return rc;
+    // coarse seeding index over every S3D_COARSE_STRIDE-th point (first-iteration seeds, see icp.cu)
+    c->coarse.valid = false;
+    if (c->n >= S3D_COARSE_MIN_POINTS) {
+        int nc = c->n / S3D_COARSE_STRIDE;
+        if (c->cap_coarse_pts < nc) {
+            cudaFree(c->d_coarse_pts); c->d_coarse_pts = nullptr;
+            S3D_CUDA(ctx, cudaMalloc(&c->d_coarse_pts, sizeof(float4) * (size_t)nc));
+            c->cap_coarse_pts = nc;
+        }
+        decimate_kernel<<<std::min(ctx->sm_count * 8, (nc + 255) / 256), 256, 0, ctx->stream>>>(c->d_pts, nc, S3D_COARSE_STRIDE, c->d_coarse_pts);
+        S3D_LAUNCHED(ctx);
+        rc = grid_build_raw(ctx, c->coarse, c->d_coarse_pts, nullptr, nc, 0.f, scale, S3D_COARSE_MAX_CELLS);
+        if (rc) return rc;
+    }
     return S3D_OK;
 }

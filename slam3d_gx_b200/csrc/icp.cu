@@ -24,36 +24,106 @@
 #include "grid.cuh"
 
 #define ICP_BLOCK 256
+#define ICP_MIN_BLOCKS 4      // 64 registers per thread: 32 warps per SM hide the gather latency
 #define GRID_MARGIN 1e-3f     // cell-coordinate rounding allowance (see DESIGN.md "exactness of the ring search")
 
 // ------------------------------------------------------------------------------------------------
 // exact NN on the grid
 // ------------------------------------------------------------------------------------------------
+// The kernel is bound by the latency of dependent gathers, not by bandwidth, so the search is built
+// to need few dependent round trips: candidates are loaded four at a time, and a query normally
+// starts from a *seed* (its correspondence of the previous iteration, or on the first iteration the
+// nearest point of a 16x decimated copy of the target) whose distance bounds the ball that has to be
+// searched.  A seed is only ever used as an upper bound, so the result is still the exact argmin.
 __device__ __forceinline__ float axis_gap(float t, int d)
 {
     float g = d > 0 ? ((float)d - t) : (d < 0 ? (t - (float)d - 1.0f) : 0.0f);
     return fmaxf(g - GRID_MARGIN, 0.0f);
 }
 
+__device__ __forceinline__ void nn_update(const float4 q, uint32_t k, float px, float py, float pz, float &bd, int &bpos, int &bidx)
+{
+    float d2 = s3d_dist2(px, py, pz, q.x, q.y, q.z);
+    int qi = __float_as_int(q.w);
+    if (d2 < bd || (d2 == bd && qi < bidx)) { bd = d2; bpos = (int)k; bidx = qi; }
+}
+
+// candidates [s,e) of the cell-sorted array, four independent loads in flight per step; the clamped
+// tail re-reads element e-1, which cannot change the result
 __device__ __forceinline__ void scan_range(const float4 *__restrict__ sp, uint32_t s, uint32_t e, float px, float py, float pz,
                                            float &bd, int &bpos, int &bidx)
 {
-    for (uint32_t k = s; k < e; ++k) {
-        float4 q = __ldg(&sp[k]);
-        float d2 = s3d_dist2(px, py, pz, q.x, q.y, q.z);
-        int qi = __float_as_int(q.w);
-        if (d2 < bd || (d2 == bd && qi < bidx)) { bd = d2; bpos = (int)k; bidx = qi; }
+    for (uint32_t k = s; k < e; k += 4) {
+        const uint32_t k1 = min(k + 1, e - 1), k2 = min(k + 2, e - 1), k3 = min(k + 3, e - 1);
+        const float4 q0 = __ldg(&sp[k]), q1 = __ldg(&sp[k1]), q2 = __ldg(&sp[k2]), q3 = __ldg(&sp[k3]);
+        nn_update(q0, k, px, py, pz, bd, bpos, bidx);
+        nn_update(q1, k1, px, py, pz, bd, bpos, bidx);
+        nn_update(q2, k2, px, py, pz, bd, bpos, bidx);
+        nn_update(q3, k3, px, py, pz, bd, bpos, bidx);
     }
 }
 
-// Returns position of the nearest target in the sorted array (-1 if the target is empty).
-__device__ __forceinline__ void grid_nn(const GridParams &gp, const uint32_t *__restrict__ cs, const float4 *__restrict__ sp,
-                                        float px, float py, float pz, float &bd, int &bpos)
+struct CellPos { int cx, cy, cz; float tx, ty, tz; };
+__device__ __forceinline__ CellPos cell_pos(const GridParams &gp, float px, float py, float pz)
 {
+    CellPos c;
     const float fx = grid_fcoord(px, gp.ox, gp.inv_cell), fy = grid_fcoord(py, gp.oy, gp.inv_cell), fz = grid_fcoord(pz, gp.oz, gp.inv_cell);
-    const int cx = grid_clampi(fx, gp.nx), cy = grid_clampi(fy, gp.ny), cz = grid_clampi(fz, gp.nz);
-    const float tx = fx - (float)cx, ty = fy - (float)cy, tz = fz - (float)cz;
-    const float cell2 = gp.cell * gp.cell;
+    c.cx = grid_clampi(fx, gp.nx); c.cy = grid_clampi(fy, gp.ny); c.cz = grid_clampi(fz, gp.nz);
+    c.tx = fx - (float)c.cx; c.ty = fy - (float)c.cy; c.tz = fz - (float)c.cz;
+    return c;
+}
+
+// one row (fixed y,z) of cells: the x-run that intersects the ball of squared radius lim is one
+// contiguous range of the sorted array
+__device__ __forceinline__ void ball_row(const GridParams &gp, const uint32_t *__restrict__ cs, const float4 *__restrict__ sp,
+                                         const CellPos &c, int y, int z, float row2, float inv_cell2, float px, float py, float pz,
+                                         float &lim, float &bd, int &bpos, int &bidx)
+{
+    const float ext = sqrtf(fmaxf(lim * inv_cell2 - row2, 0.f)) + GRID_MARGIN;
+    const int xa = max(c.cx + __float2int_rd(c.tx - ext), 0), xb = min(c.cx + __float2int_rd(c.tx + ext), gp.nx - 1);
+    if (xa > xb) return;
+    const int row = (z * gp.ny + y) * gp.nx;
+    const uint32_t s = __ldg(&cs[row + xa]), e = __ldg(&cs[row + xb + 1]);
+    scan_range(sp, s, e, px, py, pz, bd, bpos, bidx);
+    lim = fminf(lim, bd);
+}
+
+// exact NN given an upper bound `lim` (exclusive) on its squared distance: only the cells that
+// intersect the ball are visited, home row first
+__device__ __forceinline__ void grid_nn_ball(const GridParams &gp, const uint32_t *__restrict__ cs, const float4 *__restrict__ sp,
+                                             float px, float py, float pz, float lim, float &bd, int &bpos)
+{
+    const CellPos c = cell_pos(gp, px, py, pz);
+    const float cell2 = gp.cell * gp.cell, inv_cell2 = gp.inv_cell * gp.inv_cell;
+    bd = INFINITY; bpos = -1;
+    int bidx = 0x7fffffff;
+    ball_row(gp, cs, sp, c, c.cy, c.cz, 0.f, inv_cell2, px, py, pz, lim, bd, bpos, bidx);   // home row first: it usually holds the answer
+    const float Rc = sqrtf(lim * inv_cell2) + GRID_MARGIN;
+    const int z0 = max(c.cz + __float2int_rd(c.tz - Rc), 0), z1 = min(c.cz + __float2int_rd(c.tz + Rc), gp.nz - 1);
+    const int y0 = max(c.cy + __float2int_rd(c.ty - Rc), 0), y1 = min(c.cy + __float2int_rd(c.ty + Rc), gp.ny - 1);
+    for (int z = z0; z <= z1; ++z) {
+        const float gz = axis_gap(c.tz, z - c.cz);
+        if (gz * gz * cell2 >= lim) continue;
+        for (int y = y0; y <= y1; ++y) {
+            if (y == c.cy && z == c.cz) continue;
+            const float gy = axis_gap(c.ty, y - c.cy);
+            const float row2 = gy * gy + gz * gz;
+            if (row2 * cell2 >= lim) continue;
+            ball_row(gp, cs, sp, c, y, z, row2, inv_cell2, px, py, pz, lim, bd, bpos, bidx);
+        }
+    }
+}
+
+// exact NN without a bound: shells of growing Chebyshev radius around the home cell until the best
+// distance is closer than the nearest unexplored cell.  Used for the coarse seeding index, for small
+// targets and when a query has no seed.
+__device__ __forceinline__ void grid_nn_ring(const GridParams &gp, const uint32_t *__restrict__ cs, const float4 *__restrict__ sp,
+                                             float px, float py, float pz, float &bd, int &bpos)
+{
+    const CellPos c = cell_pos(gp, px, py, pz);
+    const int cx = c.cx, cy = c.cy, cz = c.cz;
+    const float tx = c.tx, ty = c.ty, tz = c.tz;
+    const float cell2 = gp.cell * gp.cell, inv_cell2 = gp.inv_cell * gp.inv_cell;
     bd = INFINITY; bpos = -1;
     int bidx = 0x7fffffff;
     if (gp.n_points == 0) return;
@@ -67,10 +137,9 @@ __device__ __forceinline__ void grid_nn(const GridParams &gp, const uint32_t *__
                 const float gy = axis_gap(ty, y - cy);
                 const float row2 = gy * gy + gz * gz;
                 if (row2 * cell2 >= bd) continue;
-                // cells of this row that can still hold a closer point: |x - tx| < sqrt(bd/cell^2 - row2)
                 int xa = cx - r, xb = cx + r;
                 if (bd < INFINITY) {
-                    float ext = sqrtf(fmaxf(bd / cell2 - row2, 0.f)) + GRID_MARGIN;
+                    float ext = sqrtf(fmaxf(bd * inv_cell2 - row2, 0.f)) + GRID_MARGIN;
                     xa = max(xa, cx + __float2int_rd(tx - ext));
                     xb = min(xb, cx + __float2int_rd(tx + ext));
                 }
@@ -78,16 +147,14 @@ __device__ __forceinline__ void grid_nn(const GridParams &gp, const uint32_t *__
                 const int row = (z * gp.ny + y) * gp.nx;
                 const bool edge = zedge || (y - cy == r) || (cy - y == r);
                 if (edge) {
-                    if (xa <= xb) scan_range(sp, cs[row + xa], cs[row + xb + 1], px, py, pz, bd, bpos, bidx);
+                    if (xa <= xb) scan_range(sp, __ldg(&cs[row + xa]), __ldg(&cs[row + xb + 1]), px, py, pz, bd, bpos, bidx);
                 } else {
-                    // interior row of the shell: only the two end cells are new
-                    const int xl = cx - r, xh = cx + r;
-                    if (xl >= xa && xl <= xb) scan_range(sp, cs[row + xl], cs[row + xl + 1], px, py, pz, bd, bpos, bidx);
-                    if (xh >= xa && xh <= xb && xh != xl) scan_range(sp, cs[row + xh], cs[row + xh + 1], px, py, pz, bd, bpos, bidx);
+                    const int xl = cx - r, xh = cx + r; // interior row of the shell: only the two end cells are new
+                    if (xl >= xa && xl <= xb) scan_range(sp, __ldg(&cs[row + xl]), __ldg(&cs[row + xl + 1]), px, py, pz, bd, bpos, bidx);
+                    if (xh >= xa && xh <= xb && xh != xl) scan_range(sp, __ldg(&cs[row + xh]), __ldg(&cs[row + xh + 1]), px, py, pz, bd, bpos, bidx);
                 }
             }
         }
-        // distance from p to the nearest unexplored cell (cube of radius r around the home cell)
         float gap = INFINITY;
         bool covered = true;
         if (cx - r > 0) { gap = fminf(gap, tx + (float)r); covered = false; }
@@ -346,10 +413,11 @@ __device__ __forceinline__ void accumulate(float *acc, float px, float py, float
 }
 
 template <int EST, int SEARCH>
-__global__ void __launch_bounds__(ICP_BLOCK, 2) icp_iter_kernel(const PairDesc *__restrict__ descs, PairState *__restrict__ states,
-                                                             double *__restrict__ partials, const int32_t *__restrict__ nn_idx,
-                                                             const float *__restrict__ nn_d2, int nn_stride, float max_d2,
-                                                             int min_corr, double pivot_eps, int32_t *__restrict__ nn_out)
+__global__ void __launch_bounds__(ICP_BLOCK, ICP_MIN_BLOCKS) icp_iter_kernel(const PairDesc *__restrict__ descs, PairState *__restrict__ states,
+                                                                             double *__restrict__ partials, const int32_t *__restrict__ nn_idx,
+                                                                             int32_t *__restrict__ nn_pos, int nn_stride, int use_seed,
+                                                                             float max_d2, int min_corr, double pivot_eps,
+                                                                             int32_t *__restrict__ nn_out)
 {
     __shared__ double wsum[ICP_BLOCK / 32][S3D_NACC];
     __shared__ double tail[8][S3D_NACC];
@@ -361,20 +429,43 @@ __global__ void __launch_bounds__(ICP_BLOCK, 2) icp_iter_kernel(const PairDesc *
     float T[12];
     #pragma unroll
     for (int k = 0; k < 12; ++k) T[k] = st->Tf[k];
-    GridParams gp;
-    if (SEARCH == S3D_SEARCH_GRID) gp = *d.grid;
+    const int tid0 = blockIdx.x * ICP_BLOCK + threadIdx.x, tstride = gridDim.x * ICP_BLOCK;
+    int32_t *my_pos = nn_pos + (size_t)pair * nn_stride;
 
+    // ---- phase 1: exact nearest neighbour of every transformed source point (grid search) ----------
+    if (SEARCH == S3D_SEARCH_GRID) {
+        const GridParams gp = *d.grid;
+        const float gate = max_d2 < INFINITY ? max_d2 * 1.00001f + 1e-30f : INFINITY;
+        for (int i = tid0; i < d.n_src; i += tstride) {
+            const float4 p = d.src[i];
+            const float3 x = s3d_xform(T, p.x, p.y, p.z);
+            float lim = INFINITY;
+            if (use_seed) {
+                const int sp_ = my_pos[i];
+                if (sp_ >= 0) { const float4 q = __ldg(&d.sorted_pts[sp_]); lim = s3d_dist2(x.x, x.y, x.z, q.x, q.y, q.z) * 1.00001f + 1e-30f; }
+            } else if (d.coarse_grid) {
+                float cd; int cpos;
+                grid_nn_ring(*d.coarse_grid, d.coarse_cell_start, d.coarse_pts, x.x, x.y, x.z, cd, cpos);
+                if (cpos >= 0) lim = cd * 1.00001f + 1e-30f;
+            }
+            lim = fminf(lim, gate);   // nothing beyond the correspondence gate can be accepted anyway
+            float bd; int bpos;
+            if (lim < INFINITY) grid_nn_ball(gp, d.cell_start, d.sorted_pts, x.x, x.y, x.z, lim, bd, bpos);
+            else grid_nn_ring(gp, d.cell_start, d.sorted_pts, x.x, x.y, x.z, bd, bpos);
+            my_pos[i] = bpos;
+        }
+    }
+
+    // ---- phase 2: residuals and normal-equation sums of the accepted correspondences --------------
     float acc[29];
     #pragma unroll
     for (int k = 0; k < 29; ++k) acc[k] = 0.f;
-
-    for (int i = blockIdx.x * ICP_BLOCK + threadIdx.x; i < d.n_src; i += gridDim.x * ICP_BLOCK) {
+    for (int i = tid0; i < d.n_src; i += tstride) {
         const float4 p = d.src[i];
         const float3 x = s3d_xform(T, p.x, p.y, p.z);
-        float bd; int j = -1; float4 q, nv = make_float4(0.f, 0.f, 0.f, 1.f);
+        int j = -1; float4 q = make_float4(0.f, 0.f, 0.f, 0.f), nv = make_float4(0.f, 0.f, 0.f, 1.f);
         if (SEARCH == S3D_SEARCH_GRID) {
-            int bpos;
-            grid_nn(gp, d.cell_start, d.sorted_pts, x.x, x.y, x.z, bd, bpos);
+            const int bpos = my_pos[i];     // written by this same thread in phase 1
             if (bpos >= 0) {
                 q = __ldg(&d.sorted_pts[bpos]);
                 j = __float_as_int(q.w);
@@ -382,13 +473,13 @@ __global__ void __launch_bounds__(ICP_BLOCK, 2) icp_iter_kernel(const PairDesc *
             }
         } else {
             j = nn_idx[(size_t)pair * nn_stride + i];
-            bd = nn_d2[(size_t)pair * nn_stride + i];
             if (j >= 0) {
                 q = __ldg(&d.tgt[j]);
                 if (EST == S3D_ESTIMATOR_POINT_TO_PLANE) nv = __ldg(&d.tgt_nrm[j]);
             }
         }
-        bool ok = (j >= 0) && (bd <= max_d2) && (nv.w != 0.f);
+        const float bd = s3d_dist2(x.x, x.y, x.z, q.x, q.y, q.z);   // same expression as in the search: identical bits
+        const bool ok = (j >= 0) && (bd <= max_d2) && (nv.w != 0.f);
         if (ok) accumulate<EST>(acc, x.x, x.y, x.z, q, nv, bd);
         if (nn_out) nn_out[i] = ok ? j : -1;
     }
@@ -486,10 +577,10 @@ static int ensure_batch(s3d_ctx *ctx, int n_pairs, int ctas)
 }
 
 template <int EST, int SEARCH>
-static void launch_iter(s3d_ctx *ctx, dim3 grid, int nn_stride, float max_d2, int min_corr, double pivot_eps, int32_t *nn_out)
+static void launch_iter(s3d_ctx *ctx, dim3 grid, int nn_stride, int use_seed, float max_d2, int min_corr, double pivot_eps, int32_t *nn_out)
 {
     icp_iter_kernel<EST, SEARCH><<<grid, ICP_BLOCK, 0, ctx->stream>>>(ctx->d_desc, ctx->d_state, ctx->d_partials, ctx->d_nn_idx,
-                                                                      ctx->d_nn_d2, nn_stride, max_d2, min_corr, pivot_eps, nn_out);
+                                                                      ctx->d_nn_pos, nn_stride, use_seed, max_d2, min_corr, pivot_eps, nn_out);
 }
 
 extern "C" int s3d_register_batch(s3d_ctx *ctx, const s3d_cloud *const *src, const s3d_cloud *const *tgt,
@@ -509,8 +600,11 @@ extern "C" int s3d_register_batch(s3d_ctx *ctx, const s3d_cloud *const *src, con
         n_max = std::max(n_max, src[i]->n);
     }
     const int64_t launches0 = ctx->launches;
-    // launch geometry: ~4 sources per thread for a lone pair, more per thread when the batch fills the GPU
-    int ctas = std::max(1, std::min((n_max + ICP_BLOCK * 4 - 1) / (ICP_BLOCK * 4), (ctx->sm_count * 16 + n_pairs - 1) / n_pairs));
+    // launch geometry: every CTA of the launch is resident at once (ICP_MIN_BLOCKS per SM), and a lone pair is
+    // spread so that each thread walks the fewest possible queries one after the other (the kernel is latency bound)
+    const int resident = ctx->sm_count * ICP_MIN_BLOCKS;
+    const int rounds = std::max(1, (n_max + resident * ICP_BLOCK - 1) / (resident * ICP_BLOCK));
+    int ctas = std::max(1, std::min((n_max + rounds * ICP_BLOCK - 1) / (rounds * ICP_BLOCK), std::max(1, resident / n_pairs)));
     int rc = ensure_batch(ctx, n_pairs, ctas);
     if (rc) return rc;
 
@@ -528,12 +622,14 @@ extern "C" int s3d_register_batch(s3d_ctx *ctx, const s3d_cloud *const *src, con
     }
     cudaEventRecord(ctx->ev[1], ctx->stream);
 
-    if (!use_grid) {
+    {
         size_t need = (size_t)n_pairs * n_max;
         if (need > (size_t)ctx->cap_nn) {
-            cudaFree(ctx->d_nn_idx); cudaFree(ctx->d_nn_d2); ctx->d_nn_idx = nullptr; ctx->d_nn_d2 = nullptr;
+            cudaFree(ctx->d_nn_idx); cudaFree(ctx->d_nn_d2); cudaFree(ctx->d_nn_pos);
+            ctx->d_nn_idx = nullptr; ctx->d_nn_d2 = nullptr; ctx->d_nn_pos = nullptr;
             S3D_CUDA(ctx, cudaMalloc(&ctx->d_nn_idx, sizeof(int32_t) * std::max<size_t>(need, 1)));
             S3D_CUDA(ctx, cudaMalloc(&ctx->d_nn_d2, sizeof(float) * std::max<size_t>(need, 1)));
+            S3D_CUDA(ctx, cudaMalloc(&ctx->d_nn_pos, sizeof(int32_t) * std::max<size_t>(need, 1)));
             ctx->cap_nn = (int)need;
         }
     }
@@ -553,6 +649,10 @@ extern "C" int s3d_register_batch(s3d_ctx *ctx, const s3d_cloud *const *src, con
         d.tgt = tgt[i]->d_pts; d.tgt_nrm = tgt[i]->d_nrm; d.n_tgt = tgt[i]->n;
         d.sorted_pts = tgt[i]->grid.d_sorted_pts; d.sorted_nrm = tgt[i]->grid.d_sorted_nrm;
         d.cell_start = tgt[i]->grid.d_cell_start; d.grid = tgt[i]->grid.d_params;
+        const bool coarse = use_grid && tgt[i]->coarse.valid;
+        d.coarse_pts = coarse ? tgt[i]->coarse.d_sorted_pts : nullptr;
+        d.coarse_cell_start = coarse ? tgt[i]->coarse.d_cell_start : nullptr;
+        d.coarse_grid = coarse ? tgt[i]->coarse.d_params : nullptr;
         PairState &s = ctx->h_state[i];
         memset(&s, 0, sizeof(s));
         static const double I12[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
@@ -576,11 +676,11 @@ extern "C" int s3d_register_batch(s3d_ctx *ctx, const s3d_cloud *const *src, con
             if (!attr_done) { cudaFuncSetAttribute(nn_brute_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_done = true; }
             nn_brute_tma_kernel<<<g2, ICP_BLOCK, smem, ctx->stream>>>(ctx->d_desc, ctx->d_state, ctx->d_nn_idx, ctx->d_nn_d2, n_max);
             S3D_LAUNCHED(ctx); ++iter_launches;
-            if (plane) launch_iter<S3D_ESTIMATOR_POINT_TO_PLANE, S3D_SEARCH_BRUTE>(ctx, grid, n_max, max_d2, min_corr, pivot_eps, no);
-            else launch_iter<S3D_ESTIMATOR_SVD, S3D_SEARCH_BRUTE>(ctx, grid, n_max, max_d2, min_corr, pivot_eps, no);
+            if (plane) launch_iter<S3D_ESTIMATOR_POINT_TO_PLANE, S3D_SEARCH_BRUTE>(ctx, grid, n_max, 0, max_d2, min_corr, pivot_eps, no);
+            else launch_iter<S3D_ESTIMATOR_SVD, S3D_SEARCH_BRUTE>(ctx, grid, n_max, 0, max_d2, min_corr, pivot_eps, no);
         } else {
-            if (plane) launch_iter<S3D_ESTIMATOR_POINT_TO_PLANE, S3D_SEARCH_GRID>(ctx, grid, n_max, max_d2, min_corr, pivot_eps, no);
-            else launch_iter<S3D_ESTIMATOR_SVD, S3D_SEARCH_GRID>(ctx, grid, n_max, max_d2, min_corr, pivot_eps, no);
+            if (plane) launch_iter<S3D_ESTIMATOR_POINT_TO_PLANE, S3D_SEARCH_GRID>(ctx, grid, n_max, it > 0, max_d2, min_corr, pivot_eps, no);
+            else launch_iter<S3D_ESTIMATOR_SVD, S3D_SEARCH_GRID>(ctx, grid, n_max, it > 0, max_d2, min_corr, pivot_eps, no);
         }
         S3D_LAUNCHED(ctx); ++iter_launches;
     }
