@@ -21,7 +21,8 @@ class S3DError(RuntimeError):
 
 
 def library_path() -> str:
-    return os.path.join(_HERE, "libslam3d_b200.so")
+    # S3D_LIBRARY: developer override to A/B-test an alternative build of the same CUDA library
+    return os.environ.get("S3D_LIBRARY") or os.path.join(_HERE, "libslam3d_b200.so")
 
 
 # every symbol include/slam3d_b200.h declares (tests check that the .so exports all of them)

@@ -21,6 +21,8 @@ struct GridParams {
     int nx, ny, nz;
     int ncells;
     int n_points;
+    int words;             // row-occupancy masks: `words` 32-bit words per row (y,z), one bit per cell along x
+    int mask_words;
 };
 
 struct GridIndex {
@@ -36,6 +38,7 @@ struct GridIndex {
     uint32_t *d_rank = nullptr;       // n : rank of the point inside its cell
     uint32_t *d_bbox = nullptr;       // 6 ordered-uint min/max
     uint32_t *d_block_sums = nullptr; // scan scratch
+    uint32_t *d_rowmask = nullptr;    // occupancy bits per row of cells (empty-space skipping in the ball search)
 };
 
 struct s3d_cloud {
@@ -53,13 +56,14 @@ struct PairDesc {
     const float4 *src; int n_src;
     const float4 *tgt; const float4 *tgt_nrm; int n_tgt;            // original order (brute force)
     const float4 *sorted_pts; const float4 *sorted_nrm;             // grid order
-    const uint32_t *cell_start; const GridParams *grid;
-    const float4 *coarse_pts; const uint32_t *coarse_cell_start; const GridParams *coarse_grid;  // null when absent
+    const uint32_t *cell_start; const GridParams *grid; const uint32_t *rowmask;
+    const float4 *coarse_pts; const uint32_t *coarse_cell_start; const uint32_t *coarse_rowmask; const GridParams *coarse_grid;  // null when absent
 };
 
 struct PairState {
     double T[12];
     float Tf[12];
+    float Tf_prev[12];   // pose of the previous iteration (skip test of the seeded search)
     double fitness;
     int inliers;
     int iterations;

@@ -34,6 +34,7 @@ __global__ void __launch_bounds__(256) bbox_kernel(const float4 *__restrict__ pt
         mn[1] = fminf(mn[1], p.y); mx[1] = fmaxf(mx[1], p.y);
         mn[2] = fminf(mn[2], p.z); mx[2] = fmaxf(mx[2], p.z);
     }
+    __shared__ float smn[8][3], smx[8][3];
     #pragma unroll
     for (int a = 0; a < 3; ++a) {
         #pragma unroll
@@ -44,9 +45,15 @@ __global__ void __launch_bounds__(256) bbox_kernel(const float4 *__restrict__ pt
     }
     if ((threadIdx.x & 31) == 0) {
         #pragma unroll
-        for (int a = 0; a < 3; ++a) {
-            if (mn[a] <= mx[a]) { atomicMin(&bbox[a], f2ord(mn[a])); atomicMax(&bbox[3 + a], f2ord(mx[a])); }
-        }
+        for (int a = 0; a < 3; ++a) { smn[threadIdx.x >> 5][a] = mn[a]; smx[threadIdx.x >> 5][a] = mx[a]; }
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) {   // one atomic pair per axis per CTA (not per warp: 6 hot addresses serialise)
+        const int a = threadIdx.x;
+        float lo = smn[0][a], hi = smx[0][a];
+        #pragma unroll
+        for (int w = 1; w < 8; ++w) { lo = fminf(lo, smn[w][a]); hi = fmaxf(hi, smx[w][a]); }
+        if (lo <= hi) { atomicMin(&bbox[a], f2ord(lo)); atomicMax(&bbox[3 + a], f2ord(hi)); }
     }
 }
 
@@ -74,27 +81,39 @@ __global__ void grid_setup_kernel(const uint32_t *__restrict__ bbox, int n, floa
         nz = (int)fminf((float)S3D_GRID_MAX_DIM, floorf(ex[2] / h) + 1.f);
         bool capped = (floorf(ex[0] / h) + 1.f > S3D_GRID_MAX_DIM) || (floorf(ex[1] / h) + 1.f > S3D_GRID_MAX_DIM) ||
                       (floorf(ex[2] / h) + 1.f > S3D_GRID_MAX_DIM);
-        if (!capped && (double)nx * ny * nz <= (double)max_cells) break;
+        if (!capped && (double)nx * ny * nz <= (double)max_cells && (double)ny * nz * ((nx + 31) / 32) <= (double)(max_cells / 8)) break;
         h *= 1.25992105f;
     }
     gp->ox = mn[0]; gp->oy = mn[1]; gp->oz = mn[2];
     gp->cell = h; gp->inv_cell = 1.0f / h;
     gp->nx = nx; gp->ny = ny; gp->nz = nz; gp->ncells = nx * ny * nz; gp->n_points = n;
+    gp->words = (nx + 31) / 32;
+    gp->mask_words = ny * nz * gp->words;
 }
 
-__global__ void __launch_bounds__(256) grid_zero_kernel(uint32_t *__restrict__ cell_start, const GridParams *__restrict__ gp)
+__global__ void __launch_bounds__(256) grid_zero_kernel(uint32_t *__restrict__ cell_start, uint32_t *__restrict__ rowmask,
+                                                        const GridParams *__restrict__ gp)
 {
     int n = gp->ncells + 1;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) cell_start[i] = 0u;
+    int m = gp->mask_words;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) rowmask[i] = 0u;
 }
 
 __global__ void __launch_bounds__(256) grid_count_kernel(const float4 *__restrict__ pts, int n, const GridParams *__restrict__ gpp,
-                                                         uint32_t *__restrict__ cell_start, uint32_t *__restrict__ rank)
+                                                         uint32_t *__restrict__ cell_start, uint32_t *__restrict__ rank,
+                                                         uint32_t *__restrict__ rowmask)
 {
     GridParams gp = *gpp;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         float4 p = pts[i];
-        rank[i] = atomicAdd(&cell_start[grid_cell_index(gp, p.x, p.y, p.z)], 1u);
+        const int cx = grid_clampi(grid_fcoord(p.x, gp.ox, gp.inv_cell), gp.nx);
+        const int cy = grid_clampi(grid_fcoord(p.y, gp.oy, gp.inv_cell), gp.ny);
+        const int cz = grid_clampi(grid_fcoord(p.z, gp.oz, gp.inv_cell), gp.nz);
+        rank[i] = atomicAdd(&cell_start[(cz * gp.ny + cy) * gp.nx + cx], 1u);
+        uint32_t *mw = &rowmask[((size_t)cz * gp.ny + cy) * gp.words + (cx >> 5)];
+        const uint32_t bit = 1u << (cx & 31);
+        if (!(*mw & bit)) atomicOr(mw, bit);
     }
 }
 
@@ -184,7 +203,7 @@ __global__ void __launch_bounds__(256) grid_scatter_kernel(const float4 *__restr
 void s3d_grid_free(GridIndex &g)
 {
     cudaFree(g.d_params); cudaFree(g.d_cell_start); cudaFree(g.d_sorted_pts); cudaFree(g.d_sorted_nrm);
-    cudaFree(g.d_rank); cudaFree(g.d_bbox); cudaFree(g.d_block_sums);
+    cudaFree(g.d_rank); cudaFree(g.d_bbox); cudaFree(g.d_block_sums); cudaFree(g.d_rowmask);
     g = GridIndex();
 }
 
@@ -195,10 +214,15 @@ static float auto_scale_from_env()
     return v > 0.f ? v : 1.5f;
 }
 
-// every `stride`-th point of the cloud: the decimated set behind the coarse seeding index
+// One point out of every `stride` consecutive ones, at a pseudo-random offset inside its group: the
+// decimated set behind the coarse seeding index.  (A fixed offset would keep whole image columns of an
+// organised cloud and leave 16-pixel gaps between them; the hashed offset gives an isotropic subsample.)
 __global__ void __launch_bounds__(256) decimate_kernel(const float4 *__restrict__ pts, int n_out, int stride, float4 *__restrict__ out)
 {
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_out; i += gridDim.x * blockDim.x) out[i] = pts[(size_t)i * stride];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_out; i += gridDim.x * blockDim.x) {
+        const uint32_t off = (uint32_t)(s3d_mix((uint64_t)i) % (uint64_t)stride);
+        out[i] = pts[(size_t)i * stride + off];
+    }
 }
 
 // Build (or rebuild) an index over n device points.  max_cells bounds the dense cell array.
@@ -207,7 +231,6 @@ static int grid_build_raw(s3d_ctx *ctx, GridIndex &g, const float4 *d_pts, const
 {
     size_t np = (size_t)(n > 0 ? n : 1);
     if (g.cap_points < n || g.cap_cells < max_cells || !g.d_params) {
-        bool had_nrm = g.d_sorted_nrm != nullptr;
         s3d_grid_free(g);
         S3D_CUDA(ctx, cudaMalloc(&g.d_params, sizeof(GridParams)));
         S3D_CUDA(ctx, cudaMalloc(&g.d_cell_start, sizeof(uint32_t) * ((size_t)max_cells + 16)));
@@ -215,18 +238,18 @@ static int grid_build_raw(s3d_ctx *ctx, GridIndex &g, const float4 *d_pts, const
         S3D_CUDA(ctx, cudaMalloc(&g.d_rank, sizeof(uint32_t) * np));
         S3D_CUDA(ctx, cudaMalloc(&g.d_bbox, sizeof(uint32_t) * 8));
         S3D_CUDA(ctx, cudaMalloc(&g.d_block_sums, sizeof(uint32_t) * (max_cells / SCAN_TILE + 8)));
+        S3D_CUDA(ctx, cudaMalloc(&g.d_rowmask, sizeof(uint32_t) * ((size_t)max_cells / 8 + 8192)));
         g.cap_points = n; g.cap_cells = max_cells;
-        (void)had_nrm;
     }
     if (d_nrm && !g.d_sorted_nrm) S3D_CUDA(ctx, cudaMalloc(&g.d_sorted_nrm, sizeof(float4) * (size_t)(g.cap_points > 0 ? g.cap_points : 1)));
     cudaStream_t st = ctx->stream;
     const int wide = ctx->sm_count * 8;
     const int scan_blocks = (int)(max_cells / SCAN_TILE) + 1;
     bbox_init_kernel<<<1, 32, 0, st>>>(g.d_bbox); S3D_LAUNCHED(ctx);
-    if (n > 0) { bbox_kernel<<<std::min(wide, (n + 255) / 256), 256, 0, st>>>(d_pts, n, g.d_bbox); S3D_LAUNCHED(ctx); }
+    if (n > 0) { bbox_kernel<<<std::min(ctx->sm_count * 2, (n + 255) / 256), 256, 0, st>>>(d_pts, n, g.d_bbox); S3D_LAUNCHED(ctx); }
     grid_setup_kernel<<<1, 32, 0, st>>>(g.d_bbox, n, cell, scale, max_cells, g.d_params); S3D_LAUNCHED(ctx);
-    grid_zero_kernel<<<std::min(wide, (int)(max_cells / 1024) + 1), 256, 0, st>>>(g.d_cell_start, g.d_params); S3D_LAUNCHED(ctx);
-    if (n > 0) { grid_count_kernel<<<std::min(wide, (n + 255) / 256), 256, 0, st>>>(d_pts, n, g.d_params, g.d_cell_start, g.d_rank); S3D_LAUNCHED(ctx); }
+    grid_zero_kernel<<<std::min(wide, (int)(max_cells / 1024) + 1), 256, 0, st>>>(g.d_cell_start, g.d_rowmask, g.d_params); S3D_LAUNCHED(ctx);
+    if (n > 0) { grid_count_kernel<<<std::min(wide, (n + 255) / 256), 256, 0, st>>>(d_pts, n, g.d_params, g.d_cell_start, g.d_rank, g.d_rowmask); S3D_LAUNCHED(ctx); }
     grid_scan_reduce_kernel<<<scan_blocks, SCAN_BLOCK, 0, st>>>(g.d_cell_start, g.d_params, g.d_block_sums); S3D_LAUNCHED(ctx);
     compact_scan_kernel<<<1, 1024, 0, st>>>(g.d_block_sums, scan_blocks, g.d_block_sums + scan_blocks); S3D_LAUNCHED(ctx);
     grid_scan_apply_kernel<<<scan_blocks, SCAN_BLOCK, 0, st>>>(g.d_cell_start, g.d_params, g.d_block_sums); S3D_LAUNCHED(ctx);

@@ -24,150 +24,10 @@
 #include "grid.cuh"
 
 #define ICP_BLOCK 256
+#ifndef ICP_MIN_BLOCKS
 #define ICP_MIN_BLOCKS 4      // 64 registers per thread: 32 warps per SM hide the gather latency
-#define GRID_MARGIN 1e-3f     // cell-coordinate rounding allowance (see DESIGN.md "exactness of the ring search")
-
-// ------------------------------------------------------------------------------------------------
-// exact NN on the grid
-// ------------------------------------------------------------------------------------------------
-// The kernel is bound by the latency of dependent gathers, not by bandwidth, so the search is built
-// to need few dependent round trips: candidates are loaded four at a time, and a query normally
-// starts from a *seed* (its correspondence of the previous iteration, or on the first iteration the
-// nearest point of a 16x decimated copy of the target) whose distance bounds the ball that has to be
-// searched.  A seed is only ever used as an upper bound, so the result is still the exact argmin.
-__device__ __forceinline__ float axis_gap(float t, int d)
-{
-    float g = d > 0 ? ((float)d - t) : (d < 0 ? (t - (float)d - 1.0f) : 0.0f);
-    return fmaxf(g - GRID_MARGIN, 0.0f);
-}
-
-__device__ __forceinline__ void nn_update(const float4 q, uint32_t k, float px, float py, float pz, float &bd, int &bpos, int &bidx)
-{
-    float d2 = s3d_dist2(px, py, pz, q.x, q.y, q.z);
-    int qi = __float_as_int(q.w);
-    if (d2 < bd || (d2 == bd && qi < bidx)) { bd = d2; bpos = (int)k; bidx = qi; }
-}
-
-// candidates [s,e) of the cell-sorted array, four independent loads in flight per step; the clamped
-// tail re-reads element e-1, which cannot change the result
-__device__ __forceinline__ void scan_range(const float4 *__restrict__ sp, uint32_t s, uint32_t e, float px, float py, float pz,
-                                           float &bd, int &bpos, int &bidx)
-{
-    for (uint32_t k = s; k < e; k += 4) {
-        const uint32_t k1 = min(k + 1, e - 1), k2 = min(k + 2, e - 1), k3 = min(k + 3, e - 1);
-        const float4 q0 = __ldg(&sp[k]), q1 = __ldg(&sp[k1]), q2 = __ldg(&sp[k2]), q3 = __ldg(&sp[k3]);
-        nn_update(q0, k, px, py, pz, bd, bpos, bidx);
-        nn_update(q1, k1, px, py, pz, bd, bpos, bidx);
-        nn_update(q2, k2, px, py, pz, bd, bpos, bidx);
-        nn_update(q3, k3, px, py, pz, bd, bpos, bidx);
-    }
-}
-
-struct CellPos { int cx, cy, cz; float tx, ty, tz; };
-__device__ __forceinline__ CellPos cell_pos(const GridParams &gp, float px, float py, float pz)
-{
-    CellPos c;
-    const float fx = grid_fcoord(px, gp.ox, gp.inv_cell), fy = grid_fcoord(py, gp.oy, gp.inv_cell), fz = grid_fcoord(pz, gp.oz, gp.inv_cell);
-    c.cx = grid_clampi(fx, gp.nx); c.cy = grid_clampi(fy, gp.ny); c.cz = grid_clampi(fz, gp.nz);
-    c.tx = fx - (float)c.cx; c.ty = fy - (float)c.cy; c.tz = fz - (float)c.cz;
-    return c;
-}
-
-// one row (fixed y,z) of cells: the x-run that intersects the ball of squared radius lim is one
-// contiguous range of the sorted array
-__device__ __forceinline__ void ball_row(const GridParams &gp, const uint32_t *__restrict__ cs, const float4 *__restrict__ sp,
-                                         const CellPos &c, int y, int z, float row2, float inv_cell2, float px, float py, float pz,
-                                         float &lim, float &bd, int &bpos, int &bidx)
-{
-    const float ext = sqrtf(fmaxf(lim * inv_cell2 - row2, 0.f)) + GRID_MARGIN;
-    const int xa = max(c.cx + __float2int_rd(c.tx - ext), 0), xb = min(c.cx + __float2int_rd(c.tx + ext), gp.nx - 1);
-    if (xa > xb) return;
-    const int row = (z * gp.ny + y) * gp.nx;
-    const uint32_t s = __ldg(&cs[row + xa]), e = __ldg(&cs[row + xb + 1]);
-    scan_range(sp, s, e, px, py, pz, bd, bpos, bidx);
-    lim = fminf(lim, bd);
-}
-
-// exact NN given an upper bound `lim` (exclusive) on its squared distance: only the cells that
-// intersect the ball are visited, home row first
-__device__ __forceinline__ void grid_nn_ball(const GridParams &gp, const uint32_t *__restrict__ cs, const float4 *__restrict__ sp,
-                                             float px, float py, float pz, float lim, float &bd, int &bpos)
-{
-    const CellPos c = cell_pos(gp, px, py, pz);
-    const float cell2 = gp.cell * gp.cell, inv_cell2 = gp.inv_cell * gp.inv_cell;
-    bd = INFINITY; bpos = -1;
-    int bidx = 0x7fffffff;
-    ball_row(gp, cs, sp, c, c.cy, c.cz, 0.f, inv_cell2, px, py, pz, lim, bd, bpos, bidx);   // home row first: it usually holds the answer
-    const float Rc = sqrtf(lim * inv_cell2) + GRID_MARGIN;
-    const int z0 = max(c.cz + __float2int_rd(c.tz - Rc), 0), z1 = min(c.cz + __float2int_rd(c.tz + Rc), gp.nz - 1);
-    const int y0 = max(c.cy + __float2int_rd(c.ty - Rc), 0), y1 = min(c.cy + __float2int_rd(c.ty + Rc), gp.ny - 1);
-    for (int z = z0; z <= z1; ++z) {
-        const float gz = axis_gap(c.tz, z - c.cz);
-        if (gz * gz * cell2 >= lim) continue;
-        for (int y = y0; y <= y1; ++y) {
-            if (y == c.cy && z == c.cz) continue;
-            const float gy = axis_gap(c.ty, y - c.cy);
-            const float row2 = gy * gy + gz * gz;
-            if (row2 * cell2 >= lim) continue;
-            ball_row(gp, cs, sp, c, y, z, row2, inv_cell2, px, py, pz, lim, bd, bpos, bidx);
-        }
-    }
-}
-
-// exact NN without a bound: shells of growing Chebyshev radius around the home cell until the best
-// distance is closer than the nearest unexplored cell.  Used for the coarse seeding index, for small
-// targets and when a query has no seed.
-__device__ __forceinline__ void grid_nn_ring(const GridParams &gp, const uint32_t *__restrict__ cs, const float4 *__restrict__ sp,
-                                             float px, float py, float pz, float &bd, int &bpos)
-{
-    const CellPos c = cell_pos(gp, px, py, pz);
-    const int cx = c.cx, cy = c.cy, cz = c.cz;
-    const float tx = c.tx, ty = c.ty, tz = c.tz;
-    const float cell2 = gp.cell * gp.cell, inv_cell2 = gp.inv_cell * gp.inv_cell;
-    bd = INFINITY; bpos = -1;
-    int bidx = 0x7fffffff;
-    if (gp.n_points == 0) return;
-    for (int r = 0;; ++r) {
-        const int z0 = max(cz - r, 0), z1 = min(cz + r, gp.nz - 1);
-        const int y0 = max(cy - r, 0), y1 = min(cy + r, gp.ny - 1);
-        for (int z = z0; z <= z1; ++z) {
-            const float gz = axis_gap(tz, z - cz);
-            const bool zedge = (z - cz == r) || (cz - z == r);
-            for (int y = y0; y <= y1; ++y) {
-                const float gy = axis_gap(ty, y - cy);
-                const float row2 = gy * gy + gz * gz;
-                if (row2 * cell2 >= bd) continue;
-                int xa = cx - r, xb = cx + r;
-                if (bd < INFINITY) {
-                    float ext = sqrtf(fmaxf(bd * inv_cell2 - row2, 0.f)) + GRID_MARGIN;
-                    xa = max(xa, cx + __float2int_rd(tx - ext));
-                    xb = min(xb, cx + __float2int_rd(tx + ext));
-                }
-                xa = max(xa, 0); xb = min(xb, gp.nx - 1);
-                const int row = (z * gp.ny + y) * gp.nx;
-                const bool edge = zedge || (y - cy == r) || (cy - y == r);
-                if (edge) {
-                    if (xa <= xb) scan_range(sp, __ldg(&cs[row + xa]), __ldg(&cs[row + xb + 1]), px, py, pz, bd, bpos, bidx);
-                } else {
-                    const int xl = cx - r, xh = cx + r; // interior row of the shell: only the two end cells are new
-                    if (xl >= xa && xl <= xb) scan_range(sp, __ldg(&cs[row + xl]), __ldg(&cs[row + xl + 1]), px, py, pz, bd, bpos, bidx);
-                    if (xh >= xa && xh <= xb && xh != xl) scan_range(sp, __ldg(&cs[row + xh]), __ldg(&cs[row + xh + 1]), px, py, pz, bd, bpos, bidx);
-                }
-            }
-        }
-        float gap = INFINITY;
-        bool covered = true;
-        if (cx - r > 0) { gap = fminf(gap, tx + (float)r); covered = false; }
-        if (cx + r < gp.nx - 1) { gap = fminf(gap, (float)(r + 1) - tx); covered = false; }
-        if (cy - r > 0) { gap = fminf(gap, ty + (float)r); covered = false; }
-        if (cy + r < gp.ny - 1) { gap = fminf(gap, (float)(r + 1) - ty); covered = false; }
-        if (cz - r > 0) { gap = fminf(gap, tz + (float)r); covered = false; }
-        if (cz + r < gp.nz - 1) { gap = fminf(gap, (float)(r + 1) - tz); covered = false; }
-        if (covered) break;
-        gap = fmaxf(gap - GRID_MARGIN, 0.f);
-        if (bd < gap * gap * cell2) break;
-    }
-}
+#endif
+#include "search.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // brute-force exact NN: target tiles staged in shared memory by TMA bulk copies
@@ -373,7 +233,7 @@ __device__ void solve_and_update(const double *acc, PairState *st, int min_corr,
         for (int c = 0; c < 3; ++c) O[4 * r + c] = D[4 * r] * T[c] + D[4 * r + 1] * T[4 + c] + D[4 * r + 2] * T[8 + c];
         O[4 * r + 3] = D[4 * r] * T[3] + D[4 * r + 1] * T[7] + D[4 * r + 2] * T[11] + D[4 * r + 3];
     }
-    for (int k = 0; k < 12; ++k) { st->T[k] = O[k]; st->Tf[k] = (float)O[k]; }
+    for (int k = 0; k < 12; ++k) { st->T[k] = O[k]; st->Tf_prev[k] = st->Tf[k]; st->Tf[k] = (float)O[k]; }
     st->iterations += 1;
 }
 
@@ -415,12 +275,13 @@ __device__ __forceinline__ void accumulate(float *acc, float px, float py, float
 template <int EST, int SEARCH>
 __global__ void __launch_bounds__(ICP_BLOCK, ICP_MIN_BLOCKS) icp_iter_kernel(const PairDesc *__restrict__ descs, PairState *__restrict__ states,
                                                                              double *__restrict__ partials, const int32_t *__restrict__ nn_idx,
-                                                                             int32_t *__restrict__ nn_pos, int nn_stride, int use_seed,
+                                                                             int32_t *__restrict__ nn_pos, float *__restrict__ nn_lb, int nn_stride, int use_seed,
                                                                              float max_d2, int min_corr, double pivot_eps,
                                                                              int32_t *__restrict__ nn_out)
 {
     __shared__ double wsum[ICP_BLOCK / 32][S3D_NACC];
     __shared__ double tail[8][S3D_NACC];
+    __shared__ uint2 rq[RANGE_QCAP * ICP_BLOCK];   // per-thread queues of candidate ranges (search.cuh)
     __shared__ bool is_last;
     const int pair = blockIdx.y;
     PairState *st = states + pair;
@@ -433,26 +294,124 @@ __global__ void __launch_bounds__(ICP_BLOCK, ICP_MIN_BLOCKS) icp_iter_kernel(con
     int32_t *my_pos = nn_pos + (size_t)pair * nn_stride;
 
     // ---- phase 1: exact nearest neighbour of every transformed source point (grid search) ----------
+    // A query keeps, between iterations, its correspondence and a lower bound `lb` on its distance to
+    // every OTHER target point.  When the pose update moved the point by less than the slack between the
+    // two, the old correspondence is provably still the exact argmin and the search is skipped (triangle
+    // inequality).  The rest are searched 4 at a time by groups of 8 lanes (search.cuh), in an order
+    // (lanes 0,8,16,24 first, then the lanes between them, ...) that lets every query start from the
+    // results of its already finished neighbours.
     if (SEARCH == S3D_SEARCH_GRID) {
         const GridParams gp = *d.grid;
+        const GridView fine = {d.grid, d.cell_start, d.rowmask, d.sorted_pts};
+        const bool have_coarse = !use_seed && d.coarse_grid != nullptr;
+        GridParams cgp = gp;
+        if (have_coarse) cgp = *d.coarse_grid;
+        const GridView coarse = {d.coarse_grid, d.coarse_cell_start, d.coarse_rowmask, d.coarse_pts};
+        float *my_lb = nn_lb + (size_t)pair * nn_stride;
+        float Tp[12];
+        #pragma unroll
+        for (int k = 0; k < 12; ++k) Tp[k] = st->Tf_prev[k];
         const float gate = max_d2 < INFINITY ? max_d2 * 1.00001f + 1e-30f : INFINITY;
-        for (int i = tid0; i < d.n_src; i += tstride) {
-            const float4 p = d.src[i];
-            const float3 x = s3d_xform(T, p.x, p.y, p.z);
-            float lim = INFINITY;
-            if (use_seed) {
-                const int sp_ = my_pos[i];
-                if (sp_ >= 0) { const float4 q = __ldg(&d.sorted_pts[sp_]); lim = s3d_dist2(x.x, x.y, x.z, q.x, q.y, q.z) * 1.00001f + 1e-30f; }
-            } else if (d.coarse_grid) {
-                float cd; int cpos;
-                grid_nn_ring(*d.coarse_grid, d.coarse_cell_start, d.coarse_pts, x.x, x.y, x.z, cd, cpos);
-                if (cpos >= 0) lim = cd * 1.00001f + 1e-30f;
+        const float slack0 = 0.2f * gp.cell, half_cell = 0.5f * gp.cell;
+        const unsigned full = 0xffffffffu;
+        const int lane = threadIdx.x & 31;
+        for (int base = tid0 - lane; base < d.n_src; base += tstride) {      // warp-uniform: 32 consecutive queries
+            const int i = base + lane;
+            const bool in = i < d.n_src;
+            float3 x = make_float3(0.f, 0.f, 0.f);
+            float own_lim = INFINITY, rqx = 0.f, rqy = 0.f, rqz = 0.f, rlb = 0.f;
+            int rpos = -1;
+            bool pending = false, has_res = false, store_pos = false;
+            if (in) {
+                const float4 p = d.src[i];
+                x = s3d_xform(T, p.x, p.y, p.z);
+                pending = true; store_pos = true;
+                if (use_seed) {
+                    const int sp_ = my_pos[i];
+                    if (sp_ >= 0) {
+                        const float4 q = __ldg(&d.sorted_pts[sp_]);
+                        const float d2q = s3d_dist2(x.x, x.y, x.z, q.x, q.y, q.z);
+                        const float3 xo = s3d_xform(Tp, p.x, p.y, p.z);
+                        const float moved = sqrtf(s3d_dist2(x.x, x.y, x.z, xo.x, xo.y, xo.z)) * 1.000002f + 5e-8f;
+                        const float lb = my_lb[i] - moved;
+                        rqx = q.x; rqy = q.y; rqz = q.z; rpos = sp_; has_res = true;   // a real target point: also a seed for the neighbours
+                        if (sqrtf(d2q) * 1.000002f + 2e-7f < lb) { rlb = lb; pending = false; store_pos = false; STAT(1, 1); }   // still the exact NN
+                        else own_lim = seed_limit(d2q, slack0, half_cell);
+                    }
+                } else if (d.n_tgt > 0) {
+                    // first iteration: the target point at the same relative index is the first upper bound
+                    const int j0 = (int)(((long long)i * d.n_tgt) / d.n_src);
+                    const float4 q = __ldg(&d.tgt[j0]);
+                    own_lim = seed_limit(s3d_dist2(x.x, x.y, x.z, q.x, q.y, q.z), slack0, half_cell);
+                }
+                own_lim = fminf(own_lim, gate);   // nothing beyond the correspondence gate can be accepted anyway
             }
-            lim = fminf(lim, gate);   // nothing beyond the correspondence gate can be accepted anyway
-            float bd; int bpos;
-            if (lim < INFINITY) grid_nn_ball(gp, d.cell_start, d.sorted_pts, x.x, x.y, x.z, lim, bd, bpos);
-            else grid_nn_ring(gp, d.cell_start, d.sorted_pts, x.x, x.y, x.z, bd, bpos);
-            my_pos[i] = bpos;
+            const unsigned pend = __ballot_sync(full, pending);
+            const unsigned resmask = __ballot_sync(full, has_res);
+            // Own bound tightened by the correspondences of the neighbouring lanes (adjacent source points have
+            // adjacent nearest neighbours) and by the nearest point of the query's own cell.
+            float lim = own_lim;
+            #pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int nl = lane + ((k & 1) ? 1 : -1) * (1 << (k >> 1));
+                const bool ok = nl >= 0 && nl < 32 && ((resmask >> (nl & 31)) & 1u);
+                const int nlc = ok ? nl : lane;
+                const float nx = __shfl_sync(full, rqx, nlc), ny = __shfl_sync(full, rqy, nlc), nz = __shfl_sync(full, rqz, nlc);
+                if (ok && pending) lim = fminf(lim, seed_limit(s3d_dist2(x.x, x.y, x.z, nx, ny, nz), slack0, half_cell));
+            }
+            if (pending) {
+                const float hd = home_cell_probe(fine, gp, x.x, x.y, x.z);
+                if (hd < INFINITY) lim = fminf(lim, seed_limit(hd, slack0, half_cell));
+            }
+            // Work classes.  A search whose ball spans many rows of cells ("big") would keep its lane busy long after the
+            // others are done; unless most of the warp is in that state, big searches are done one after the other by
+            // the whole warp (32 rows per round), the small ones all at once, one per lane.
+            const float rc_est = 2.f * sqrtf(lim) * gp.inv_cell + 1.f;
+            const bool big_q = pending && (!(lim < INFINITY) || rc_est * rc_est > 24.f || have_coarse);
+            unsigned bigm = __ballot_sync(full, big_q);
+            if (__popc(pend) <= COOP) bigm = pend;
+            else if (__popc(bigm) > 16) bigm = 0u;
+            const bool mine_small = pending && !((bigm >> lane) & 1u);
+#ifdef S3D_STATS
+            {
+                float rr = mine_small ? rc_est * rc_est : 0.f;
+                float mx = rr;
+                for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(full, mx, o));
+                STAT(7, lane == 0 ? (unsigned long long)mx : 0ull);
+                STAT(8, (unsigned long long)rr);
+                STAT(9, (bigm >> lane) & 1u);
+                STAT(10, lane == 0 && (pend & ~bigm));
+                STAT(11, lane == 0 && pend);
+            }
+#endif
+            if (pend & ~bigm) {
+                if (have_coarse) {
+                    Best cb; float clim = lim;
+                    STAT(6, mine_small);
+                    ball_search_lane(coarse, cgp, x.x, x.y, x.z, clim, cb, mine_small, rq + threadIdx.x, ICP_BLOCK);
+                    if (cb.bpos >= 0) lim = fminf(lim, seed_limit(cb.bd, slack0, half_cell));
+                }
+                Best b;
+                STAT(0, mine_small);
+                ball_search_lane(fine, gp, x.x, x.y, x.z, lim, b, mine_small, rq + threadIdx.x, ICP_BLOCK);
+                if (mine_small) { rpos = b.bpos; rlb = sqrtf(lim) * 0.999998f - 5e-8f; }   // lim already follows the runner-up
+            }
+            for (unsigned pm = bigm; pm; pm &= pm - 1) {
+                const int ol = __ffs(pm) - 1;
+                const float qx = __shfl_sync(full, x.x, ol), qy = __shfl_sync(full, x.y, ol), qz = __shfl_sync(full, x.z, ol);
+                float wl = __shfl_sync(full, lim, ol);
+                if (have_coarse) {
+                    Best cb; float clim = wl;
+                    STAT(6, lane == 0);
+                    ball_search<32, 1>(coarse, cgp, qx, qy, qz, clim, cb, full, lane, true);
+                    if (cb.bpos >= 0) wl = fminf(wl, seed_limit(cb.bd, slack0, half_cell));
+                }
+                Best b;
+                STAT(0, lane == 0);
+                ball_search<32, 1>(fine, gp, qx, qy, qz, wl, b, full, lane, true);
+                if (lane == ol) { rpos = b.bpos; rlb = sqrtf(wl) * 0.999998f - 5e-8f; }
+            }
+            if (in) { my_lb[i] = rlb; if (store_pos) my_pos[i] = rpos; }
         }
     }
 
@@ -580,7 +539,7 @@ template <int EST, int SEARCH>
 static void launch_iter(s3d_ctx *ctx, dim3 grid, int nn_stride, int use_seed, float max_d2, int min_corr, double pivot_eps, int32_t *nn_out)
 {
     icp_iter_kernel<EST, SEARCH><<<grid, ICP_BLOCK, 0, ctx->stream>>>(ctx->d_desc, ctx->d_state, ctx->d_partials, ctx->d_nn_idx,
-                                                                      ctx->d_nn_pos, nn_stride, use_seed, max_d2, min_corr, pivot_eps, nn_out);
+                                                                      ctx->d_nn_pos, ctx->d_nn_d2, nn_stride, use_seed, max_d2, min_corr, pivot_eps, nn_out);
 }
 
 extern "C" int s3d_register_batch(s3d_ctx *ctx, const s3d_cloud *const *src, const s3d_cloud *const *tgt,
@@ -648,10 +607,11 @@ extern "C" int s3d_register_batch(s3d_ctx *ctx, const s3d_cloud *const *src, con
         d.src = src[i]->d_pts; d.n_src = src[i]->n;
         d.tgt = tgt[i]->d_pts; d.tgt_nrm = tgt[i]->d_nrm; d.n_tgt = tgt[i]->n;
         d.sorted_pts = tgt[i]->grid.d_sorted_pts; d.sorted_nrm = tgt[i]->grid.d_sorted_nrm;
-        d.cell_start = tgt[i]->grid.d_cell_start; d.grid = tgt[i]->grid.d_params;
+        d.cell_start = tgt[i]->grid.d_cell_start; d.grid = tgt[i]->grid.d_params; d.rowmask = tgt[i]->grid.d_rowmask;
         const bool coarse = use_grid && tgt[i]->coarse.valid;
         d.coarse_pts = coarse ? tgt[i]->coarse.d_sorted_pts : nullptr;
         d.coarse_cell_start = coarse ? tgt[i]->coarse.d_cell_start : nullptr;
+        d.coarse_rowmask = coarse ? tgt[i]->coarse.d_rowmask : nullptr;
         d.coarse_grid = coarse ? tgt[i]->coarse.d_params : nullptr;
         PairState &s = ctx->h_state[i];
         memset(&s, 0, sizeof(s));
@@ -733,3 +693,13 @@ extern "C" int s3d_last_timing(const s3d_ctx *ctx, s3d_timing *out)
     *out = ctx->timing;
     return S3D_OK;
 }
+
+#ifdef S3D_STATS
+extern "C" int s3d_debug_stats(unsigned long long *out16, int reset)
+{
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out16, g_stats, sizeof(unsigned long long) * 16);
+    if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(g_stats, z, sizeof(z)); }
+    return 0;
+}
+#endif
