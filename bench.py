@@ -159,18 +159,15 @@ def main():
         src.append(ctx.upload(p["src"]))
         tgt.append(ctx.upload(p["tgt"], p["tgt_normals"]))
     prm = _abi.icp_params(ITERS, reuse_index=0)
+    from slam3d_gx_b200 import sharding
     rec_bytes = _abi.RESULT_BYTES
-    gather_in = torch.zeros(rec_bytes, dtype=torch.uint8, device="cuda")
-    gather_out = torch.zeros(world * rec_bytes, dtype=torch.uint8, device="cuda") if world > 1 else None
-    pinned_rec = torch.zeros(rec_bytes, dtype=torch.uint8).pin_memory()
 
     def step(i):
         k = i % args.pool
         res = ctx.register_batch([src[k]], [tgt[k]], None, prm, raw=True)
-        if world > 1:   # pose gather: the only collective of the path
-            pinned_rec.numpy()[:] = np.frombuffer(bytes(res[0]), dtype=np.uint8)
-            gather_in.copy_(pinned_rec, non_blocking=True)
-            dist.all_gather_into_tensor(gather_out, gather_in)
+        if world > 1:   # pose gather over NCCL: the only collective of the path
+            allr = sharding.gather_results([res[0]], world, dist, device="cuda")
+            assert len(allr) == world
         return res[0]
 
     for k in range(args.pool):      # prime every pair once (first-use device allocations of its index), untimed

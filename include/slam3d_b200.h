@@ -71,7 +71,7 @@ typedef struct s3d_icp_params {
 } s3d_icp_params;
 
 /* Result record: what RESULT_OF_MULTIPNP{T,norm,inliers} (src/GraphicEnd.h:59-69) carries, plus
- * diagnostics.  96+32 bytes, POD, the unit gathered across GPUs. */
+ * diagnostics.  160 bytes, POD, the unit gathered across GPUs. */
 typedef struct s3d_result {
     double  T[16];        /* row-major 4x4, source -> target */
     double  norm;         /* |min(theta,2pi-theta)| + 0.9*|t|   (src/GraphicEnd.cpp:618) */

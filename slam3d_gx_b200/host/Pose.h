@@ -1,0 +1,47 @@
+// Pose.h -- the little of Eigen::Isometry3d the front end uses (reference src/GraphicEnd.h:13-14):
+// identity, product, inverse, exact comparison with identity (the failure convention, src/GraphicEnd.cpp:173),
+// and conversion to the translation + unit quaternion that g2o's text format stores.
+#pragma once
+#include <cmath>
+#include <cstring>
+
+struct Isometry3d {
+    double m[16];   // row-major 4x4
+    Isometry3d() { setIdentity(); }
+    static Isometry3d Identity() { return Isometry3d(); }
+    void setIdentity() { std::memset(m, 0, sizeof(m)); m[0] = m[5] = m[10] = m[15] = 1.0; }
+    bool isIdentity() const { Isometry3d I; return std::memcmp(m, I.m, sizeof(m)) == 0; }   // T.matrix() == Identity
+    double &operator()(int r, int c) { return m[4 * r + c]; }
+    double operator()(int r, int c) const { return m[4 * r + c]; }
+    Isometry3d operator*(const Isometry3d &o) const
+    {
+        Isometry3d r;
+        for (int i = 0; i < 3; ++i) {
+            for (int j = 0; j < 4; ++j) {
+                double s = 0;
+                for (int k = 0; k < 3; ++k) s += m[4 * i + k] * o.m[4 * k + j];
+                r.m[4 * i + j] = s + (j == 3 ? m[4 * i + 3] : 0.0);
+            }
+        }
+        return r;
+    }
+    Isometry3d inverse() const
+    {
+        Isometry3d r;
+        for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) r.m[4 * i + j] = m[4 * j + i];
+        for (int i = 0; i < 3; ++i) r.m[4 * i + 3] = -(r.m[4 * i] * m[3] + r.m[4 * i + 1] * m[7] + r.m[4 * i + 2] * m[11]);
+        return r;
+    }
+    // unit quaternion (qx,qy,qz,qw), qw >= 0
+    void quaternion(double q[4]) const
+    {
+        double tr = m[0] + m[5] + m[10];
+        double qw, qx, qy, qz;
+        if (tr > 0) { double s = std::sqrt(tr + 1.0) * 2; qw = 0.25 * s; qx = (m[9] - m[6]) / s; qy = (m[2] - m[8]) / s; qz = (m[4] - m[1]) / s; }
+        else if (m[0] > m[5] && m[0] > m[10]) { double s = std::sqrt(1.0 + m[0] - m[5] - m[10]) * 2; qw = (m[9] - m[6]) / s; qx = 0.25 * s; qy = (m[1] + m[4]) / s; qz = (m[2] + m[8]) / s; }
+        else if (m[5] > m[10]) { double s = std::sqrt(1.0 + m[5] - m[0] - m[10]) * 2; qw = (m[2] - m[8]) / s; qx = (m[1] + m[4]) / s; qy = 0.25 * s; qz = (m[6] + m[9]) / s; }
+        else { double s = std::sqrt(1.0 + m[10] - m[0] - m[5]) * 2; qw = (m[4] - m[1]) / s; qx = (m[2] + m[8]) / s; qy = (m[6] + m[9]) / s; qz = 0.25 * s; }
+        if (qw < 0) { qw = -qw; qx = -qx; qy = -qy; qz = -qz; }
+        q[0] = qx; q[1] = qy; q[2] = qz; q[3] = qw;
+    }
+};

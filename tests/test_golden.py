@@ -1,0 +1,98 @@
+"""Golden fixtures (tests/golden, produced by tests/golden/make_golden.py): known-answer poses from the independent
+scipy/numpy float64 implementation, and the reference's real Kinect pair (subsampled).  The oracle is checked on CPU,
+the CUDA path on the GPU box."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+from slam3d_gx_b200 import synth, _abi
+from oracle import oracle
+from conftest import pose_close
+
+HERE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+CASES = json.load(open(os.path.join(HERE, "icp_golden.json")))
+TOL = {"plane": (1e-6, 1e-6), "svd": (2e-5, 2e-5)}     # oracle (float32 correspondences) vs float64 reference
+
+
+def _inputs(c):
+    cam = synth.Camera().scaled(c["scale"])
+    kw = {k: (tuple(v) if isinstance(v, list) else v) for k, v in c["kw"].items()}
+    p = synth.make_pair(c["pair"], cam=cam, **kw)
+    h = hashlib.sha256()
+    for a in (p["src"], p["tgt"], p["tgt_normals"]):
+        h.update(np.ascontiguousarray(a).tobytes())
+    return p, h.hexdigest()
+
+
+def _params(c):
+    est = _abi.ESTIMATOR_POINT_TO_PLANE if c["estimator"] == "plane" else _abi.ESTIMATOR_SVD
+    return _abi.icp_params(c["iterations"], estimator=est, max_corr_dist=c["max_corr_dist"])
+
+
+@pytest.mark.parametrize("c", CASES, ids=[c["name"] for c in CASES])
+def test_oracle_against_golden(c):
+    p, sha = _inputs(c)
+    assert (len(p["src"]), len(p["tgt"])) == (c["n_src"], c["n_tgt"])
+    if sha != c["input_sha256"]:
+        pytest.skip("synthetic inputs differ in the last bits on this platform (libm); golden pose not comparable")
+    r = oracle.icp(p["src"], p["tgt"], p["tgt_normals"], params=_params(c))
+    ok, err = pose_close(r["T"], np.array(c["T"]), *TOL[c["estimator"]])
+    assert ok, err
+    assert abs(r["inliers"] - c["inliers"]) <= 1
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("c", CASES, ids=[c["name"] for c in CASES])
+def test_cuda_against_golden(ctx, c):
+    p, sha = _inputs(c)
+    if sha != c["input_sha256"]:
+        pytest.skip("synthetic inputs differ in the last bits on this platform (libm); golden pose not comparable")
+    src, tgt = ctx.upload(p["src"]), ctx.upload(p["tgt"], p["tgt_normals"])
+    r = ctx.register(src, tgt, None, _params(c))
+    src.free(); tgt.free()
+    ok, err = pose_close(r["T"], np.array(c["T"]), 1e-4, 1e-4)      # north-star tolerance
+    assert ok, err
+    assert abs(r["inliers"] - c["inliers"]) <= 2
+
+
+def _exp1():
+    z = np.load(os.path.join(HERE, "exp1_depth_q4.npz"))
+    cam = synth.Camera(fx=525.0 / 4, fy=525.0 / 4, cx=319.5 / 4, cy=235.5 / 4, factor=1000.0, width=160, height=120)
+    return z["d1"], z["d2"], cam
+
+
+def test_real_pair_oracle_pipeline():
+    """The reference's own Kinect pair (data/exp1, subsampled): plane extraction + ICP run and agree with themselves."""
+    d1, d2, cam = _exp1()
+    assert d1.shape == (120, 160) and 0.2 < (d1 == 0).mean() < 0.35
+    src, tgt = oracle.backproject(d1, cam, 7.0), oracle.backproject(d2, cam, 7.0)
+    seg = oracle.segment_planes(tgt, _abi.plane_params())
+    assert 1 <= len(seg["planes"]) <= 3
+    r = oracle.icp(src, tgt, seg["normals"], params=_abi.icp_params(10, max_corr_dist=0.3))
+    assert r["status"] in (_abi.PAIR_OK, _abi.PAIR_DEGENERATE)
+
+
+@pytest.mark.gpu
+def test_real_pair_cuda_matches_oracle(ctx):
+    d1, d2, cam = _exp1()
+    cs, ct = ctx.from_depth(d1, cam, 7.0), ctx.from_depth(d2, cam, 7.0)
+    src, tgt = oracle.backproject(d1, cam, 7.0), oracle.backproject(d2, cam, 7.0)
+    assert np.array_equal(cs.download()["xyz"], src[:, :3]) and np.array_equal(ct.download()["xyz"], tgt[:, :3])
+    prm = _abi.plane_params()
+    planes = ct.segment_planes(prm)
+    got = ct.download(xyz=False, normals=True, labels=True)
+    seg = oracle.segment_planes(tgt, prm)
+    assert len(planes) == len(seg["planes"])
+    assert (got["labels"] != seg["labels"]).sum() <= 4
+    icp = _abi.icp_params(10, max_corr_dist=0.3)
+    r = ctx.register(cs, ct, None, icp)
+    nrm4 = np.c_[got["normals"], (got["labels"] >= 0).astype(np.float32)].astype(np.float32)
+    o = oracle.icp(src, tgt, nrm4, params=icp)
+    assert r["status"] == o["status"]
+    if o["status"] == 0:
+        ok, err = pose_close(r["T"], o["T"], 1e-4, 1e-4)
+        assert ok, err
+    cs.free(); ct.free()
