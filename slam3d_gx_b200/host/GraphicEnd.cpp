@@ -13,7 +13,7 @@ using namespace std;
 #define S3D_CHECK(call) do { int rc__ = (call); if (rc__ != S3D_OK) { cerr << BOLDRED << "slam3d_b200: " #call " failed (" << rc__ << "): " \
     << s3d_last_error(_ctx) << RESET << endl; exit(1); } } while (0)
 
-GraphicEnd::GraphicEnd() : _pSLAMEnd(0), _currCloud(0), _lost(0), _index(0), _moreLoops(0), _ctx(0)
+GraphicEnd::GraphicEnd() : _pSLAMEnd(0), _currCloud(0), _lost(0), _index(0), _moreLoops(0), _ctx(0), _have_guess(false), _use_guess(false)
 {
     g_pParaReader = new ParameterReader(parameter_file_addr);                       // :62
     int seed = atoi(g_pParaReader->GetPara("random_seed").c_str());
@@ -92,7 +92,13 @@ int GraphicEnd::run()
     readimage();
     _present.planes = extractPlanesAndGenerateImage(_currCloud);                                    // :158
 
+    // the reference registers from scratch every frame (features); an ICP tracks, so the previous frame's result
+    // (same key frame) is the initial guess
+    _use_guess = _have_guess;
     RESULT_OF_MULTIPNP result = multiPnP(_currKF.planes, _present.planes);                          // :168
+    _use_guess = false;
+    _have_guess = !result.T.isIdentity();
+    if (_have_guess) _guess = result.T;
     Isometry3d T = result.T.inverse();                                                              // :170
 
     if (T.isIdentity()) {                                                                           // :173 lost
@@ -122,6 +128,7 @@ int GraphicEnd::run()
         errorfile << result.norm << endl;
         _robot = T * _kf_pos;
         generateKeyFrame(T);
+        _have_guess = false;                                                                        // new key frame: start from identity
         if (_loop_closure_detection) loopClosure();
         _lost = 0;
         _last = _present;
@@ -233,8 +240,8 @@ RESULT_OF_MULTIPNP GraphicEnd::multiPnP(vector<PLANE> &plane1, vector<PLANE> &pl
         return RESULT_OF_MULTIPNP();
     }
     s3d_result r;
-    S3D_CHECK(s3d_register_pair(_ctx, plane1[0].cloud, plane2[0].cloud, 0, &_icp, &r));
-    cout << "Multipnp inliers = " << r.inliers << endl;
+    S3D_CHECK(s3d_register_pair(_ctx, plane1[0].cloud, plane2[0].cloud, _use_guess ? _guess.m : 0, &_icp, &r));
+    cout << "Multipnp inliers = " << r.inliers << " (status " << r.status << ", iterations " << r.iterations << ", rmse " << std::sqrt(r.fitness) << ")" << endl;
     return toResult(r, s3d_cloud_size(plane1[0].cloud), minimum_inliers);
 }
 

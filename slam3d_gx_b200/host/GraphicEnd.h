@@ -97,6 +97,8 @@ class GraphicEnd
     double _icp_max_rmse, _icp_min_inlier_ratio;
     std::vector<s3d_cloud *> _clouds;   // every cloud uploaded so far (keyframes keep theirs resident in HBM)
     std::stringstream ss;
+    bool _have_guess, _use_guess;       // tracking: last successful key-frame -> frame pose as the next initial guess
+    Isometry3d _guess;
 
  protected:
     RESULT_OF_MULTIPNP toResult(const s3d_result &r, int n_src, int minimum_inliers);

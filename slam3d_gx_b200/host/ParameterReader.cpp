@@ -2,8 +2,8 @@
 // src/ParameterReader.cpp:28-66 (27 typed fields + 5 camera globals); numeric values are re-formatted through
 // a stringstream like the reference's num2string (so "0.080" reads back as "0.08").
 // New OPTIONAL keys of the ICP backend (defaults keep the stock parameters.yaml loadable):
-//   icp_iterations (10)  icp_max_corr_dist (0 = unlimited)  icp_estimator (plane|svd)  icp_search (grid|brute)
-//   icp_grid_cell (0 = auto)  icp_max_rmse (0.05)  icp_min_inlier_ratio (0.3)  ransac_seed (12345)
+//   icp_iterations (10)  icp_max_corr_dist (0.2 m; 0 = unlimited like PCL's default)  icp_estimator (plane|svd)  icp_search (grid|brute)
+//   icp_grid_cell (0 = auto)  icp_max_rmse (0.08)  icp_min_inlier_ratio (0.3)  ransac_seed (12345)
 //   random_seed (-1 = time(0) like the reference)  use_voxel_grid (no)  gpu_device (0)
 #include "ParameterReader.h"
 #include <cstdlib>
@@ -73,8 +73,8 @@ string ParameterReader::GetPara(const string &para_name)
     for (int i = 0; strings[i]; ++i) if (para_name == strings[i]) return raw(para_name, "");
     // optional keys of the ICP backend, with defaults
     struct Opt { const char *name; const char *def; };
-    static const Opt opts[] = {{"icp_iterations", "10"}, {"icp_max_corr_dist", "0"}, {"icp_estimator", "plane"}, {"icp_search", "grid"},
-                               {"icp_grid_cell", "0"}, {"icp_max_rmse", "0.05"}, {"icp_min_inlier_ratio", "0.3"}, {"ransac_seed", "12345"},
+    static const Opt opts[] = {{"icp_iterations", "10"}, {"icp_max_corr_dist", "0.2"}, {"icp_estimator", "plane"}, {"icp_search", "grid"},
+                               {"icp_grid_cell", "0"}, {"icp_max_rmse", "0.08"}, {"icp_min_inlier_ratio", "0.3"}, {"ransac_seed", "12345"},
                                {"random_seed", "-1"}, {"use_voxel_grid", "no"}, {"gpu_device", "0"}, {0, 0}};
     for (int i = 0; opts[i].name; ++i) if (para_name == opts[i].name) return raw(para_name, opts[i].def);
     cerr << "Unknown parameter: " << para_name << endl;

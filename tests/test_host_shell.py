@@ -90,7 +90,7 @@ def test_run_slam_end_to_end(tmp_path):
     subprocess.run(["make", "-C", HOST, "-s"], check=True, env={**os.environ, "CXX": "g++", "CC": "gcc"})
     cam = synth.Camera().scaled(0.25)
     n_frames = 13
-    D = synth.make_T(synth.rot_axis_angle([0.2, 1.0, 0.1], 0.025), [0.035, -0.01, 0.02])    # camera motion per frame
+    D = synth.make_T(synth.rot_axis_angle([0.1, 1.0, 0.05], -0.012), [0.03, -0.01, 0.025])    # camera motion per frame (norm ~0.05)
     poses = [synth.base_pose()]
     for k in range(1, n_frames):
         poses.append(poses[-1] @ D)
