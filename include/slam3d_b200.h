@@ -49,8 +49,10 @@ enum {
 
 enum { S3D_ESTIMATOR_POINT_TO_PLANE = 0,   /* PCL TransformationEstimationPointToPlaneLLS */
        S3D_ESTIMATOR_SVD = 1 };            /* PCL TransformationEstimationSVD (Kabsch/Umeyama) */
-enum { S3D_SEARCH_GRID = 0,                /* exact NN on a device-built uniform grid (default) */
-       S3D_SEARCH_BRUTE = 1 };             /* exact NN, brute force over TMA-staged target tiles */
+enum { S3D_SEARCH_GRID = 0,                /* exact NN on a device-built uniform grid, shared-memory tiles, one
+                                              persistent launch for all iterations (default) */
+       S3D_SEARCH_BRUTE = 1,               /* exact NN, brute force over TMA-staged target tiles */
+       S3D_SEARCH_GRID_LANE = 2 };         /* exact NN on the grid, per-lane ball search, one launch per iteration */
 
 typedef struct s3d_ctx s3d_ctx;
 typedef struct s3d_cloud s3d_cloud;

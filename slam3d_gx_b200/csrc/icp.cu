@@ -8,13 +8,21 @@
 //                   A += J^T J, g += J^T r  with J = [X x n ; n], r = n.(Q - X)     (LLS)
 //                   or  sums for Kabsch                                            (SVD)
 //                   T <- dT * T
-// One kernel launch per iteration: every CTA reduces its 29 accumulators (warp shuffles, then
-// double precision across warps), writes one partial row, and the last CTA to finish (atomic
-// ticket) sums the rows in a fixed order, solves in double and publishes the new pose, so the
-// iteration loop never returns to the host.  Two exact search back ends share that epilogue:
-//   S3D_SEARCH_GRID   ring search on the uniform grid of grid.cu (O(1) candidates per query)
-//   S3D_SEARCH_BRUTE  all targets streamed through shared memory by TMA bulk copies
-//                     (cp.async.bulk + mbarrier), 4 sources per thread in registers
+// Three exact search back ends (bit-identical results, tests/test_gpu_parity.py):
+//   S3D_SEARCH_GRID       (default) icp_persist_kernel: ONE cooperative launch runs every iteration of
+//                         every pair.  A group of CTAs owns a pair; each warp owns 32 consecutive source
+//                         points, finds their exact neighbours in a shared-memory tile gathered from the
+//                         target's grid (tile_search.cuh), accumulates the 29 sums in registers; the CTAs of
+//                         the group exchange one row of 29 doubles through L2, meet at a group barrier, and
+//                         every CTA sums the rows in the same fixed order and solves the 6x6 (or Kabsch)
+//                         in double: no host round trip, no kernel boundary between iterations, and from
+//                         the ~4th iteration on >99% of the queries keep their correspondence by the
+//                         triangle-inequality test, so an iteration is one streaming pass over 52 B/point.
+//   S3D_SEARCH_GRID_LANE  icp_iter_kernel, one launch per iteration, per-lane ball search (search.cuh);
+//                         the last CTA to finish (atomic ticket) solves.  Kept as an independent check.
+//   S3D_SEARCH_BRUTE      all targets streamed through shared memory by TMA bulk copies
+//                         (cp.async.bulk + mbarrier), 4 sources per thread in registers; the north star's
+//                         literal kernel and the verification mode (FP32-issue bound).
 #include <cstdio>
 #include <cstring>
 #include <cmath>
@@ -28,6 +36,7 @@
 #define ICP_MIN_BLOCKS 4      // 64 registers per thread: 32 warps per SM hide the gather latency
 #endif
 #include "search.cuh"
+#include "tile_search.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // brute-force exact NN: target tiles staged in shared memory by TMA bulk copies
@@ -129,24 +138,48 @@ __global__ void __launch_bounds__(ICP_BLOCK) nn_brute_tma_kernel(const PairDesc 
 // ------------------------------------------------------------------------------------------------
 // small dense solvers (double, one thread) -- same algorithms as oracle/icp_oracle.c
 // ------------------------------------------------------------------------------------------------
-__device__ int chol6_solve(const double A[6][6], const double g[6], double pivot_eps, double x[6])
+__device__ __forceinline__ int chol6_solve(const double A[6][6], const double g[6], double pivot_eps, double x[6])
 {
+    // fully unrolled: every index is a compile-time constant, so L, y live in registers (same operation order as
+    // chol6_solve of oracle/icp_oracle.c)
     double L[6][6];
-    for (int i = 0; i < 6; ++i) for (int j = 0; j < 6; ++j) L[i][j] = 0.0;
+    #pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        #pragma unroll
+        for (int j = 0; j < 6; ++j) L[i][j] = 0.0;
+    }
+    int bad = 0;
+    #pragma unroll
     for (int j = 0; j < 6; ++j) {
         double s = A[j][j];
+        #pragma unroll
         for (int k = 0; k < j; ++k) s -= L[j][k] * L[j][k];
-        if (!(s > pivot_eps * A[j][j]) || !(A[j][j] > 0.0)) return 1;
+        if (!(s > pivot_eps * A[j][j]) || !(A[j][j] > 0.0)) bad = 1;
         L[j][j] = sqrt(s);
+        #pragma unroll
         for (int i = j + 1; i < 6; ++i) {
             double v = A[i][j];
+            #pragma unroll
             for (int k = 0; k < j; ++k) v -= L[i][k] * L[j][k];
             L[i][j] = v / L[j][j];
         }
     }
+    if (bad) return 1;
     double y[6];
-    for (int i = 0; i < 6; ++i) { double v = g[i]; for (int k = 0; k < i; ++k) v -= L[i][k] * y[k]; y[i] = v / L[i][i]; }
-    for (int i = 5; i >= 0; --i) { double v = y[i]; for (int k = i + 1; k < 6; ++k) v -= L[k][i] * x[k]; x[i] = v / L[i][i]; }
+    #pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        double v = g[i];
+        #pragma unroll
+        for (int k = 0; k < i; ++k) v -= L[i][k] * y[k];
+        y[i] = v / L[i][i];
+    }
+    #pragma unroll
+    for (int i = 5; i >= 0; --i) {
+        double v = y[i];
+        #pragma unroll
+        for (int k = i + 1; k < 6; ++k) v -= L[k][i] * x[k];
+        x[i] = v / L[i][i];
+    }
     return 0;
 }
 
@@ -199,7 +232,7 @@ __device__ void kabsch_rotation(double H[3][3], double R[3][3])
 
 // consumes the summed accumulators of one pair, updates its state (runs in one thread)
 template <int EST>
-__device__ void solve_and_update(const double *acc, PairState *st, int min_corr, double pivot_eps)
+__device__ __noinline__ void solve_and_update(const double *acc, PairState *st, int min_corr, double pivot_eps)
 {
     const double cnt_d = acc[S3D_ACC_COUNT];
     const int cnt = (int)(cnt_d + 0.5);
@@ -209,8 +242,12 @@ __device__ void solve_and_update(const double *acc, PairState *st, int min_corr,
     double D[12];
     if (EST == S3D_ESTIMATOR_POINT_TO_PLANE) {
         double A[6][6], g[6], x[6];
-        int k = 0;
-        for (int a = 0; a < 6; ++a) for (int b = a; b < 6; ++b) { A[a][b] = acc[k]; A[b][a] = acc[k]; ++k; }
+        #pragma unroll
+        for (int a = 0; a < 6; ++a) {
+            #pragma unroll
+            for (int b = a; b < 6; ++b) { const int k = a * 6 - (a * (a - 1)) / 2 + (b - a); A[a][b] = acc[k]; A[b][a] = acc[k]; }
+        }
+        #pragma unroll
         for (int a = 0; a < 6; ++a) g[a] = acc[21 + a];
         if (chol6_solve(A, g, pivot_eps, x)) { st->status = S3D_PAIR_DEGENERATE; return; }
         euler_to_T(x, D);
@@ -270,6 +307,46 @@ __device__ __forceinline__ void accumulate(float *acc, float px, float py, float
     }
     acc[S3D_ACC_SUMD2] += d2;
     acc[S3D_ACC_COUNT] += 1.0f;
+}
+
+
+// Same sums with the oracle's arithmetic: J and r in float32 (bit-identical expressions), products exact in
+// double, double accumulation -- GPU and oracle then differ only by the order of double additions, which keeps
+// even the rank-deficiency verdict (a pivot compared with 1e-9 * diagonal) in agreement.
+template <int EST>
+__device__ __forceinline__ void accumulate_d(double *acc, float px, float py, float pz, float4 q, float4 nv, float d2)
+{
+    if (EST == S3D_ESTIMATOR_POINT_TO_PLANE) {
+        float J[6];
+        J[0] = __fmaf_rn(nv.z, py, -__fmul_rn(nv.y, pz));
+        J[1] = __fmaf_rn(nv.x, pz, -__fmul_rn(nv.z, px));
+        J[2] = __fmaf_rn(nv.y, px, -__fmul_rn(nv.x, py));
+        J[3] = nv.x; J[4] = nv.y; J[5] = nv.z;
+        float ex = __fsub_rn(q.x, px), ey = __fsub_rn(q.y, py), ez = __fsub_rn(q.z, pz);
+        float r = __fmaf_rn(nv.z, ez, __fmaf_rn(nv.y, ey, __fmul_rn(nv.x, ex)));
+        double Jd[6];
+        #pragma unroll
+        for (int a = 0; a < 6; ++a) Jd[a] = (double)J[a];
+        const double rd = (double)r;
+        int k = 0;
+        #pragma unroll
+        for (int a = 0; a < 6; ++a) {
+            #pragma unroll
+            for (int b = a; b < 6; ++b) { acc[k] = fma(Jd[a], Jd[b], acc[k]); ++k; }
+        }
+        #pragma unroll
+        for (int a = 0; a < 6; ++a) acc[21 + a] = fma(Jd[a], rd, acc[21 + a]);
+    } else {
+        const double p[3] = {(double)px, (double)py, (double)pz}, qq[3] = {(double)q.x, (double)q.y, (double)q.z};
+        #pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            acc[a] += p[a]; acc[3 + a] += qq[a];
+            #pragma unroll
+            for (int b = 0; b < 3; ++b) acc[6 + 3 * a + b] = fma(p[a], qq[b], acc[6 + 3 * a + b]);
+        }
+    }
+    acc[S3D_ACC_SUMD2] += (double)d2;
+    acc[S3D_ACC_COUNT] += 1.0;
 }
 
 template <int EST, int SEARCH>
@@ -491,6 +568,253 @@ __global__ void __launch_bounds__(ICP_BLOCK, ICP_MIN_BLOCKS) icp_iter_kernel(con
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// the persistent kernel: all iterations of all pairs in one cooperative launch
+// ------------------------------------------------------------------------------------------------
+#define TS_BLOCK 512
+#define TS_WARPS (TS_BLOCK / 32)
+
+#if defined(S3D_STATS) || defined(S3D_PHASES)
+#define PHASE_T0() long long ph_t = clock64()
+#define PHASE(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) { long long n_ = clock64(); atomicAdd(&g_stats[i], (unsigned long long)(n_ - ph_t)); ph_t = n_; } } while (0)
+#else
+#define PHASE_T0()
+#define PHASE(i)
+#endif
+
+struct PersistArgs {
+    const PairDesc *descs; PairState *states;
+    double *partials;            // [2][groups][group_ctas][S3D_NACC]
+    unsigned *barriers;          // [groups], zero at launch, monotonic
+    float4 *cq;                  // per query: its correspondence (x,y,z, original target index; -1: none)
+    float4 *cn;                  // per query: the correspondence's normal (nx,ny,nz,valid)   (point-to-plane)
+    float *lb;                   // per query: lower bound on the distance to every other target point
+    long long nn_stride;         // queries per pair in the three arrays above
+    int n_pairs, groups, group_ctas, iterations;
+    float max_d2; int min_corr; double pivot_eps;
+    int32_t *nn_out;             // correspondences of the last iteration (single pair) or null
+};
+
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p)
+{
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+template <int EST>
+__global__ void __launch_bounds__(TS_BLOCK, 1) icp_persist_kernel(const PersistArgs a)
+{
+    extern __shared__ __align__(16) unsigned char ts_smem[];
+    float4 *tiles = reinterpret_cast<float4 *>(ts_smem);          // TS_WARPS tiles of TS_CAP candidates
+    __shared__ PairState st;                                      // this CTA's copy of the pair state (all CTAs of a group agree bit for bit)
+    __shared__ double wsum[TS_WARPS][S3D_NACC];
+    __shared__ double tail[TS_WARPS][S3D_NACC];
+    __shared__ __align__(8) uint64_t tile_bar[TS_WARPS];         // one mbarrier per warp: completion of its TMA row copies
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int group = blockIdx.x / a.group_ctas, rank = blockIdx.x - group * a.group_ctas;
+    float4 *buf = tiles + warp * TS_CAP;
+    uint64_t *bar_w = &tile_bar[warp];
+    uint32_t parity = 0u;
+    if (lane == 0) {
+        ts_mbar_init(bar_w, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    unsigned *bar = a.barriers + group;
+    unsigned epoch = 0;
+    const float gate_r = a.max_d2 < INFINITY ? sqrtf(a.max_d2) : INFINITY;
+
+    for (int pair = group; pair < a.n_pairs; pair += a.groups) {
+        const PairDesc d = a.descs[pair];
+        __syncthreads();
+        if (threadIdx.x == 0) st = a.states[pair];
+        __syncthreads();
+        GridParams gp = *d.grid;
+        const GridView fine = {d.grid, d.cell_start, d.rowmask, d.sorted_pts};
+        const bool have_coarse = d.coarse_grid != nullptr;
+        GridParams cgp = gp;
+        if (have_coarse) cgp = *d.coarse_grid;
+        const GridView coarse = {d.coarse_grid, d.coarse_cell_start, d.coarse_rowmask, d.coarse_pts};
+        const float slack = 0.2f * gp.cell;
+        float4 *my_cq = a.cq + (size_t)pair * a.nn_stride;
+        float4 *my_cn = a.cn + (size_t)pair * a.nn_stride;
+        float *my_lb = a.lb + (size_t)pair * a.nn_stride;
+        const int nchunks = (d.n_src + 31) >> 5;
+
+        for (int it = 0; it < a.iterations; ++it) {
+            if (st.status != 0) break;            // failed pairs stop; every CTA of the group sees the same state
+            float T[12], Tp[12];
+            #pragma unroll
+            for (int k = 0; k < 12; ++k) { T[k] = st.Tf[k]; Tp[k] = st.Tf_prev[k]; }
+            const bool last = (it == a.iterations - 1);
+            // float pose bitwise unchanged since the previous iteration: every transformed point is bitwise the same,
+            // so every correspondence of the previous iteration is still the exact answer
+            bool same_pose = it > 0;
+            #pragma unroll
+            for (int k = 0; k < 12; ++k) same_pose = same_pose && (__float_as_uint(T[k]) == __float_as_uint(Tp[k]));
+            double acc[29];
+            #pragma unroll
+            for (int k = 0; k < 29; ++k) acc[k] = 0.0;
+            PHASE_T0();
+#if defined(S3D_STATS) || defined(S3D_PHASES)
+            if (blockIdx.x == 0 && threadIdx.x == 0 && same_pose) atomicAdd(&g_stats[30], 1ull);
+#endif
+#if defined(S3D_STATS) || defined(S3D_PHASES)
+            const long long wl_t0 = clock64(); long long ws_t = 0; int ws_n = 0;
+#if defined(S3D_PHASES)
+            long long tm[5] = {0, 0, 0, 0, 0};
+#endif
+#endif
+
+            for (int chunk = rank * TS_WARPS + warp; chunk < nchunks; chunk += a.group_ctas * TS_WARPS) {
+                const int i = (chunk << 5) + lane;
+                const bool in = i < d.n_src;
+                float3 x = make_float3(0.f, 0.f, 0.f);
+                float4 q = make_float4(0.f, 0.f, 0.f, __int_as_float(-1)), nv = make_float4(0.f, 0.f, 0.f, 1.f);
+                float d2q = INFINITY, r = 1.5f * gp.cell;
+                bool pending = in;
+                if (in) {
+                    const float4 p = d.src[i];
+                    x = s3d_xform(T, p.x, p.y, p.z);
+                    if (it > 0) {
+                        q = my_cq[i];
+                        if (same_pose) {
+                            pending = false;
+                            if (__float_as_int(q.w) >= 0) {
+                                d2q = s3d_dist2(x.x, x.y, x.z, q.x, q.y, q.z);
+                                if (EST == S3D_ESTIMATOR_POINT_TO_PLANE) nv = my_cn[i];
+                            }
+                            STAT(1, 1);
+                        } else if (__float_as_int(q.w) >= 0) {
+                            d2q = s3d_dist2(x.x, x.y, x.z, q.x, q.y, q.z);
+                            const float3 xo = s3d_xform(Tp, p.x, p.y, p.z);
+                            const float mv = sqrtf(s3d_dist2(x.x, x.y, x.z, xo.x, xo.y, xo.z));
+                            const float moved = mv * 1.000002f + 5e-8f;
+                            const float lbm = my_lb[i] - moved;
+                            const float dq = sqrtf(d2q);
+                            if (dq * 1.000002f + 2e-7f < lbm) {       // still the exact nearest neighbour: no search
+                                pending = false; my_lb[i] = lbm;
+                                if (EST == S3D_ESTIMATOR_POINT_TO_PLANE) nv = my_cn[i];
+                                STAT(1, 1);
+                            } else {
+                                // The old correspondence is a real target point, so dq bounds the ball.  After a small move it is
+                                // also tight; after a big pose update (first iterations) the point slid along the surface and one
+                                // cell is the better first guess (tile_search verifies and widens when needed).
+                                r = dq * 1.00001f + slack;
+                                if (mv > 0.25f * gp.cell) r = fminf(r, gp.cell + slack);
+                            }
+                        }
+                    }
+                }
+                if (__any_sync(full, pending)) {
+#if defined(S3D_STATS) || defined(S3D_PHASES)
+                    const long long s_t0 = clock64();
+#endif
+                    // first iteration: the nearest point of the decimated target (level 0) bounds the fine search (level 1)
+                    TileBest b; float lbv = 0.f;
+                    for (int level = (it == 0 && have_coarse) ? 0 : 1; level < 2; ++level) {
+                        const GridView &gv = level ? fine : coarse;
+                        const GridParams &gq = level ? gp : cgp;
+                        const float rr = level ? r : cgp.cell, sl = level ? slack : 0.2f * cgp.cell;
+                        STAT(level ? 0 : 6, pending);
+                        tile_search(gv, gq, x.x, x.y, x.z, rr, pending, gate_r, sl, buf, bar_w, parity, lane, b, lbv TS_TM_PASS);
+                        if (level == 0 && pending && b.bd < INFINITY) r = sqrtf(b.bd) * 1.00001f + slack;
+                    }
+                    if (pending) {
+                        q = b.bq; d2q = b.bd;
+                        if (!(b.bd < INFINITY)) q.w = __int_as_float(-1);      // nothing within reach
+                        my_cq[i] = q; my_lb[i] = lbv;
+                        if (EST == S3D_ESTIMATOR_POINT_TO_PLANE && __float_as_int(q.w) >= 0) {
+                            nv = __ldg(&d.tgt_nrm[__float_as_int(q.w)]);
+                            my_cn[i] = nv;
+                        }
+                    }
+#if defined(S3D_STATS) || defined(S3D_PHASES)
+                    ws_t += clock64() - s_t0; ++ws_n;
+#endif
+                }
+                const int j = __float_as_int(q.w);
+                const bool ok = in && (j >= 0) && (d2q <= a.max_d2) && (nv.w != 0.f);
+                if (ok) accumulate_d<EST>(acc, x.x, x.y, x.z, q, nv, d2q);
+                if (last && a.nn_out && in) a.nn_out[i] = ok ? j : -1;
+            }
+
+#if defined(S3D_STATS) || defined(S3D_PHASES)
+            if (blockIdx.x == 0 && lane == 0) {
+                const unsigned long long wl = (unsigned long long)(clock64() - wl_t0);
+                atomicMax(&g_stats[16], wl); atomicAdd(&g_stats[17], wl);                 // chunk loop of one warp: max (over the run), sum
+                atomicAdd(&g_stats[18], (unsigned long long)ws_t); atomicAdd(&g_stats[19], (unsigned long long)ws_n);   // inside searches: cycles, count
+                atomicMax(&g_stats[20], (unsigned long long)ws_t);
+#if defined(S3D_PHASES)
+                for (int k = 0; k < 5; ++k) atomicAdd(&g_stats[21 + k], (unsigned long long)tm[k]);
+#endif
+            }
+#endif
+            PHASE(8);
+            // CTA reduction in double: shuffles inside the warp, shared memory across warps, one row per CTA
+            // (through the warp's tile, transposed: lane k sums slot k of the 32 lanes in lane order -- ~100 instructions
+            //  instead of 29 five-step double shuffle trees)
+            {
+                double *tr = reinterpret_cast<double *>(buf);          // 29 x 33 doubles <= TS_CAP float4
+                __syncwarp();
+                #pragma unroll
+                for (int k = 0; k < 29; ++k) tr[k * 33 + lane] = acc[k];
+                __syncwarp();
+                if (lane < 29) {
+                    double s = 0.0;
+                    #pragma unroll 8
+                    for (int l = 0; l < 32; ++l) s += tr[lane * 33 + l];
+                    wsum[warp][lane] = s;
+                }
+                __syncwarp();
+            }
+            __syncthreads();
+            double *rows = a.partials + ((size_t)(epoch & 1u) * a.groups + group) * a.group_ctas * S3D_NACC;
+            if (threadIdx.x < 29) {
+                double s = 0.0;
+                #pragma unroll
+                for (int w = 0; w < TS_WARPS; ++w) s += wsum[w][threadIdx.x];
+                __stcg(&rows[(size_t)rank * S3D_NACC + threadIdx.x], s);
+            }
+            // group barrier (all CTAs are co-resident: cooperative launch)
+            ++epoch;
+            __syncthreads();
+            PHASE(9);
+            if (a.group_ctas > 1 && threadIdx.x == 0) {
+                __threadfence();
+                atomicAdd(bar, 1u);
+                const unsigned target = epoch * (unsigned)a.group_ctas;
+                while (ld_acquire_u32(bar) < target) { }
+            }
+            __syncthreads();
+            PHASE(10);
+            // every CTA: the same fixed-order sum of the group's rows, then the same solve
+            {
+                double s = 0.0;
+                if (lane < 29)
+                    for (int c = warp; c < a.group_ctas; c += TS_WARPS) s += __ldcg(&rows[(size_t)c * S3D_NACC + lane]);
+                tail[warp][lane] = s;
+            }
+            __syncthreads();
+            if (threadIdx.x < 32) {
+                double s = 0.0;
+                #pragma unroll
+                for (int w = 0; w < TS_WARPS; ++w) s += tail[w][threadIdx.x];
+                tail[0][threadIdx.x] = s;
+            }
+            __syncthreads();
+            PHASE(11);
+            if (threadIdx.x == 0) solve_and_update<EST>(tail[0], &st, a.min_corr, a.pivot_eps);
+            __syncthreads();
+            PHASE(12);
+        }
+        if (rank == 0 && threadIdx.x == 0) a.states[pair] = st;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
@@ -547,11 +871,13 @@ extern "C" int s3d_register_batch(s3d_ctx *ctx, const s3d_cloud *const *src, con
 {
     if (!ctx || !src || !tgt || !prm || !out || n_pairs <= 0) return s3d_fail(ctx, S3D_E_ARG, "s3d_register_batch: bad argument");
     if (prm->estimator != S3D_ESTIMATOR_POINT_TO_PLANE && prm->estimator != S3D_ESTIMATOR_SVD) return s3d_fail(ctx, S3D_E_ARG, "unknown estimator");
-    if (prm->search != S3D_SEARCH_GRID && prm->search != S3D_SEARCH_BRUTE) return s3d_fail(ctx, S3D_E_ARG, "unknown search mode");
+    if (prm->search != S3D_SEARCH_GRID && prm->search != S3D_SEARCH_BRUTE && prm->search != S3D_SEARCH_GRID_LANE)
+        return s3d_fail(ctx, S3D_E_ARG, "unknown search mode");
     if (prm->max_iterations < 0) return s3d_fail(ctx, S3D_E_ARG, "max_iterations < 0");
     cudaSetDevice(ctx->device);
     const bool plane = prm->estimator == S3D_ESTIMATOR_POINT_TO_PLANE;
-    const bool use_grid = prm->search == S3D_SEARCH_GRID;
+    const bool use_grid = prm->search != S3D_SEARCH_BRUTE;
+    const bool persist = prm->search == S3D_SEARCH_GRID;
     int n_max = 0;
     for (int i = 0; i < n_pairs; ++i) {
         if (!src[i] || !tgt[i]) return s3d_fail(ctx, S3D_E_ARG, "null cloud in batch");
@@ -564,6 +890,25 @@ extern "C" int s3d_register_batch(s3d_ctx *ctx, const s3d_cloud *const *src, con
     const int resident = ctx->sm_count * ICP_MIN_BLOCKS;
     const int rounds = std::max(1, (n_max + resident * ICP_BLOCK - 1) / (resident * ICP_BLOCK));
     int ctas = std::max(1, std::min((n_max + rounds * ICP_BLOCK - 1) / (rounds * ICP_BLOCK), std::max(1, resident / n_pairs)));
+    // persistent path: groups of CTAs, all co-resident (cooperative launch), one group per pair at a time
+    int p_groups = 1, p_group_ctas = 1;
+    const size_t p_smem = sizeof(float4) * TS_CAP * TS_WARPS;
+    if (persist) {
+        if (ctx->persist_resident[plane ? 0 : 1] == 0) {
+            const void *fn = plane ? (const void *)icp_persist_kernel<S3D_ESTIMATOR_POINT_TO_PLANE> : (const void *)icp_persist_kernel<S3D_ESTIMATOR_SVD>;
+            S3D_CUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p_smem));
+            int per_sm = 0;
+            S3D_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, TS_BLOCK, p_smem));
+            if (per_sm < 1) return s3d_fail(ctx, S3D_E_CUDA, "icp_persist_kernel does not fit on an SM");
+            ctx->persist_resident[plane ? 0 : 1] = per_sm * ctx->sm_count;
+        }
+        const int p_res = ctx->persist_resident[plane ? 0 : 1];
+        const int chunks_per_cta = 2 * TS_WARPS;      // at least two chunks of 32 queries per warp before a pair is spread wider
+        const int useful = std::max(1, (n_max + 32 * chunks_per_cta - 1) / (32 * chunks_per_cta));
+        p_group_ctas = std::max(1, std::min(useful, p_res / std::min(n_pairs, p_res)));
+        p_groups = std::max(1, std::min(n_pairs, p_res / p_group_ctas));
+        ctas = 2 * p_group_ctas;                      // partial rows are double buffered
+    }
     int rc = ensure_batch(ctx, n_pairs, ctas);
     if (rc) return rc;
 
@@ -581,7 +926,7 @@ extern "C" int s3d_register_batch(s3d_ctx *ctx, const s3d_cloud *const *src, con
     }
     cudaEventRecord(ctx->ev[1], ctx->stream);
 
-    {
+    if (!persist) {
         size_t need = (size_t)n_pairs * n_max;
         if (need > (size_t)ctx->cap_nn) {
             cudaFree(ctx->d_nn_idx); cudaFree(ctx->d_nn_d2); cudaFree(ctx->d_nn_pos);
@@ -590,6 +935,23 @@ extern "C" int s3d_register_batch(s3d_ctx *ctx, const s3d_cloud *const *src, con
             S3D_CUDA(ctx, cudaMalloc(&ctx->d_nn_d2, sizeof(float) * std::max<size_t>(need, 1)));
             S3D_CUDA(ctx, cudaMalloc(&ctx->d_nn_pos, sizeof(int32_t) * std::max<size_t>(need, 1)));
             ctx->cap_nn = (int)need;
+        }
+    }
+    if (persist) {
+        size_t need = (size_t)n_pairs * std::max(n_max, 1);
+        if (need > ctx->cap_tile_nn) {
+            cudaFree(ctx->d_cq); cudaFree(ctx->d_cn); cudaFree(ctx->d_lb);
+            ctx->d_cq = nullptr; ctx->d_cn = nullptr; ctx->d_lb = nullptr; ctx->cap_tile_nn = 0;
+            S3D_CUDA(ctx, cudaMalloc(&ctx->d_cq, sizeof(float4) * need));
+            S3D_CUDA(ctx, cudaMalloc(&ctx->d_cn, sizeof(float4) * need));
+            S3D_CUDA(ctx, cudaMalloc(&ctx->d_lb, sizeof(float) * need));
+            ctx->cap_tile_nn = need;
+        }
+        if (p_groups > ctx->cap_barriers) {
+            cudaFree(ctx->d_barriers); ctx->d_barriers = nullptr; ctx->cap_barriers = 0;
+            int cap = std::max(p_groups, 1024);
+            S3D_CUDA(ctx, cudaMalloc(&ctx->d_barriers, sizeof(unsigned) * cap));
+            ctx->cap_barriers = cap;
         }
     }
     int32_t *nn_out = nullptr;
@@ -627,7 +989,19 @@ extern "C" int s3d_register_batch(s3d_ctx *ctx, const s3d_cloud *const *src, con
     const double pivot_eps = prm->pivot_eps > 0 ? prm->pivot_eps : 1e-9;
     const dim3 grid(ctas, n_pairs);
     int iter_launches = 0;
-    for (int it = 0; it < prm->max_iterations; ++it) {
+    if (persist && prm->max_iterations > 0) {
+        S3D_CUDA(ctx, cudaMemsetAsync(ctx->d_barriers, 0, sizeof(unsigned) * p_groups, ctx->stream));
+        PersistArgs pa;
+        pa.descs = ctx->d_desc; pa.states = ctx->d_state; pa.partials = ctx->d_partials; pa.barriers = ctx->d_barriers;
+        pa.cq = ctx->d_cq; pa.cn = ctx->d_cn; pa.lb = ctx->d_lb; pa.nn_stride = std::max(n_max, 1);
+        pa.n_pairs = n_pairs; pa.groups = p_groups; pa.group_ctas = p_group_ctas; pa.iterations = prm->max_iterations;
+        pa.max_d2 = max_d2; pa.min_corr = min_corr; pa.pivot_eps = pivot_eps; pa.nn_out = nn_out;
+        void *kargs[] = {&pa};
+        const void *fn = plane ? (const void *)icp_persist_kernel<S3D_ESTIMATOR_POINT_TO_PLANE> : (const void *)icp_persist_kernel<S3D_ESTIMATOR_SVD>;
+        S3D_CUDA(ctx, cudaLaunchCooperativeKernel(fn, dim3(p_groups * p_group_ctas), dim3(TS_BLOCK), kargs, p_smem, ctx->stream));
+        S3D_LAUNCHED(ctx); ++iter_launches;
+    }
+    for (int it = 0; it < prm->max_iterations && !persist; ++it) {
         int32_t *no = (it == prm->max_iterations - 1) ? nn_out : nullptr;
         if (!use_grid) {
             dim3 g2((n_max + ICP_BLOCK * BF_SRC_PER_THREAD - 1) / (ICP_BLOCK * BF_SRC_PER_THREAD), n_pairs);
@@ -694,12 +1068,12 @@ extern "C" int s3d_last_timing(const s3d_ctx *ctx, s3d_timing *out)
     return S3D_OK;
 }
 
-#ifdef S3D_STATS
-extern "C" int s3d_debug_stats(unsigned long long *out16, int reset)
+#if defined(S3D_STATS) || defined(S3D_PHASES)
+extern "C" int s3d_debug_stats(unsigned long long *out32, int reset)
 {
     cudaDeviceSynchronize();
-    cudaMemcpyFromSymbol(out16, g_stats, sizeof(unsigned long long) * 16);
-    if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(g_stats, z, sizeof(z)); }
+    cudaMemcpyFromSymbol(out32, g_stats, sizeof(unsigned long long) * 32);
+    if (reset) { unsigned long long z[32] = {0}; cudaMemcpyToSymbol(g_stats, z, sizeof(z)); }
     return 0;
 }
 #endif

@@ -28,9 +28,11 @@
 #define GRID_MARGIN 1e-3f     // cell-coordinate rounding allowance, in cells (DESIGN.md "exactness of the grid search")
 #define COOP 8                // lanes per query
 
+#if defined(S3D_STATS) || defined(S3D_PHASES)
+__device__ unsigned long long g_stats[32];   // debug builds only: [0] searched [1] skipped [2] rows looked up [3] candidates
+                                             // [4] mask loads [5] search rounds [6] coarse searches [8..] phase cycles of CTA 0
+#endif
 #ifdef S3D_STATS
-__device__ unsigned long long g_stats[16];   // debug build only: [0] searched [1] skipped [2] rows looked up [3] candidates
-                                             // [4] mask loads [5] search rounds [6] coarse searches
 #define STAT(i, v) atomicAdd(&g_stats[i], (unsigned long long)(v))
 #else
 #define STAT(i, v)

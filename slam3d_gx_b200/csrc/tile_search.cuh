@@ -1,0 +1,291 @@
+// tile_search.cuh -- exact nearest-neighbour search: a warp serves up to TS_GROUP neighbouring queries at a
+// time from a shared-memory tile of target points staged by TMA bulk copies.
+//
+// Semantics: PCL-1.7 CorrespondenceEstimation::determineCorrespondences (exact 1-NN of every source point in
+// the target; restated in oracle/icp_oracle.c): argmin over the float32 value s3d_dist2() with the lowest
+// target index winning ties.  Nothing below changes that answer; it is only about finding it with
+// convergent, bandwidth-friendly work instead of per-lane dependent gathers:
+//
+//   * Consecutive source points (a piece of a scan line of an organised cloud) are neighbours in space, so
+//     their search balls overlap.  The warp takes the bounding box (in cell space) of the balls of a group of
+//     pending queries; every row of cells (fixed y,z; contiguous along x in the cell-sorted target) that
+//     crosses the box is ONE contiguous range of float4 points: two cell-start loads per row, then one
+//     cp.async.bulk (TMA) per row into the warp's tile, completion counted by the warp's mbarrier.
+//   * The 32 lanes split the tile between them: with n queries in the group, 32/n lanes work on each query
+//     (a lone pending query of a late iteration is served by all 32 lanes), partial results merged by
+//     shuffles.  Shared-memory reads are broadcasts, there is no divergence, ~11 FP32-pipe instructions per
+//     candidate, nearest and runner-up kept.
+//   * Completeness is VERIFIED, not assumed: every target point that is not in the tile lies outside the
+//     box, i.e. at least `margin` (distance from the query to the nearest box face that is not a face of the
+//     whole grid) away.  A query is done when its best candidate is nearer than that; otherwise its radius is
+//     replaced by the distance just found (a valid bound) and it goes round again.  Radii passed in are
+//     therefore only hints.  Queries whose radius is far above the rest of their group (depth
+//     discontinuities, image borders) wait for a later pass so that they do not inflate everybody's box.
+//   * min(runner-up, margin) is a lower bound on the distance to every OTHER target point: the caller uses
+//     it to skip the search altogether on later iterations (triangle inequality, see icp.cu).
+#pragma once
+#include <limits.h>
+#include "context.h"
+#include "common.cuh"
+#include "grid.cuh"
+#include "search.cuh"
+
+#ifndef TS_CAP
+#define TS_CAP 512            // candidates per warp tile (8 KiB)
+#endif
+#ifndef TS_GROUP
+#define TS_GROUP 8            // queries per box (power of two <= 32)
+#endif
+#define TS_MAX_TRIES 64
+
+#if defined(S3D_PHASES)
+#define TS_TM_ARG , long long *tm
+#define TS_TM_PASS , tm
+#define TS_T0() long long ts_last = clock64()
+#define TS_T(i) do { const long long n_ = clock64(); tm[i] += n_ - ts_last; ts_last = n_; } while (0)
+#define TS_CNT(i, v) do { if (blockIdx.x == 0 && lane == 0) atomicAdd(&g_stats[i], (unsigned long long)(v)); } while (0)
+#else
+#define TS_TM_ARG
+#define TS_TM_PASS
+#define TS_T0()
+#define TS_T(i)
+#define TS_CNT(i, v)
+#endif
+
+// ---- mbarrier / TMA bulk copy (PTX) ----------------------------------------------------------------
+__device__ __forceinline__ uint32_t ts_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void ts_mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(ts_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void ts_mbar_expect_tx(uint64_t *bar, uint32_t bytes)      // no arrival, only more bytes to wait for
+{
+    asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(ts_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void ts_mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(ts_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void ts_mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t ok = 0;
+    while (!ok) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(ts_smem_u32(bar)), "r"(parity) : "memory");
+    }
+}
+__device__ __forceinline__ void ts_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(ts_smem_u32(dst)), "l"(src), "r"(bytes), "r"(ts_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void ts_fence_proxy_async()
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+struct TileBest {             // nearest candidate (point + original index in .w), its d2, and the runner-up's d2
+    float4 bq; float bd; float sd;
+};
+
+__device__ __forceinline__ void tile_best_init(TileBest &B)
+{
+    B.bq = make_float4(0.f, 0.f, 0.f, __int_as_float(INT_MAX)); B.bd = INFINITY; B.sd = INFINITY;
+}
+
+// merge of two partial results over DISJOINT candidate sets (commutative, associative)
+__device__ __forceinline__ void tile_best_merge(TileBest &a, const float4 obq, float obd, float osd)
+{
+    const int ai = __float_as_int(a.bq.w), oi = __float_as_int(obq.w);
+    const bool better = obd < a.bd || (obd == a.bd && oi < ai);
+    a.sd = fminf(fminf(a.sd, osd), better ? a.bd : obd);
+    if (better) { a.bd = obd; a.bq = obq; }
+}
+
+// One lane's share of the tile: candidates sub, sub+step, ... < m against the query (qx,qy,qz); result merged into W.
+__device__ __forceinline__ void tile_compare_pass(const float4 *__restrict__ buf, int m, int sub, int step,
+                                                  float qx, float qy, float qz, TileBest &W)
+{
+    // two independent running minima (even / odd visits) halve the dependent chain
+    float pd0 = INFINITY, ps0 = INFINITY, pd1 = INFINITY, ps1 = INFINITY;
+    int pk0 = -1, pk1 = -1;
+    int k = sub;
+    for (; k + step < m; k += 2 * step) {
+        const float4 a = buf[k], b = buf[k + step];
+        const float da = s3d_dist2(qx, qy, qz, a.x, a.y, a.z), db = s3d_dist2(qx, qy, qz, b.x, b.y, b.z);
+        const bool la = da < pd0, lbb = db < pd1;
+        ps0 = fminf(ps0, fmaxf(pd0, da)); ps1 = fminf(ps1, fmaxf(pd1, db));
+        pd0 = fminf(pd0, da); pd1 = fminf(pd1, db);
+        pk0 = la ? k : pk0; pk1 = lbb ? k + step : pk1;
+    }
+    if (k < m) {
+        const float4 a = buf[k];
+        const float da = s3d_dist2(qx, qy, qz, a.x, a.y, a.z);
+        const bool la = da < pd0;
+        ps0 = fminf(ps0, fmaxf(pd0, da)); pd0 = fminf(pd0, da); pk0 = la ? k : pk0;
+    }
+    // combine the two chains: nearest, runner-up, and whether the minimum is attained more than once
+    const float pd = fminf(pd0, pd1);
+    const float ps = fminf(fminf(ps0, ps1), fmaxf(pd0, pd1));
+    int pk = (pd1 < pd0) ? pk1 : pk0;
+    if (pk < 0) return;                                   // this lane saw no candidate
+    if (ps == pd) {
+        // equal distances: the lowest original index wins (rare; rescan this lane's share)
+        int bi = INT_MAX;
+        for (int kk = sub; kk < m; kk += step) {
+            const float4 q = buf[kk];
+            const float d2 = s3d_dist2(qx, qy, qz, q.x, q.y, q.z);
+            const int qi = __float_as_int(q.w);
+            if (d2 == pd && qi < bi) { bi = qi; pk = kk; }
+        }
+    }
+    tile_best_merge(W, buf[pk], pd, ps);
+}
+
+// Exact NN of the pending queries of one warp.  (px,py,pz): this lane's query; r: its search radius hint in
+// metres (any positive finite value; a valid upper bound on the NN distance makes the first pass final);
+// `pending`: lane has a query.  gate_r: nothing farther than this can be accepted (INFINITY: no gate).
+// buf: this warp's tile (TS_CAP float4); bar/parity: this warp's mbarrier and its phase.  On return, for
+// pending lanes: B = nearest target point and runner-up distance among ALL target points (B.bq.w = INT_MAX
+// when the target has no point within reach), lbound = lower bound on the distance from the query to every
+// target point other than the winner.
+__device__ __forceinline__ void tile_search(const GridView &g, const GridParams &gp, float px, float py, float pz, float r,
+                                            bool pending, float gate_r, float slack, float4 *__restrict__ buf,
+                                            uint64_t *bar, uint32_t &parity, int lane, TileBest &B, float &lbound TS_TM_ARG)
+{
+    TS_T0();
+    const unsigned full = 0xffffffffu;
+    tile_best_init(B);
+    lbound = 0.f;
+    const float fx = grid_fcoord(px, gp.ox, gp.inv_cell), fy = grid_fcoord(py, gp.oy, gp.inv_cell), fz = grid_fcoord(pz, gp.oz, gp.inv_cell);
+    const float4 *__restrict__ sp = g.pts;
+    bool todo = pending;
+    r = fminf(r, gate_r * 1.00001f + 1e-6f);
+    ts_fence_proxy_async();          // the tile may have been written with ordinary stores since the last bulk copy
+    for (int tries = 0; ; ++tries) {
+        const unsigned todomask = __ballot_sync(full, todo);
+        if (!todomask) break;
+        // ---- this pass's group: the first TS_GROUP pending queries, minus those whose radius is far above the rest ----
+        unsigned grp = todomask;
+        if (__popc(grp) > TS_GROUP) grp &= (2u << (__fns(todomask, 0, TS_GROUP) & 31)) - 1u;
+        const bool ingrp = (grp >> lane) & 1u;
+        float rmin = ingrp ? r : INFINITY;
+        #pragma unroll
+        for (int o = 16; o > 0; o >>= 1) rmin = fminf(rmin, __shfl_xor_sync(full, rmin, o));
+        float thr = 3.f * rmin + slack;
+        if (2 * __popc(__ballot_sync(full, ingrp && r > thr)) >= __popc(grp)) thr = INFINITY;
+        const bool inbox = ingrp && r <= thr;
+        const unsigned inmask = __ballot_sync(full, inbox);
+        const int nin = __popc(inmask);
+        // ---- the box: union of the balls of the group ----
+        int lox = INT_MAX, loy = INT_MAX, loz = INT_MAX, hix = INT_MIN, hiy = INT_MIN, hiz = INT_MIN;
+        if (inbox) {
+            const float Rc = r * gp.inv_cell * 1.00001f + GRID_MARGIN;
+            lox = min(max(__float2int_rd(fx - Rc), 0), gp.nx - 1); hix = min(max(__float2int_rd(fx + Rc), 0), gp.nx - 1);
+            loy = min(max(__float2int_rd(fy - Rc), 0), gp.ny - 1); hiy = min(max(__float2int_rd(fy + Rc), 0), gp.ny - 1);
+            loz = min(max(__float2int_rd(fz - Rc), 0), gp.nz - 1); hiz = min(max(__float2int_rd(fz + Rc), 0), gp.nz - 1);
+        }
+        lox = __reduce_min_sync(full, lox); loy = __reduce_min_sync(full, loy); loz = __reduce_min_sync(full, loz);
+        hix = __reduce_max_sync(full, hix); hiy = __reduce_max_sync(full, hiy); hiz = __reduce_max_sync(full, hiz);
+        if (tries >= TS_MAX_TRIES) { lox = loy = loz = 0; hix = gp.nx - 1; hiy = gp.ny - 1; hiz = gp.nz - 1; }   // safety net: whole grid
+        const int ny_s = hiy - loy + 1, nz_s = hiz - loz + 1;
+        const int rows = gp.n_points > 0 ? ny_s * nz_s : 0;
+        // ---- work split: NS query slots (power of two >= nin), 32/NS lanes per slot ----
+        int NS = 1;
+        while (NS < nin) NS <<= 1;
+        const int step = 32 / NS, slot = lane & (NS - 1), sub = lane / NS;
+        const int src = (slot < nin) ? (int)__fns(inmask, 0, slot + 1) : 0;
+        const float qx = __shfl_sync(full, px, src), qy = __shfl_sync(full, py, src), qz = __shfl_sync(full, pz, src);
+        const bool work = slot < nin;
+        TileBest W; tile_best_init(W);
+        STAT(5, lane == 0);
+        TS_CNT(27, rows); TS_CNT(28, 1); TS_CNT(29, nin);
+        TS_T(0);
+        // ---- gather the rows into the tile by TMA, compare whenever it is full ----
+        // 32 rows per round (one per lane): two cell-start loads give the row's point range, one bulk copy moves it.
+        // What does not fit into the tile stays with its lane for the next turn (`carry`): rows of any length go through.
+        int fill = 0, t0 = 0;
+        uint32_t rs = 0u, cnt = 0u;
+        bool carry = false;
+        while (carry || t0 < rows) {
+            if (!carry) {
+                const int t = t0 + lane;
+                rs = 0u; cnt = 0u;
+                if (t < rows) {
+                    const int zi = t / ny_s;
+                    const size_t base = ((size_t)(loz + zi) * gp.ny + (loy + (t - zi * ny_s))) * gp.nx;
+                    rs = __ldg(&g.cell_start[base + lox]);
+                    cnt = __ldg(&g.cell_start[base + hix + 1]) - rs;
+                    STAT(2, 1);
+                }
+                t0 += 32;
+            }
+            TS_T(1);
+            uint32_t incl = cnt;
+            #pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t v = __shfl_up_sync(full, incl, o);
+                if (lane >= o) incl += v;
+            }
+            const uint32_t total = __shfl_sync(full, incl, 31), excl = incl - cnt;
+            const uint32_t room = (uint32_t)(TS_CAP - fill);
+            uint32_t take = cnt;
+            if (total > room) take = excl >= room ? 0u : min(cnt, room - excl);
+            const uint32_t moved_pts = min(total, room);
+            if (moved_pts > 0u) {
+                if (lane == 0) ts_mbar_expect_tx(bar, moved_pts * 16u);
+                __syncwarp();
+                if (take > 0u) ts_bulk_g2s(buf + fill + excl, sp + rs, take * 16u, bar);
+            }
+            rs += take; cnt -= take;
+            TS_T(2);
+            carry = total > room;
+            fill += (int)moved_pts;
+            if ((carry || t0 >= rows) && fill > 0) {
+                if (lane == 0) ts_mbar_arrive(bar);
+                ts_mbar_wait(bar, parity);
+                parity ^= 1u;
+                if (work) tile_compare_pass(buf, fill, sub, step, qx, qy, qz, W);
+                STAT(3, work ? fill / step : 0);
+                __syncwarp();
+                TS_CNT(26, fill);
+                fill = 0;
+                TS_T(3);
+            }
+        }
+        // ---- merge the lanes of each slot, hand the result back to the query's lane ----
+        for (int o = NS; o < 32; o <<= 1) {
+            const float4 obq = make_float4(__shfl_xor_sync(full, W.bq.x, o), __shfl_xor_sync(full, W.bq.y, o),
+                                           __shfl_xor_sync(full, W.bq.z, o), __shfl_xor_sync(full, W.bq.w, o));
+            const float obd = __shfl_xor_sync(full, W.bd, o), osd = __shfl_xor_sync(full, W.sd, o);
+            tile_best_merge(W, obq, obd, osd);
+        }
+        const int myslot = __popc(inmask & ((1u << lane) - 1u));        // slot that served this lane's query (valid if inbox)
+        TileBest R;
+        R.bq = make_float4(__shfl_sync(full, W.bq.x, myslot), __shfl_sync(full, W.bq.y, myslot),
+                           __shfl_sync(full, W.bq.z, myslot), __shfl_sync(full, W.bq.w, myslot));
+        R.bd = __shfl_sync(full, W.bd, myslot); R.sd = __shfl_sync(full, W.sd, myslot);
+        // ---- verify: everything outside the box is at least `margin` away ----
+        float mc = INFINITY;
+        if (lox > 0) mc = fminf(mc, fx - (float)lox);
+        if (hix < gp.nx - 1) mc = fminf(mc, (float)(hix + 1) - fx);
+        if (loy > 0) mc = fminf(mc, fy - (float)loy);
+        if (hiy < gp.ny - 1) mc = fminf(mc, (float)(hiy + 1) - fy);
+        if (loz > 0) mc = fminf(mc, fz - (float)loz);
+        if (hiz < gp.nz - 1) mc = fminf(mc, (float)(hiz + 1) - fz);
+        const float margin = fmaxf((mc - GRID_MARGIN) * gp.cell * 0.99999f, 0.f);     // INFINITY when the box is the whole grid
+        if (inbox) {
+            const bool done = (R.bd <= margin * margin) || (margin >= gate_r) || !(mc < INFINITY);
+            if (done) {
+                B = R;
+                lbound = fminf(sqrtf(R.sd), margin) * 0.999998f - 5e-8f;
+                todo = false;
+            } else {
+                // what was found is a valid bound; a query that found nothing doubles its hint
+                r = (R.bd < INFINITY) ? sqrtf(R.bd) * 1.00001f + slack : 2.f * r + slack;
+                r = fminf(r, gate_r * 1.00001f + 1e-6f);
+            }
+        }
+        TS_T(4);
+    }
+}

@@ -25,7 +25,7 @@ def _gpu_icp(ctx, p, prm, guess=None, normals="analytic"):
     return r, nn
 
 
-@pytest.mark.parametrize("search", [_abi.SEARCH_GRID, _abi.SEARCH_BRUTE])
+@pytest.mark.parametrize("search", [_abi.SEARCH_GRID, _abi.SEARCH_BRUTE, _abi.SEARCH_GRID_LANE])
 def test_correspondences_bit_exact(ctx, small_pair, search):
     p = small_pair
     prm = _abi.icp_params(1, search=search)
@@ -57,7 +57,7 @@ def test_grid_search_far_apart_clouds(ctx, small_pair):
 
 
 @pytest.mark.parametrize("est", [_abi.ESTIMATOR_POINT_TO_PLANE, _abi.ESTIMATOR_SVD])
-@pytest.mark.parametrize("search", [_abi.SEARCH_GRID, _abi.SEARCH_BRUTE])
+@pytest.mark.parametrize("search", [_abi.SEARCH_GRID, _abi.SEARCH_BRUTE, _abi.SEARCH_GRID_LANE])
 def test_icp_pose_parity_small(ctx, small_pair, est, search):
     p = small_pair
     prm = _abi.icp_params(10, estimator=est, search=search)
@@ -72,11 +72,17 @@ def test_icp_pose_parity_small(ctx, small_pair, est, search):
 
 
 def test_grid_and_brute_agree_bitwise(ctx, small_pair):
+    """Three independent exact searches: identical correspondences after 6 iterations.  The per-iteration-launch
+    modes also share the reduction order (same pose bits); the persistent kernel sums in another fixed order."""
     p = small_pair
     a, nna = _gpu_icp(ctx, p, _abi.icp_params(6, search=_abi.SEARCH_GRID))
     b, nnb = _gpu_icp(ctx, p, _abi.icp_params(6, search=_abi.SEARCH_BRUTE))
-    assert np.array_equal(nna, nnb)
-    assert np.array_equal(a["T"], b["T"])       # same correspondences, same reduction order => same bits
+    c, nnc = _gpu_icp(ctx, p, _abi.icp_params(6, search=_abi.SEARCH_GRID_LANE))
+    assert np.array_equal(nna, nnb) and np.array_equal(nnc, nnb)
+    assert np.array_equal(c["T"], b["T"])
+    assert a["inliers"] == b["inliers"]
+    ok, err = pose_close(a["T"], b["T"], 1e-7, 1e-7)
+    assert ok, err
 
 
 def test_icp_is_deterministic(ctx, small_pair):
@@ -218,7 +224,10 @@ def test_full_size_brute_force_matches_grid(ctx, full_pair):
     p = full_pair
     a, nna = _gpu_icp(ctx, p, _abi.icp_params(2, search=_abi.SEARCH_GRID))
     b, nnb = _gpu_icp(ctx, p, _abi.icp_params(2, search=_abi.SEARCH_BRUTE))
-    assert np.array_equal(nna, nnb) and np.array_equal(a["T"], b["T"])
+    c, nnc = _gpu_icp(ctx, p, _abi.icp_params(2, search=_abi.SEARCH_GRID_LANE))
+    assert np.array_equal(nna, nnb) and np.array_equal(nnc, nnb) and np.array_equal(c["T"], b["T"])
+    ok, err = pose_close(a["T"], b["T"], 1e-7, 1e-7)
+    assert ok, err
 
 
 def test_roundtrip_property_full_size(ctx, full_pair):
