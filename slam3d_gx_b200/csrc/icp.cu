@@ -589,17 +589,18 @@ struct PersistArgs {
     unsigned *barriers;          // [groups], zero at launch, monotonic
     float4 *cq;                  // per query: its correspondence (x,y,z, original target index; -1: none)
     float4 *cn;                  // per query: the correspondence's normal (nx,ny,nz,valid)   (point-to-plane)
-    float *lb;                   // per query: lower bound on the distance to every other target point
+    float4 *xl;                  // per query: its transformed position when it was last searched (x,y,z) and, in .w, the lower
+                                 // bound found then on its distance to every target point other than the correspondence
     long long nn_stride;         // queries per pair in the three arrays above
     int n_pairs, groups, group_ctas, iterations;
     float max_d2; int min_corr; double pivot_eps;
     int32_t *nn_out;             // correspondences of the last iteration (single pair) or null
 };
 
-__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p)
+__device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned *p)      // polling load: no L1 invalidate per poll
 {
     unsigned v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
 
@@ -611,11 +612,15 @@ __global__ void __launch_bounds__(TS_BLOCK, 1) icp_persist_kernel(const PersistA
     __shared__ PairState st;                                      // this CTA's copy of the pair state (all CTAs of a group agree bit for bit)
     __shared__ double wsum[TS_WARPS][S3D_NACC];
     __shared__ double tail[TS_WARPS][S3D_NACC];
+    __shared__ TileCfg cfg[2];                                    // search levels of the current pair: [0] decimated grid, [1] full grid
+#ifdef TS_USE_TMA
     __shared__ __align__(8) uint64_t tile_bar[TS_WARPS];         // one mbarrier per warp: completion of its TMA row copies
+#endif
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int group = blockIdx.x / a.group_ctas, rank = blockIdx.x - group * a.group_ctas;
     float4 *buf = tiles + warp * TS_CAP;
+#ifdef TS_USE_TMA
     uint64_t *bar_w = &tile_bar[warp];
     uint32_t parity = 0u;
     if (lane == 0) {
@@ -623,25 +628,30 @@ __global__ void __launch_bounds__(TS_BLOCK, 1) icp_persist_kernel(const PersistA
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+#endif
     unsigned *bar = a.barriers + group;
     unsigned epoch = 0;
     const float gate_r = a.max_d2 < INFINITY ? sqrtf(a.max_d2) : INFINITY;
 
     for (int pair = group; pair < a.n_pairs; pair += a.groups) {
         const PairDesc d = a.descs[pair];
-        __syncthreads();
-        if (threadIdx.x == 0) st = a.states[pair];
-        __syncthreads();
-        GridParams gp = *d.grid;
-        const GridView fine = {d.grid, d.cell_start, d.rowmask, d.sorted_pts};
         const bool have_coarse = d.coarse_grid != nullptr;
-        GridParams cgp = gp;
-        if (have_coarse) cgp = *d.coarse_grid;
-        const GridView coarse = {d.coarse_grid, d.coarse_cell_start, d.coarse_rowmask, d.coarse_pts};
-        const float slack = 0.2f * gp.cell;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            st = a.states[pair];
+            cfg[1].gp = *d.grid; cfg[1].cell_start = d.cell_start; cfg[1].pts = d.sorted_pts;
+            cfg[1].slack = 0.2f * cfg[1].gp.cell; cfg[1].gate_r = gate_r;
+            cfg[0] = cfg[1];
+            if (have_coarse) {
+                cfg[0].gp = *d.coarse_grid; cfg[0].cell_start = d.coarse_cell_start; cfg[0].pts = d.coarse_pts;
+                cfg[0].slack = 0.2f * cfg[0].gp.cell;
+            }
+        }
+        __syncthreads();
+        const float cell = cfg[1].gp.cell, slack = cfg[1].slack, ccell = cfg[0].gp.cell;
         float4 *my_cq = a.cq + (size_t)pair * a.nn_stride;
         float4 *my_cn = a.cn + (size_t)pair * a.nn_stride;
-        float *my_lb = a.lb + (size_t)pair * a.nn_stride;
+        float4 *my_xl = a.xl + (size_t)pair * a.nn_stride;
         const int nchunks = (d.n_src + 31) >> 5;
 
         for (int it = 0; it < a.iterations; ++it) {
@@ -669,42 +679,62 @@ __global__ void __launch_bounds__(TS_BLOCK, 1) icp_persist_kernel(const PersistA
 #endif
 #endif
 
-            for (int chunk = rank * TS_WARPS + warp; chunk < nchunks; chunk += a.group_ctas * TS_WARPS) {
+            // Streaming part: each warp walks its chunks of 32 consecutive queries (fixed assignment: the same thread
+            // sees the same query every iteration).  The four 16-byte loads of the NEXT chunk are issued before the
+            // current one is processed, so a late iteration (nearly every query keeps its correspondence) is one pass
+            // over 64 B/point with the latency of one chunk exposed, not of every chunk.
+            const int cstride = a.group_ctas * TS_WARPS;
+            int chunk = rank * TS_WARPS + warp;
+            float4 n_p = make_float4(0.f, 0.f, 0.f, 0.f), n_q = n_p, n_xl = n_p, n_nv = n_p;
+            {
+                const int i0 = (chunk << 5) + lane;
+                if (chunk < nchunks && i0 < d.n_src) {
+                    n_p = d.src[i0];
+                    if (it > 0) { n_q = my_cq[i0]; n_xl = my_xl[i0]; if (EST == S3D_ESTIMATOR_POINT_TO_PLANE) n_nv = my_cn[i0]; }
+                }
+            }
+            for (; chunk < nchunks; chunk += cstride) {
                 const int i = (chunk << 5) + lane;
                 const bool in = i < d.n_src;
+                const float4 p = n_p, q_old = n_q, xl = n_xl, nv_old = n_nv;
+                {
+                    const int i1 = ((chunk + cstride) << 5) + lane;
+                    if (chunk + cstride < nchunks && i1 < d.n_src) {
+                        n_p = d.src[i1];
+                        if (it > 0) { n_q = my_cq[i1]; n_xl = my_xl[i1]; if (EST == S3D_ESTIMATOR_POINT_TO_PLANE) n_nv = my_cn[i1]; }
+                    }
+                }
                 float3 x = make_float3(0.f, 0.f, 0.f);
                 float4 q = make_float4(0.f, 0.f, 0.f, __int_as_float(-1)), nv = make_float4(0.f, 0.f, 0.f, 1.f);
-                float d2q = INFINITY, r = 1.5f * gp.cell;
+                float d2q = INFINITY, r = 1.5f * cell;
                 bool pending = in;
                 if (in) {
-                    const float4 p = d.src[i];
                     x = s3d_xform(T, p.x, p.y, p.z);
                     if (it > 0) {
-                        q = my_cq[i];
+                        q = q_old;
                         if (same_pose) {
                             pending = false;
-                            if (__float_as_int(q.w) >= 0) {
-                                d2q = s3d_dist2(x.x, x.y, x.z, q.x, q.y, q.z);
-                                if (EST == S3D_ESTIMATOR_POINT_TO_PLANE) nv = my_cn[i];
-                            }
+                            if (__float_as_int(q.w) >= 0) { d2q = s3d_dist2(x.x, x.y, x.z, q.x, q.y, q.z); if (EST == S3D_ESTIMATOR_POINT_TO_PLANE) nv = nv_old; }
                             STAT(1, 1);
                         } else if (__float_as_int(q.w) >= 0) {
+                            // Triangle inequality against the state of the last search of this query: it was at xl.xyz, and every
+                            // target point other than q was at least xl.w away from there.
                             d2q = s3d_dist2(x.x, x.y, x.z, q.x, q.y, q.z);
-                            const float3 xo = s3d_xform(Tp, p.x, p.y, p.z);
-                            const float mv = sqrtf(s3d_dist2(x.x, x.y, x.z, xo.x, xo.y, xo.z));
-                            const float moved = mv * 1.000002f + 5e-8f;
-                            const float lbm = my_lb[i] - moved;
+                            const float mv = sqrtf(s3d_dist2(x.x, x.y, x.z, xl.x, xl.y, xl.z));
+                            const float lbm = xl.w - (mv * 1.000002f + 5e-8f);
                             const float dq = sqrtf(d2q);
-                            if (dq * 1.000002f + 2e-7f < lbm) {       // still the exact nearest neighbour: no search
-                                pending = false; my_lb[i] = lbm;
-                                if (EST == S3D_ESTIMATOR_POINT_TO_PLANE) nv = my_cn[i];
+                            if (dq * 1.000002f + 2e-7f < lbm) {       // still the exact nearest neighbour: no search, no state update
+                                pending = false;
+                                if (EST == S3D_ESTIMATOR_POINT_TO_PLANE) nv = nv_old;
                                 STAT(1, 1);
                             } else {
                                 // The old correspondence is a real target point, so dq bounds the ball.  After a small move it is
                                 // also tight; after a big pose update (first iterations) the point slid along the surface and one
                                 // cell is the better first guess (tile_search verifies and widens when needed).
+                                const float3 xo = s3d_xform(Tp, p.x, p.y, p.z);
+                                const float step_mv = sqrtf(s3d_dist2(x.x, x.y, x.z, xo.x, xo.y, xo.z));
                                 r = dq * 1.00001f + slack;
-                                if (mv > 0.25f * gp.cell) r = fminf(r, gp.cell + slack);
+                                if (step_mv > 0.25f * cell) r = fminf(r, cell + slack);
                             }
                         }
                     }
@@ -714,19 +744,21 @@ __global__ void __launch_bounds__(TS_BLOCK, 1) icp_persist_kernel(const PersistA
                     const long long s_t0 = clock64();
 #endif
                     // first iteration: the nearest point of the decimated target (level 0) bounds the fine search (level 1)
-                    TileBest b; float lbv = 0.f;
+                    TileOut b;
                     for (int level = (it == 0 && have_coarse) ? 0 : 1; level < 2; ++level) {
-                        const GridView &gv = level ? fine : coarse;
-                        const GridParams &gq = level ? gp : cgp;
-                        const float rr = level ? r : cgp.cell, sl = level ? slack : 0.2f * cgp.cell;
                         STAT(level ? 0 : 6, pending);
-                        tile_search(gv, gq, x.x, x.y, x.z, rr, pending, gate_r, sl, buf, bar_w, parity, lane, b, lbv TS_TM_PASS);
+#ifdef TS_USE_TMA
+                        b = tile_search(&cfg[level], x.x, x.y, x.z, level ? r : ccell, pending, buf, lane, bar_w, &parity TS_TM_PASS);
+#else
+                        b = tile_search(&cfg[level], x.x, x.y, x.z, level ? r : ccell, pending, buf, lane TS_TM_PASS);
+#endif
                         if (level == 0 && pending && b.bd < INFINITY) r = sqrtf(b.bd) * 1.00001f + slack;
                     }
+                    const float lbv = b.lb;
                     if (pending) {
                         q = b.bq; d2q = b.bd;
                         if (!(b.bd < INFINITY)) q.w = __int_as_float(-1);      // nothing within reach
-                        my_cq[i] = q; my_lb[i] = lbv;
+                        my_cq[i] = q; my_xl[i] = make_float4(x.x, x.y, x.z, lbv);
                         if (EST == S3D_ESTIMATOR_POINT_TO_PLANE && __float_as_int(q.w) >= 0) {
                             nv = __ldg(&d.tgt_nrm[__float_as_int(q.w)]);
                             my_cn[i] = nv;
@@ -787,7 +819,8 @@ __global__ void __launch_bounds__(TS_BLOCK, 1) icp_persist_kernel(const PersistA
                 __threadfence();
                 atomicAdd(bar, 1u);
                 const unsigned target = epoch * (unsigned)a.group_ctas;
-                while (ld_acquire_u32(bar) < target) { }
+                while (ld_relaxed_u32(bar) < target) { }
+                __threadfence();          // acquire: the other CTAs' rows are visible to everything after the barrier
             }
             __syncthreads();
             PHASE(10);
@@ -944,7 +977,7 @@ extern "C" int s3d_register_batch(s3d_ctx *ctx, const s3d_cloud *const *src, con
             ctx->d_cq = nullptr; ctx->d_cn = nullptr; ctx->d_lb = nullptr; ctx->cap_tile_nn = 0;
             S3D_CUDA(ctx, cudaMalloc(&ctx->d_cq, sizeof(float4) * need));
             S3D_CUDA(ctx, cudaMalloc(&ctx->d_cn, sizeof(float4) * need));
-            S3D_CUDA(ctx, cudaMalloc(&ctx->d_lb, sizeof(float) * need));
+            S3D_CUDA(ctx, cudaMalloc(&ctx->d_lb, sizeof(float4) * need));
             ctx->cap_tile_nn = need;
         }
         if (p_groups > ctx->cap_barriers) {
@@ -993,7 +1026,7 @@ extern "C" int s3d_register_batch(s3d_ctx *ctx, const s3d_cloud *const *src, con
         S3D_CUDA(ctx, cudaMemsetAsync(ctx->d_barriers, 0, sizeof(unsigned) * p_groups, ctx->stream));
         PersistArgs pa;
         pa.descs = ctx->d_desc; pa.states = ctx->d_state; pa.partials = ctx->d_partials; pa.barriers = ctx->d_barriers;
-        pa.cq = ctx->d_cq; pa.cn = ctx->d_cn; pa.lb = ctx->d_lb; pa.nn_stride = std::max(n_max, 1);
+        pa.cq = ctx->d_cq; pa.cn = ctx->d_cn; pa.xl = ctx->d_lb; pa.nn_stride = std::max(n_max, 1);
         pa.n_pairs = n_pairs; pa.groups = p_groups; pa.group_ctas = p_group_ctas; pa.iterations = prm->max_iterations;
         pa.max_d2 = max_d2; pa.min_corr = min_corr; pa.pivot_eps = pivot_eps; pa.nn_out = nn_out;
         void *kargs[] = {&pa};

@@ -9,8 +9,11 @@
 //   * Consecutive source points (a piece of a scan line of an organised cloud) are neighbours in space, so
 //     their search balls overlap.  The warp takes the bounding box (in cell space) of the balls of a group of
 //     pending queries; every row of cells (fixed y,z; contiguous along x in the cell-sorted target) that
-//     crosses the box is ONE contiguous range of float4 points: two cell-start loads per row, then one
-//     cp.async.bulk (TMA) per row into the warp's tile, completion counted by the warp's mbarrier.
+//     crosses the box is ONE contiguous range of float4 points: two cell-start loads per row, then an
+//     asynchronous copy into the warp's tile: per-lane 16-byte cp.async (LDGSTS) by default -- rows are short
+//     (~10 points) and a TMA bulk copy needs warp-uniform operands, so one cp.async.bulk per row costs a
+//     ~10-instruction serialised issue per lane (measured: 13 % of all instructions); -DTS_USE_TMA keeps that
+//     variant (completion counted by the warp's mbarrier) for comparison.
 //   * The 32 lanes split the tile between them: with n queries in the group, 32/n lanes work on each query
 //     (a lone pending query of a late iteration is served by all 32 lanes), partial results merged by
 //     shuffles.  Shared-memory reads are broadcasts, there is no divergence, ~11 FP32-pipe instructions per
@@ -83,6 +86,15 @@ __device__ __forceinline__ void ts_fence_proxy_async()
 {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
+// 16-byte asynchronous copy global -> shared (LDGSTS): per-lane addresses, no register staging, fire and forget
+__device__ __forceinline__ void ts_cp_async16(void *dst, const void *src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(ts_smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void ts_cp_async_wait_all()
+{
+    asm volatile("cp.async.wait_all;" ::: "memory");
+}
 
 struct TileBest {             // nearest candidate (point + original index in .w), its d2, and the runner-up's d2
     float4 bq; float bd; float sd;
@@ -145,23 +157,44 @@ __device__ __forceinline__ void tile_compare_pass(const float4 *__restrict__ buf
 // Exact NN of the pending queries of one warp.  (px,py,pz): this lane's query; r: its search radius hint in
 // metres (any positive finite value; a valid upper bound on the NN distance makes the first pass final);
 // `pending`: lane has a query.  gate_r: nothing farther than this can be accepted (INFINITY: no gate).
-// buf: this warp's tile (TS_CAP float4); bar/parity: this warp's mbarrier and its phase.  On return, for
-// pending lanes: B = nearest target point and runner-up distance among ALL target points (B.bq.w = INT_MAX
-// when the target has no point within reach), lbound = lower bound on the distance from the query to every
-// target point other than the winner.
-__device__ __forceinline__ void tile_search(const GridView &g, const GridParams &gp, float px, float py, float pz, float r,
-                                            bool pending, float gate_r, float slack, float4 *__restrict__ buf,
-                                            uint64_t *bar, uint32_t &parity, int lane, TileBest &B, float &lbound TS_TM_ARG)
+// buf: this warp's tile (TS_CAP float4); bar/parity (TMA variant): this warp's mbarrier and its phase.  Returns,
+// for pending lanes: bq/bd = nearest target point among ALL target points and its squared distance (bd = INFINITY
+// when the target has no point within reach), lb = lower bound on the distance from the query to every target
+// point other than the winner.
+struct TileCfg {              // one search level (fine grid / decimated grid); lives in shared memory
+    GridParams gp; const uint32_t *cell_start; const float4 *pts; float slack; float gate_r;
+};
+struct TileOut { float4 bq; float bd; float lb; };
+
+#ifdef TS_USE_TMA
+#define TS_BAR_ARG , uint64_t *bar, uint32_t *parity_p
+#else
+#define TS_BAR_ARG
+#endif
+
+// NOT inlined on purpose: the caller keeps 29 double accumulators and a prefetched chunk in registers; as a real
+// call the search spills them only around itself (the rare path of a late iteration) instead of raising the
+// register pressure of the whole streaming loop.
+__device__ __noinline__ TileOut tile_search(const TileCfg *cfg, float px, float py, float pz, float r, bool pending,
+                                            float4 *__restrict__ buf, int lane TS_BAR_ARG TS_TM_ARG)
 {
     TS_T0();
     const unsigned full = 0xffffffffu;
+    const GridParams gp = cfg->gp;
+    const uint32_t *__restrict__ cell_start = cfg->cell_start;
+    const float slack = cfg->slack, gate_r = cfg->gate_r;
+    TileBest B; float lbound = 0.f;
     tile_best_init(B);
-    lbound = 0.f;
+#ifdef TS_USE_TMA
+    uint32_t parity = *parity_p;
+#endif
     const float fx = grid_fcoord(px, gp.ox, gp.inv_cell), fy = grid_fcoord(py, gp.oy, gp.inv_cell), fz = grid_fcoord(pz, gp.oz, gp.inv_cell);
-    const float4 *__restrict__ sp = g.pts;
+    const float4 *__restrict__ sp = cfg->pts;
     bool todo = pending;
     r = fminf(r, gate_r * 1.00001f + 1e-6f);
+#ifdef TS_USE_TMA
     ts_fence_proxy_async();          // the tile may have been written with ordinary stores since the last bulk copy
+#endif
     for (int tries = 0; ; ++tries) {
         const unsigned todomask = __ballot_sync(full, todo);
         if (!todomask) break;
@@ -214,8 +247,8 @@ __device__ __forceinline__ void tile_search(const GridView &g, const GridParams 
                 if (t < rows) {
                     const int zi = t / ny_s;
                     const size_t base = ((size_t)(loz + zi) * gp.ny + (loy + (t - zi * ny_s))) * gp.nx;
-                    rs = __ldg(&g.cell_start[base + lox]);
-                    cnt = __ldg(&g.cell_start[base + hix + 1]) - rs;
+                    rs = __ldg(&cell_start[base + lox]);
+                    cnt = __ldg(&cell_start[base + hix + 1]) - rs;
                     STAT(2, 1);
                 }
                 t0 += 32;
@@ -232,19 +265,32 @@ __device__ __forceinline__ void tile_search(const GridView &g, const GridParams 
             uint32_t take = cnt;
             if (total > room) take = excl >= room ? 0u : min(cnt, room - excl);
             const uint32_t moved_pts = min(total, room);
+#ifdef TS_USE_TMA
             if (moved_pts > 0u) {
                 if (lane == 0) ts_mbar_expect_tx(bar, moved_pts * 16u);
                 __syncwarp();
                 if (take > 0u) ts_bulk_g2s(buf + fill + excl, sp + rs, take * 16u, bar);
             }
+#else
+            {
+                float4 *dst = buf + fill + excl;
+                const float4 *srcp = sp + rs;
+                for (uint32_t k = 0; k < take; ++k) ts_cp_async16(dst + k, srcp + k);
+            }
+#endif
             rs += take; cnt -= take;
             TS_T(2);
             carry = total > room;
             fill += (int)moved_pts;
             if ((carry || t0 >= rows) && fill > 0) {
+#ifdef TS_USE_TMA
                 if (lane == 0) ts_mbar_arrive(bar);
                 ts_mbar_wait(bar, parity);
                 parity ^= 1u;
+#else
+                ts_cp_async_wait_all();
+                __syncwarp();
+#endif
                 if (work) tile_compare_pass(buf, fill, sub, step, qx, qy, qz, W);
                 STAT(3, work ? fill / step : 0);
                 __syncwarp();
@@ -288,4 +334,10 @@ __device__ __forceinline__ void tile_search(const GridView &g, const GridParams 
         }
         TS_T(4);
     }
+#ifdef TS_USE_TMA
+    *parity_p = parity;
+#endif
+    TileOut o;
+    o.bq = B.bq; o.bd = B.bd; o.lb = lbound;
+    return o;
 }
