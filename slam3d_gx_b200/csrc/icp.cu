@@ -25,6 +25,7 @@
 //                         literal kernel and the verification mode (FP32-issue bound).
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <cmath>
 #include <algorithm>
 #include "context.h"
@@ -140,28 +141,25 @@ __global__ void __launch_bounds__(ICP_BLOCK) nn_brute_tma_kernel(const PairDesc 
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ int chol6_solve(const double A[6][6], const double g[6], double pivot_eps, double x[6])
 {
-    // fully unrolled: every index is a compile-time constant, so L, y live in registers (same operation order as
-    // chol6_solve of oracle/icp_oracle.c)
-    double L[6][6];
-    #pragma unroll
-    for (int i = 0; i < 6; ++i) {
-        #pragma unroll
-        for (int j = 0; j < 6; ++j) L[i][j] = 0.0;
-    }
+    // Square-root-free Cholesky (A = L D L^T), fully unrolled: every index is a compile-time constant, so L, D, y live
+    // in registers, and the dependent chain is 6 reciprocals instead of 6 square roots + 21 divisions.  The pivots D[j]
+    // are exactly the quantities chol6_solve of oracle/icp_oracle.c tests (its s = L[j][j]^2), so the rank-deficiency
+    // verdict is the same; the solution agrees to rounding.
+    double L[6][6], D[6], iD[6];
     int bad = 0;
     #pragma unroll
     for (int j = 0; j < 6; ++j) {
         double s = A[j][j];
         #pragma unroll
-        for (int k = 0; k < j; ++k) s -= L[j][k] * L[j][k];
+        for (int k = 0; k < j; ++k) s -= L[j][k] * L[j][k] * D[k];
         if (!(s > pivot_eps * A[j][j]) || !(A[j][j] > 0.0)) bad = 1;
-        L[j][j] = sqrt(s);
+        D[j] = s; iD[j] = 1.0 / s;
         #pragma unroll
         for (int i = j + 1; i < 6; ++i) {
             double v = A[i][j];
             #pragma unroll
-            for (int k = 0; k < j; ++k) v -= L[i][k] * L[j][k];
-            L[i][j] = v / L[j][j];
+            for (int k = 0; k < j; ++k) v -= L[i][k] * L[j][k] * D[k];
+            L[i][j] = v * iD[j];
         }
     }
     if (bad) return 1;
@@ -171,14 +169,14 @@ __device__ __forceinline__ int chol6_solve(const double A[6][6], const double g[
         double v = g[i];
         #pragma unroll
         for (int k = 0; k < i; ++k) v -= L[i][k] * y[k];
-        y[i] = v / L[i][i];
+        y[i] = v;
     }
     #pragma unroll
     for (int i = 5; i >= 0; --i) {
-        double v = y[i];
+        double v = y[i] * iD[i];
         #pragma unroll
         for (int k = i + 1; k < 6; ++k) v -= L[k][i] * x[k];
-        x[i] = v / L[i][i];
+        x[i] = v;
     }
     return 0;
 }
@@ -595,6 +593,7 @@ struct PersistArgs {
     int n_pairs, groups, group_ctas, iterations;
     float max_d2; int min_corr; double pivot_eps;
     int32_t *nn_out;             // correspondences of the last iteration (single pair) or null
+    float hint_cells;            // first-guess search radius after a big pose update, in cells
 };
 
 __device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned *p)      // polling load: no L1 invalidate per poll
@@ -683,8 +682,10 @@ __global__ void __launch_bounds__(TS_BLOCK, 1) icp_persist_kernel(const PersistA
             // sees the same query every iteration).  The four 16-byte loads of the NEXT chunk are issued before the
             // current one is processed, so a late iteration (nearly every query keeps its correspondence) is one pass
             // over 64 B/point with the latency of one chunk exposed, not of every chunk.
+            // chunk c belongs to CTA (c mod group_ctas), warp ((c / group_ctas) mod TS_WARPS): every CTA samples the whole
+            // cloud evenly (search cost varies smoothly with depth), which keeps the group barrier wait short
             const int cstride = a.group_ctas * TS_WARPS;
-            int chunk = rank * TS_WARPS + warp;
+            int chunk = rank + a.group_ctas * warp;
             float4 n_p = make_float4(0.f, 0.f, 0.f, 0.f), n_q = n_p, n_xl = n_p, n_nv = n_p;
             {
                 const int i0 = (chunk << 5) + lane;
@@ -734,7 +735,7 @@ __global__ void __launch_bounds__(TS_BLOCK, 1) icp_persist_kernel(const PersistA
                                 const float3 xo = s3d_xform(Tp, p.x, p.y, p.z);
                                 const float step_mv = sqrtf(s3d_dist2(x.x, x.y, x.z, xo.x, xo.y, xo.z));
                                 r = dq * 1.00001f + slack;
-                                if (step_mv > 0.25f * cell) r = fminf(r, cell + slack);
+                                if (step_mv > 0.25f * cell) r = fminf(r, a.hint_cells * cell + slack);
                             }
                         }
                     }
@@ -1029,6 +1030,7 @@ extern "C" int s3d_register_batch(s3d_ctx *ctx, const s3d_cloud *const *src, con
         pa.cq = ctx->d_cq; pa.cn = ctx->d_cn; pa.xl = ctx->d_lb; pa.nn_stride = std::max(n_max, 1);
         pa.n_pairs = n_pairs; pa.groups = p_groups; pa.group_ctas = p_group_ctas; pa.iterations = prm->max_iterations;
         pa.max_d2 = max_d2; pa.min_corr = min_corr; pa.pivot_eps = pivot_eps; pa.nn_out = nn_out;
+        { static const char *e = getenv("S3D_HINT_CELLS"); pa.hint_cells = e ? (float)atof(e) : 1.0f; }
         void *kargs[] = {&pa};
         const void *fn = plane ? (const void *)icp_persist_kernel<S3D_ESTIMATOR_POINT_TO_PLANE> : (const void *)icp_persist_kernel<S3D_ESTIMATOR_SVD>;
         S3D_CUDA(ctx, cudaLaunchCooperativeKernel(fn, dim3(p_groups * p_group_ctas), dim3(TS_BLOCK), kargs, p_smem, ctx->stream));
