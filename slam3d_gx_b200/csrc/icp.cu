@@ -651,7 +651,15 @@ __global__ void __launch_bounds__(TS_BLOCK, 1) icp_persist_kernel(const PersistA
         float4 *my_cq = a.cq + (size_t)pair * a.nn_stride;
         float4 *my_cn = a.cn + (size_t)pair * a.nn_stride;
         float4 *my_xl = a.xl + (size_t)pair * a.nn_stride;
-        const int nchunks = (d.n_src + 31) >> 5;
+        // Work is dealt out in OCTETS (8 consecutive source points = 128 contiguous bytes of every per-query array):
+        // octet u belongs to warp slot (u mod W) of the group (W = all its warps; slot = rank + group_ctas * warp, so
+        // consecutive octets go to different CTAs).  A warp's k-th chunk is its octets 4k..4k+3, one per 8 lanes: every
+        // warp samples the whole cloud evenly (the search cost varies smoothly with depth) and warps differ by at most
+        // one octet, which keeps both the CTA and the group barrier waits short.  An octet is also the group one
+        // search box is built for (tile_search.cuh).
+        const int nunits = (d.n_src + 7) >> 3;
+        const int W = a.group_ctas * TS_WARPS, wslot = rank + a.group_ctas * warp;
+#define CHUNK_UNIT(kc) (wslot + W * (4 * (kc) + (lane >> 3)))        // octet handled by this lane in the warp's kc-th chunk
 
         for (int it = 0; it < a.iterations; ++it) {
             if (st.status != 0) break;            // failed pairs stop; every CTA of the group sees the same state
@@ -682,25 +690,22 @@ __global__ void __launch_bounds__(TS_BLOCK, 1) icp_persist_kernel(const PersistA
             // sees the same query every iteration).  The four 16-byte loads of the NEXT chunk are issued before the
             // current one is processed, so a late iteration (nearly every query keeps its correspondence) is one pass
             // over 64 B/point with the latency of one chunk exposed, not of every chunk.
-            // chunk c belongs to CTA (c mod group_ctas), warp ((c / group_ctas) mod TS_WARPS): every CTA samples the whole
-            // cloud evenly (search cost varies smoothly with depth), which keeps the group barrier wait short
-            const int cstride = a.group_ctas * TS_WARPS;
-            int chunk = rank + a.group_ctas * warp;
+            int kc = 0;
             float4 n_p = make_float4(0.f, 0.f, 0.f, 0.f), n_q = n_p, n_xl = n_p, n_nv = n_p;
             {
-                const int i0 = (chunk << 5) + lane;
-                if (chunk < nchunks && i0 < d.n_src) {
+                const int u0 = CHUNK_UNIT(0), i0 = (u0 << 3) + (lane & 7);
+                if (u0 < nunits && i0 < d.n_src) {
                     n_p = d.src[i0];
                     if (it > 0) { n_q = my_cq[i0]; n_xl = my_xl[i0]; if (EST == S3D_ESTIMATOR_POINT_TO_PLANE) n_nv = my_cn[i0]; }
                 }
             }
-            for (; chunk < nchunks; chunk += cstride) {
-                const int i = (chunk << 5) + lane;
-                const bool in = i < d.n_src;
+            for (; wslot + W * 4 * kc < nunits; ++kc) {          // warp-uniform: the chunk's first octet exists
+                const int u = CHUNK_UNIT(kc), i = (u << 3) + (lane & 7);
+                const bool in = u < nunits && i < d.n_src;
                 const float4 p = n_p, q_old = n_q, xl = n_xl, nv_old = n_nv;
                 {
-                    const int i1 = ((chunk + cstride) << 5) + lane;
-                    if (chunk + cstride < nchunks && i1 < d.n_src) {
+                    const int u1 = CHUNK_UNIT(kc + 1), i1 = (u1 << 3) + (lane & 7);
+                    if (u1 < nunits && i1 < d.n_src) {
                         n_p = d.src[i1];
                         if (it > 0) { n_q = my_cq[i1]; n_xl = my_xl[i1]; if (EST == S3D_ESTIMATOR_POINT_TO_PLANE) n_nv = my_cn[i1]; }
                     }

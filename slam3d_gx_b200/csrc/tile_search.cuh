@@ -36,9 +36,7 @@
 #ifndef TS_CAP
 #define TS_CAP 512            // candidates per warp tile (8 KiB)
 #endif
-#ifndef TS_GROUP
-#define TS_GROUP 8            // queries per box (power of two <= 32)
-#endif
+#define TS_GROUP 8            // queries per box: an aligned octet of lanes
 #define TS_MAX_TRIES 64
 
 #if defined(S3D_PHASES)
@@ -199,8 +197,8 @@ __device__ __noinline__ TileOut tile_search(const TileCfg *cfg, float px, float 
         const unsigned todomask = __ballot_sync(full, todo);
         if (!todomask) break;
         // ---- this pass's group: the first TS_GROUP pending queries, minus those whose radius is far above the rest ----
-        unsigned grp = todomask;
-        if (__popc(grp) > TS_GROUP) grp &= (2u << (__fns(todomask, 0, TS_GROUP) & 31)) - 1u;
+        // (an aligned octet of lanes = 8 consecutive source points; different octets may be far apart in space)
+        unsigned grp = todomask & (0xffu << ((__ffs(todomask) - 1) & 24));
         const bool ingrp = (grp >> lane) & 1u;
         float rmin = ingrp ? r : INFINITY;
         #pragma unroll
