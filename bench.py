@@ -270,10 +270,10 @@ def main():
             "gpu_launches": total_launches,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": "icp_iter_kernel<point_to_plane, grid>", "peak_source": peak_src,
+                         "traffic": traffic, "kernel": "icp_persist_kernel<point_to_plane> (one cooperative launch = all 30 iterations)", "peak_source": peak_src,
                          "algorithmic_bytes_per_iteration": B_ALG, "iterations_per_launch": units_per_launch,
                          "avg_launch_us": per_launch_s * 1e6,
-                         "note": "latency/ALU-bound gather kernel; data set is L2 resident after the first iteration (SURVEY.md 0.4, 8d)"},
+                         "note": "achieved = algorithmic bytes (16N+32M per iteration, SURVEY.md 8d) / measured kernel time; the single-pair working set (~45 MB) is L2 resident, so the kernel is bound by search issue slots and per-iteration barrier latency, not by HBM"},
             "breakdown_ms_per_step": {"index_build": index_ms / args.steps, "iterations": iter_ms / args.steps},
         }
         if not args.no_cpu_baseline and world == 1:

@@ -30,6 +30,58 @@ void *s3d_pinned(s3d_ctx *ctx, size_t bytes)
     return ctx->h_pinned;
 }
 
+// ---- caching device allocator --------------------------------------------------------------------
+#define S3D_POOL_MAX_CACHED ((size_t)16 << 30)      // beyond this, freed blocks really go back to the driver
+
+static size_t pool_round(size_t bytes)
+{
+    if (bytes < 4096) return 4096;
+    size_t step = (size_t)1 << 12;
+    while ((step << 4) <= bytes) step <<= 1;         // ~6-12 % granularity: blocks of similar clouds are interchangeable
+    return (bytes + step - 1) / step * step;
+}
+
+cudaError_t s3d_dev_alloc(s3d_ctx *ctx, void **out, size_t bytes)
+{
+    const size_t want = pool_round(bytes);
+    auto it = ctx->pool_free.lower_bound(want);
+    if (it != ctx->pool_free.end() && it->first <= want + want / 4) {
+        *out = it->second;
+        ctx->pool_live[it->second] = it->first;
+        ctx->pool_cached -= it->first;
+        ctx->pool_free.erase(it);
+        return cudaSuccess;
+    }
+    cudaError_t e = cudaMalloc(out, want);
+    if (e != cudaSuccess && !ctx->pool_free.empty()) {   // out of memory with blocks cached: give them back and retry
+        cudaGetLastError();
+        s3d_dev_pool_release(ctx);
+        e = cudaMalloc(out, want);
+    }
+    if (e == cudaSuccess) ctx->pool_live[*out] = want;
+    return e;
+}
+
+void s3d_dev_free(s3d_ctx *ctx, void *p)
+{
+    if (!p) return;
+    auto it = ctx->pool_live.find(p);
+    if (it == ctx->pool_live.end()) { cudaFree(p); return; }
+    const size_t sz = it->second;
+    ctx->pool_live.erase(it);
+    if (ctx->pool_cached + sz > S3D_POOL_MAX_CACHED) { cudaFree(p); return; }
+    ctx->pool_free.insert({sz, p});
+    ctx->pool_cached += sz;
+}
+
+void s3d_dev_pool_release(s3d_ctx *ctx)
+{
+    cudaStreamSynchronize(ctx->stream);
+    for (auto &kv : ctx->pool_free) cudaFree(kv.second);
+    ctx->pool_free.clear();
+    ctx->pool_cached = 0;
+}
+
 extern "C" int s3d_abi_version(void) { return S3D_ABI_VERSION; }
 
 extern "C" int s3d_create(s3d_ctx **out, int device_id)
@@ -68,6 +120,9 @@ extern "C" void s3d_destroy(s3d_ctx *ctx)
     cudaFree(ctx->d_partials); cudaFree(ctx->d_nn_idx); cudaFree(ctx->d_nn_d2); cudaFree(ctx->d_nn_pos); cudaFree(ctx->d_last_nn);
     cudaFree(ctx->d_cq); cudaFree(ctx->d_cn); cudaFree(ctx->d_lb); cudaFree(ctx->d_barriers);
     cudaFree(ctx->d_seg);
+    s3d_dev_pool_release(ctx);
+    for (auto &kv : ctx->pool_live) cudaFree(kv.first);     // handles the caller never freed
+    ctx->pool_live.clear();
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     for (int i = 0; i < 4; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -94,7 +149,7 @@ static int cloud_alloc(s3d_ctx *ctx, int n, s3d_cloud **out)
 {
     s3d_cloud *c = new s3d_cloud();
     c->n = n;
-    cudaError_t e = cudaMalloc(&c->d_pts, sizeof(float4) * (size_t)(n > 0 ? n : 1));
+    cudaError_t e = s3d_dev_alloc_t(ctx, &c->d_pts, sizeof(float4) * (size_t)(n > 0 ? n : 1));
     if (e != cudaSuccess) { delete c; return s3d_fail(ctx, S3D_E_CUDA, "cudaMalloc cloud", e); }
     *out = c;
     return S3D_OK;
@@ -134,12 +189,12 @@ extern "C" int s3d_cloud_upload(s3d_ctx *ctx, const float *xyz, int stride_float
             S3D_LAUNCHED(ctx);
         } else {
             float *tmp = nullptr;
-            S3D_CUDA(ctx, cudaMalloc(&tmp, bytes));
+            S3D_CUDA(ctx, s3d_dev_alloc_t(ctx, &tmp, bytes));
             S3D_CUDA(ctx, cudaMemcpyAsync(tmp, xyz, bytes, cudaMemcpyHostToDevice, ctx->stream));
             pack_xyz_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(tmp, stride_floats, n, c->d_pts);
             S3D_LAUNCHED(ctx);
             S3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-            cudaFree(tmp);
+            s3d_dev_free(ctx, tmp);
         }
         S3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     }
@@ -196,9 +251,9 @@ extern "C" int s3d_cloud_from_depth(s3d_ctx *ctx, const uint16_t *depth, int wid
     int npx = width * height;
     int nblocks = (npx + S3D_COMPACT_BLOCK - 1) / S3D_COMPACT_BLOCK;
     uint16_t *d_depth = nullptr; uint32_t *d_counts = nullptr; float4 *d_tmp = nullptr;
-    S3D_CUDA(ctx, cudaMalloc(&d_depth, sizeof(uint16_t) * (size_t)npx));
-    S3D_CUDA(ctx, cudaMalloc(&d_counts, sizeof(uint32_t) * (size_t)(nblocks + 1)));
-    S3D_CUDA(ctx, cudaMalloc(&d_tmp, sizeof(float4) * (size_t)npx));
+    S3D_CUDA(ctx, s3d_dev_alloc_t(ctx, &d_depth, sizeof(uint16_t) * (size_t)npx));
+    S3D_CUDA(ctx, s3d_dev_alloc_t(ctx, &d_counts, sizeof(uint32_t) * (size_t)(nblocks + 1)));
+    S3D_CUDA(ctx, s3d_dev_alloc_t(ctx, &d_tmp, sizeof(float4) * (size_t)npx));
     S3D_CUDA(ctx, cudaMemcpyAsync(d_depth, depth, sizeof(uint16_t) * (size_t)npx, cudaMemcpyHostToDevice, ctx->stream));
     DepthPred pred{d_depth, 0.0, cam->factor, z_max};
     DepthEmit emit{d_depth, width, cam->fx, cam->fy, cam->cx, cam->cy, cam->factor, d_tmp};
@@ -217,8 +272,8 @@ extern "C" int s3d_cloud_from_depth(s3d_ctx *ctx, const uint16_t *depth, int wid
         rc = cudaMemcpyAsync(c->d_pts, d_tmp, sizeof(float4) * (size_t)total, cudaMemcpyDeviceToDevice, ctx->stream) == cudaSuccess
                  ? S3D_OK : s3d_fail(ctx, S3D_E_CUDA, "copy compacted cloud");
     cudaStreamSynchronize(ctx->stream);
-    cudaFree(d_depth); cudaFree(d_counts); cudaFree(d_tmp);
-    if (rc) { if (c) { cudaFree(c->d_pts); delete c; } return rc; }
+    s3d_dev_free(ctx, d_depth); s3d_dev_free(ctx, d_counts); s3d_dev_free(ctx, d_tmp);
+    if (rc) { if (c) { s3d_dev_free(ctx, c->d_pts); delete c; } return rc; }
     *out = c;
     return S3D_OK;
 }
@@ -227,7 +282,7 @@ extern "C" int s3d_cloud_from_depth(s3d_ctx *ctx, const uint16_t *depth, int wid
 
 static int ensure_normals(s3d_ctx *ctx, s3d_cloud *c)
 {
-    if (!c->d_nrm) S3D_CUDA(ctx, cudaMalloc(&c->d_nrm, sizeof(float4) * (size_t)(c->n > 0 ? c->n : 1)));
+    if (!c->d_nrm) S3D_CUDA(ctx, s3d_dev_alloc_t(ctx, &c->d_nrm, sizeof(float4) * (size_t)(c->n > 0 ? c->n : 1)));
     return S3D_OK;
 }
 
@@ -240,12 +295,12 @@ extern "C" int s3d_cloud_set_normals(s3d_ctx *ctx, s3d_cloud *cloud, const float
     if (n > 0) {
         float *tmp = nullptr;
         size_t bytes = sizeof(float) * (size_t)n * stride_floats;
-        S3D_CUDA(ctx, cudaMalloc(&tmp, bytes));
+        S3D_CUDA(ctx, s3d_dev_alloc_t(ctx, &tmp, bytes));
         S3D_CUDA(ctx, cudaMemcpyAsync(tmp, nrm, bytes, cudaMemcpyHostToDevice, ctx->stream));
         pack_normals_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(tmp, stride_floats, n, cloud->d_nrm);
         S3D_LAUNCHED(ctx);
         S3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        cudaFree(tmp);
+        s3d_dev_free(ctx, tmp);
     }
     cloud->grid.valid = false; // sorted normals are stale
     return S3D_OK;
@@ -305,9 +360,10 @@ extern "C" void s3d_cloud_free(s3d_ctx *ctx, s3d_cloud *cloud)
 {
     if (!cloud) return;
     if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
-    s3d_grid_free(cloud->grid);
-    s3d_grid_free(cloud->coarse);
-    cudaFree(cloud->d_coarse_pts);
-    cudaFree(cloud->d_pts); cudaFree(cloud->d_nrm); cudaFree(cloud->d_labels);
+    if (!ctx) { delete cloud; return; }     // cannot return device memory without its context (leak rather than crash)
+    s3d_grid_free(ctx, cloud->grid);
+    s3d_grid_free(ctx, cloud->coarse);
+    s3d_dev_free(ctx, cloud->d_coarse_pts);
+    s3d_dev_free(ctx, cloud->d_pts); s3d_dev_free(ctx, cloud->d_nrm); s3d_dev_free(ctx, cloud->d_labels);
     delete cloud;
 }

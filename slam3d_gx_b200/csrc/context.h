@@ -99,14 +99,24 @@ struct s3d_ctx {
     void *d_seg = nullptr;
     void *h_pinned = nullptr; size_t cap_pinned = 0;
     std::map<uint64_t, cudaGraphExec_t> graphs;
+    // caching device allocator: clouds and search indices come and go per frame, cudaMalloc/cudaFree of their
+    // 10..40 MB buffers costs milliseconds; freed blocks are kept and handed out again (same stream => ordered)
+    std::map<void *, size_t> pool_live;
+    std::multimap<size_t, void *> pool_free;
+    size_t pool_cached = 0;
 };
 
 int s3d_fail(s3d_ctx *ctx, int code, const char *what, cudaError_t e = cudaSuccess);
 #define S3D_CUDA(ctx, call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return s3d_fail(ctx, S3D_E_CUDA, #call, e__); } while (0)
 #define S3D_LAUNCHED(ctx) do { (ctx)->launches++; cudaError_t e__ = cudaGetLastError(); if (e__ != cudaSuccess) return s3d_fail(ctx, S3D_E_CUDA, "kernel launch", e__); } while (0)
 
+// device memory pool (cloud.cu)
+cudaError_t s3d_dev_alloc(s3d_ctx *ctx, void **out, size_t bytes);
+void s3d_dev_free(s3d_ctx *ctx, void *p);
+void s3d_dev_pool_release(s3d_ctx *ctx);
+template <typename T> static inline cudaError_t s3d_dev_alloc_t(s3d_ctx *ctx, T **out, size_t bytes) { return s3d_dev_alloc(ctx, reinterpret_cast<void **>(out), bytes); }
 // grid.cu
 int s3d_grid_build(s3d_ctx *ctx, s3d_cloud *cloud, float cell);
-void s3d_grid_free(GridIndex &g);
+void s3d_grid_free(s3d_ctx *ctx, GridIndex &g);
 // pinned staging
 void *s3d_pinned(s3d_ctx *ctx, size_t bytes);

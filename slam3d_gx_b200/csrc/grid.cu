@@ -200,10 +200,10 @@ __global__ void __launch_bounds__(256) grid_scatter_kernel(const float4 *__restr
     }
 }
 
-void s3d_grid_free(GridIndex &g)
+void s3d_grid_free(s3d_ctx *ctx, GridIndex &g)
 {
-    cudaFree(g.d_params); cudaFree(g.d_cell_start); cudaFree(g.d_sorted_pts); cudaFree(g.d_sorted_nrm);
-    cudaFree(g.d_rank); cudaFree(g.d_bbox); cudaFree(g.d_block_sums); cudaFree(g.d_rowmask);
+    s3d_dev_free(ctx, g.d_params); s3d_dev_free(ctx, g.d_cell_start); s3d_dev_free(ctx, g.d_sorted_pts); s3d_dev_free(ctx, g.d_sorted_nrm);
+    s3d_dev_free(ctx, g.d_rank); s3d_dev_free(ctx, g.d_bbox); s3d_dev_free(ctx, g.d_block_sums); s3d_dev_free(ctx, g.d_rowmask);
     g = GridIndex();
 }
 
@@ -231,17 +231,17 @@ static int grid_build_raw(s3d_ctx *ctx, GridIndex &g, const float4 *d_pts, const
 {
     size_t np = (size_t)(n > 0 ? n : 1);
     if (g.cap_points < n || g.cap_cells < max_cells || !g.d_params) {
-        s3d_grid_free(g);
-        S3D_CUDA(ctx, cudaMalloc(&g.d_params, sizeof(GridParams)));
-        S3D_CUDA(ctx, cudaMalloc(&g.d_cell_start, sizeof(uint32_t) * ((size_t)max_cells + 16)));
-        S3D_CUDA(ctx, cudaMalloc(&g.d_sorted_pts, sizeof(float4) * np));
-        S3D_CUDA(ctx, cudaMalloc(&g.d_rank, sizeof(uint32_t) * np));
-        S3D_CUDA(ctx, cudaMalloc(&g.d_bbox, sizeof(uint32_t) * 8));
-        S3D_CUDA(ctx, cudaMalloc(&g.d_block_sums, sizeof(uint32_t) * (max_cells / SCAN_TILE + 8)));
-        S3D_CUDA(ctx, cudaMalloc(&g.d_rowmask, sizeof(uint32_t) * ((size_t)max_cells / 8 + 8192)));
+        s3d_grid_free(ctx, g);
+        S3D_CUDA(ctx, s3d_dev_alloc_t(ctx, &g.d_params, sizeof(GridParams)));
+        S3D_CUDA(ctx, s3d_dev_alloc_t(ctx, &g.d_cell_start, sizeof(uint32_t) * ((size_t)max_cells + 16)));
+        S3D_CUDA(ctx, s3d_dev_alloc_t(ctx, &g.d_sorted_pts, sizeof(float4) * np));
+        S3D_CUDA(ctx, s3d_dev_alloc_t(ctx, &g.d_rank, sizeof(uint32_t) * np));
+        S3D_CUDA(ctx, s3d_dev_alloc_t(ctx, &g.d_bbox, sizeof(uint32_t) * 8));
+        S3D_CUDA(ctx, s3d_dev_alloc_t(ctx, &g.d_block_sums, sizeof(uint32_t) * (max_cells / SCAN_TILE + 8)));
+        S3D_CUDA(ctx, s3d_dev_alloc_t(ctx, &g.d_rowmask, sizeof(uint32_t) * ((size_t)max_cells / 8 + 8192)));
         g.cap_points = n; g.cap_cells = max_cells;
     }
-    if (d_nrm && !g.d_sorted_nrm) S3D_CUDA(ctx, cudaMalloc(&g.d_sorted_nrm, sizeof(float4) * (size_t)(g.cap_points > 0 ? g.cap_points : 1)));
+    if (d_nrm && !g.d_sorted_nrm) S3D_CUDA(ctx, s3d_dev_alloc_t(ctx, &g.d_sorted_nrm, sizeof(float4) * (size_t)(g.cap_points > 0 ? g.cap_points : 1)));
     cudaStream_t st = ctx->stream;
     const int wide = ctx->sm_count * 8;
     const int scan_blocks = (int)(max_cells / SCAN_TILE) + 1;
@@ -272,8 +272,8 @@ int s3d_grid_build(s3d_ctx *ctx, s3d_cloud *c, float cell)
     if (c->n >= S3D_COARSE_MIN_POINTS) {
         int nc = c->n / S3D_COARSE_STRIDE;
         if (c->cap_coarse_pts < nc) {
-            cudaFree(c->d_coarse_pts); c->d_coarse_pts = nullptr;
-            S3D_CUDA(ctx, cudaMalloc(&c->d_coarse_pts, sizeof(float4) * (size_t)nc));
+            s3d_dev_free(ctx, c->d_coarse_pts); c->d_coarse_pts = nullptr;
+            S3D_CUDA(ctx, s3d_dev_alloc_t(ctx, &c->d_coarse_pts, sizeof(float4) * (size_t)nc));
             c->cap_coarse_pts = nc;
         }
         decimate_kernel<<<std::min(ctx->sm_count * 8, (nc + 255) / 256), 256, 0, ctx->stream>>>(c->d_pts, nc, S3D_COARSE_STRIDE, c->d_coarse_pts);

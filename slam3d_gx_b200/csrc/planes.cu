@@ -219,8 +219,8 @@ extern "C" int s3d_segment_planes(s3d_ctx *ctx, s3d_cloud *cloud, const s3d_plan
     *n_planes_out = 0;
     const int n = cloud->n;
     const size_t np = (size_t)(n > 0 ? n : 1);
-    if (!cloud->d_nrm) S3D_CUDA(ctx, cudaMalloc(&cloud->d_nrm, sizeof(float4) * np));
-    if (!cloud->d_labels) S3D_CUDA(ctx, cudaMalloc(&cloud->d_labels, sizeof(int32_t) * np));
+    if (!cloud->d_nrm) S3D_CUDA(ctx, s3d_dev_alloc_t(ctx, &cloud->d_nrm, sizeof(float4) * np));
+    if (!cloud->d_labels) S3D_CUDA(ctx, s3d_dev_alloc_t(ctx, &cloud->d_labels, sizeof(int32_t) * np));
     cloud->grid.valid = false;
 
     const int n_cand = prm->max_iterations + PLANE_CANDIDATES_EXTRA;
