@@ -663,15 +663,15 @@ __global__ void __launch_bounds__(TS_BLOCK, 1) icp_persist_kernel(const PersistA
 
         for (int it = 0; it < a.iterations; ++it) {
             if (st.status != 0) break;            // failed pairs stop; every CTA of the group sees the same state
-            float T[12], Tp[12];
+            float T[12];                          // (the previous pose stays in shared memory: it is needed on rare paths only)
             #pragma unroll
-            for (int k = 0; k < 12; ++k) { T[k] = st.Tf[k]; Tp[k] = st.Tf_prev[k]; }
+            for (int k = 0; k < 12; ++k) T[k] = st.Tf[k];
             const bool last = (it == a.iterations - 1);
             // float pose bitwise unchanged since the previous iteration: every transformed point is bitwise the same,
             // so every correspondence of the previous iteration is still the exact answer
             bool same_pose = it > 0;
             #pragma unroll
-            for (int k = 0; k < 12; ++k) same_pose = same_pose && (__float_as_uint(T[k]) == __float_as_uint(Tp[k]));
+            for (int k = 0; k < 12; ++k) same_pose = same_pose && (__float_as_uint(T[k]) == __float_as_uint(st.Tf_prev[k]));
             double acc[29];
             #pragma unroll
             for (int k = 0; k < 29; ++k) acc[k] = 0.0;
@@ -737,7 +737,7 @@ __global__ void __launch_bounds__(TS_BLOCK, 1) icp_persist_kernel(const PersistA
                                 // The old correspondence is a real target point, so dq bounds the ball.  After a small move it is
                                 // also tight; after a big pose update (first iterations) the point slid along the surface and one
                                 // cell is the better first guess (tile_search verifies and widens when needed).
-                                const float3 xo = s3d_xform(Tp, p.x, p.y, p.z);
+                                const float3 xo = s3d_xform(st.Tf_prev, p.x, p.y, p.z);
                                 const float step_mv = sqrtf(s3d_dist2(x.x, x.y, x.z, xo.x, xo.y, xo.z));
                                 r = dq * 1.00001f + slack;
                                 if (step_mv > 0.25f * cell) r = fminf(r, a.hint_cells * cell + slack);
@@ -822,11 +822,13 @@ __global__ void __launch_bounds__(TS_BLOCK, 1) icp_persist_kernel(const PersistA
             __syncthreads();
             PHASE(9);
             if (a.group_ctas > 1 && threadIdx.x == 0) {
-                __threadfence();
+                // release (this CTA's row, written by its other threads before the __syncthreads above) -> arrive -> wait ->
+                // acquire (the other CTAs' rows); acq_rel fences, not the sequentially consistent __threadfence
+                asm volatile("fence.acq_rel.gpu;" ::: "memory");
                 atomicAdd(bar, 1u);
                 const unsigned target = epoch * (unsigned)a.group_ctas;
                 while (ld_relaxed_u32(bar) < target) { }
-                __threadfence();          // acquire: the other CTAs' rows are visible to everything after the barrier
+                asm volatile("fence.acq_rel.gpu;" ::: "memory");
             }
             __syncthreads();
             PHASE(10);

@@ -94,6 +94,16 @@ __device__ __forceinline__ void ts_cp_async_wait_all()
     asm volatile("cp.async.wait_all;" ::: "memory");
 }
 
+// The tile pointer crosses a real call (tile_search is not inlined), where the compiler no longer knows it is
+// shared memory and would emit generic LD.E (measured: the compare loop stalled on them).  Candidates are
+// therefore read with explicit ld.shared through the 32-bit shared address.
+__device__ __forceinline__ float4 ts_lds128(uint32_t saddr)
+{
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+    return v;
+}
+
 struct TileBest {             // nearest candidate (point + original index in .w), its d2, and the runner-up's d2
     float4 bq; float bd; float sd;
 };
@@ -113,7 +123,7 @@ __device__ __forceinline__ void tile_best_merge(TileBest &a, const float4 obq, f
 }
 
 // One lane's share of the tile: candidates sub, sub+step, ... < m against the query (qx,qy,qz); result merged into W.
-__device__ __forceinline__ void tile_compare_pass(const float4 *__restrict__ buf, int m, int sub, int step,
+__device__ __forceinline__ void tile_compare_pass(uint32_t sbuf, int m, int sub, int step,
                                                   float qx, float qy, float qz, TileBest &W)
 {
     // two independent running minima (even / odd visits) halve the dependent chain
@@ -121,7 +131,7 @@ __device__ __forceinline__ void tile_compare_pass(const float4 *__restrict__ buf
     int pk0 = -1, pk1 = -1;
     int k = sub;
     for (; k + step < m; k += 2 * step) {
-        const float4 a = buf[k], b = buf[k + step];
+        const float4 a = ts_lds128(sbuf + 16u * (uint32_t)k), b = ts_lds128(sbuf + 16u * (uint32_t)(k + step));
         const float da = s3d_dist2(qx, qy, qz, a.x, a.y, a.z), db = s3d_dist2(qx, qy, qz, b.x, b.y, b.z);
         const bool la = da < pd0, lbb = db < pd1;
         ps0 = fminf(ps0, fmaxf(pd0, da)); ps1 = fminf(ps1, fmaxf(pd1, db));
@@ -129,7 +139,7 @@ __device__ __forceinline__ void tile_compare_pass(const float4 *__restrict__ buf
         pk0 = la ? k : pk0; pk1 = lbb ? k + step : pk1;
     }
     if (k < m) {
-        const float4 a = buf[k];
+        const float4 a = ts_lds128(sbuf + 16u * (uint32_t)k);
         const float da = s3d_dist2(qx, qy, qz, a.x, a.y, a.z);
         const bool la = da < pd0;
         ps0 = fminf(ps0, fmaxf(pd0, da)); pd0 = fminf(pd0, da); pk0 = la ? k : pk0;
@@ -143,13 +153,13 @@ __device__ __forceinline__ void tile_compare_pass(const float4 *__restrict__ buf
         // equal distances: the lowest original index wins (rare; rescan this lane's share)
         int bi = INT_MAX;
         for (int kk = sub; kk < m; kk += step) {
-            const float4 q = buf[kk];
+            const float4 q = ts_lds128(sbuf + 16u * (uint32_t)kk);
             const float d2 = s3d_dist2(qx, qy, qz, q.x, q.y, q.z);
             const int qi = __float_as_int(q.w);
             if (d2 == pd && qi < bi) { bi = qi; pk = kk; }
         }
     }
-    tile_best_merge(W, buf[pk], pd, ps);
+    tile_best_merge(W, ts_lds128(sbuf + 16u * (uint32_t)pk), pd, ps);
 }
 
 // Exact NN of the pending queries of one warp.  (px,py,pz): this lane's query; r: its search radius hint in
@@ -188,6 +198,7 @@ __device__ __noinline__ TileOut tile_search(const TileCfg *cfg, float px, float 
 #endif
     const float fx = grid_fcoord(px, gp.ox, gp.inv_cell), fy = grid_fcoord(py, gp.oy, gp.inv_cell), fz = grid_fcoord(pz, gp.oz, gp.inv_cell);
     const float4 *__restrict__ sp = cfg->pts;
+    const uint32_t sbuf = ts_smem_u32(buf);
     bool todo = pending;
     r = fminf(r, gate_r * 1.00001f + 1e-6f);
 #ifdef TS_USE_TMA
@@ -271,9 +282,10 @@ __device__ __noinline__ TileOut tile_search(const TileCfg *cfg, float px, float 
             }
 #else
             {
-                float4 *dst = buf + fill + excl;
+                const uint32_t dst = sbuf + 16u * ((uint32_t)fill + excl);
                 const float4 *srcp = sp + rs;
-                for (uint32_t k = 0; k < take; ++k) ts_cp_async16(dst + k, srcp + k);
+                for (uint32_t k = 0; k < take; ++k)
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + 16u * k), "l"(srcp + k) : "memory");
             }
 #endif
             rs += take; cnt -= take;
@@ -289,7 +301,7 @@ __device__ __noinline__ TileOut tile_search(const TileCfg *cfg, float px, float 
                 ts_cp_async_wait_all();
                 __syncwarp();
 #endif
-                if (work) tile_compare_pass(buf, fill, sub, step, qx, qy, qz, W);
+                if (work) tile_compare_pass(sbuf, fill, sub, step, qx, qy, qz, W);
                 STAT(3, work ? fill / step : 0);
                 __syncwarp();
                 TS_CNT(26, fill);
