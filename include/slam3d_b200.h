@@ -153,6 +153,23 @@ int  s3d_cloud_download(s3d_ctx *ctx, const s3d_cloud *cloud, float *xyz, float 
 int  s3d_cloud_drop_index(s3d_ctx *ctx, s3d_cloud *cloud);
 void s3d_cloud_free(s3d_ctx *ctx, s3d_cloud *cloud);
 
+/* ---- filters and map fusion (the steps either side of the registration path) ------------------ */
+/* pcl::PassThrough on "z": keeps finite points with z_min <= z <= z_max, order preserved
+ * (reference src/GraphicEnd.cpp:283-285,291-292; src/saveOutput.cpp:40-46,81-84). */
+int  s3d_cloud_passthrough_z(s3d_ctx *ctx, const s3d_cloud *cloud, float z_min, float z_max, s3d_cloud **out);
+/* pcl::VoxelGrid with a cubic leaf: one centroid per occupied voxel, ascending voxel index
+ * (reference src/GraphicEnd.cpp:287-295 "grid_leaf"; src/saveOutput.cpp:44-46,76-79,90-93).
+ * S3D_E_ARG when the voxel indices would overflow 32 bits (PCL refuses the same input). */
+int  s3d_cloud_voxel_grid(s3d_ctx *ctx, const s3d_cloud *cloud, float leaf, s3d_cloud **out);
+/* pcl::transformPointCloud: out = T * cloud, T row-major 4x4 (reference src/saveOutput.cpp:87). */
+int  s3d_cloud_transform(s3d_ctx *ctx, const s3d_cloud *cloud, const double *T16, s3d_cloud **out);
+/* PointCloud::operator+= over a list (reference src/saveOutput.cpp:88). */
+int  s3d_cloud_concat(s3d_ctx *ctx, const s3d_cloud *const *clouds, int n_clouds, s3d_cloud **out);
+/* The key-frame fusion loop of saveOutput (reference src/saveOutput.cpp:47-95): per key frame voxel grid,
+ * z pass-through [0, z_max], transform by its pose (poses16: n_clouds row-major 4x4), append; voxel grid of the sum. */
+int  s3d_map_fuse(s3d_ctx *ctx, const s3d_cloud *const *clouds, const double *poses16, int n_clouds, float leaf, float z_max,
+                  s3d_cloud **out);
+
 /* ---- plane extraction (replaces GraphicEnd::extractPlanesAndGenerateImage, src/GraphicEnd.cpp:353-430,
  *      i.e. pcl::SACSegmentation + ExtractIndices; image painting is not on the path) ------------- */
 /* Writes per-point plane label and plane normal into the cloud (used as target normals by ICP). */

@@ -17,7 +17,7 @@ _LIB = None
 
 def build(force: bool = False) -> str:
     so = os.path.join(_HERE, "liboracle.so")
-    srcs = [os.path.join(_HERE, f) for f in ("icp_oracle.c", "plane_oracle.c", "oracle_common.h")]
+    srcs = [os.path.join(_HERE, f) for f in ("icp_oracle.c", "plane_oracle.c", "filter_oracle.c", "oracle_common.h")]
     stale = force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs)
     if stale:
         subprocess.run(["make", "-C", _HERE, "-B" if force else "-s"], check=True,
@@ -117,6 +117,37 @@ def backproject(depth, cam, z_max=0.0):
     k = lib().oracle_backproject(depth.ctypes.data_as(C.POINTER(C.c_uint16)), depth.shape[1], depth.shape[0],
                                  C.byref(camc), C.c_float(z_max), _fp(out))
     return out[:k].copy()
+
+
+def passthrough_z(pts, z_min, z_max):
+    """pcl::PassThrough on z (reference src/GraphicEnd.cpp:283-285)."""
+    pts = _f4(pts)
+    out = np.empty((max(len(pts), 1), 4), np.float32)
+    k = lib().oracle_passthrough_z(_fp(pts), len(pts), C.c_float(z_min), C.c_float(z_max), _fp(out))
+    return out[:k].copy()
+
+
+def voxel_grid(pts, leaf):
+    """pcl::VoxelGrid with a cubic leaf (reference src/GraphicEnd.cpp:287-295); None when PCL would refuse (index overflow)."""
+    pts = _f4(pts)
+    out = np.empty((max(len(pts), 1), 4), np.float32)
+    k = lib().oracle_voxel_grid(_fp(pts), len(pts), C.c_float(leaf), _fp(out))
+    return None if k < 0 else out[:k].copy()
+
+
+def transform(pts, T):
+    """pcl::transformPointCloud with the float32 cast of T (reference src/saveOutput.cpp:87)."""
+    pts = _f4(pts)
+    T = np.ascontiguousarray(T, dtype=np.float64).reshape(16)
+    out = np.empty((max(len(pts), 1), 4), np.float32)
+    lib().oracle_transform(_fp(pts), len(pts), T.ctypes.data_as(C.POINTER(C.c_double)), _fp(out))
+    return out[:len(pts)].copy()
+
+
+def map_fuse(clouds, poses, leaf, z_max):
+    """The key-frame fusion loop of saveOutput (reference src/saveOutput.cpp:47-95)."""
+    parts = [transform(passthrough_z(voxel_grid(c, leaf), 0.0, z_max), T) for c, T in zip(clouds, poses)]
+    return voxel_grid(np.concatenate(parts, axis=0), leaf)
 
 
 def pose_norm(T):

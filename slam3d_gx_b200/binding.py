@@ -32,7 +32,8 @@ EXPORTS = [
     "s3d_cloud_set_normals_device", "s3d_cloud_size", "s3d_cloud_has_normals", "s3d_cloud_download",
     "s3d_cloud_drop_index", "s3d_cloud_free", "s3d_segment_planes", "s3d_register_batch", "s3d_register_pair",
     "s3d_last_correspondences", "s3d_last_timing", "s3d_icp_params_default", "s3d_plane_params_default",
-    "s3d_planar_keypoints", "s3d_gather_results",
+    "s3d_planar_keypoints", "s3d_gather_results", "s3d_cloud_passthrough_z", "s3d_cloud_voxel_grid", "s3d_cloud_transform",
+    "s3d_cloud_concat", "s3d_map_fuse",
 ]
 
 
@@ -80,6 +81,11 @@ def load_library():
     lib.s3d_plane_params_default.restype = None
     lib.s3d_planar_keypoints.argtypes = [vp, vp, ci, ci, C.POINTER(_abi.CameraC), vp, ci, C.c_float, ci, C.c_uint64, vp]
     lib.s3d_gather_results.argtypes = [vp, vp, C.POINTER(_abi.Result), ci, ci, C.POINTER(_abi.Result)]
+    lib.s3d_cloud_passthrough_z.argtypes = [vp, vp, C.c_float, C.c_float, C.POINTER(vp)]
+    lib.s3d_cloud_voxel_grid.argtypes = [vp, vp, C.c_float, C.POINTER(vp)]
+    lib.s3d_cloud_transform.argtypes = [vp, vp, vp, C.POINTER(vp)]
+    lib.s3d_cloud_concat.argtypes = [vp, C.POINTER(vp), ci, C.POINTER(vp)]
+    lib.s3d_map_fuse.argtypes = [vp, C.POINTER(vp), vp, ci, C.c_float, C.c_float, C.POINTER(vp)]
     _LIB = lib
     return lib
 
@@ -133,6 +139,25 @@ class Cloud:
 
     def drop_index(self):
         self.ctx.lib.s3d_cloud_drop_index(self.ctx.h, self.handle)
+
+    def passthrough_z(self, z_min: float, z_max: float) -> "Cloud":
+        """pcl::PassThrough on z (reference src/GraphicEnd.cpp:283-285)."""
+        h = C.c_void_p()
+        self.ctx._check(self.ctx.lib.s3d_cloud_passthrough_z(self.ctx.h, self.handle, z_min, z_max, C.byref(h)))
+        return Cloud(self.ctx, h)
+
+    def voxel_grid(self, leaf: float) -> "Cloud":
+        """pcl::VoxelGrid with a cubic leaf (reference src/GraphicEnd.cpp:287-295, parameter grid_leaf)."""
+        h = C.c_void_p()
+        self.ctx._check(self.ctx.lib.s3d_cloud_voxel_grid(self.ctx.h, self.handle, leaf, C.byref(h)))
+        return Cloud(self.ctx, h)
+
+    def transform(self, T) -> "Cloud":
+        """pcl::transformPointCloud (reference src/saveOutput.cpp:87)."""
+        T = np.ascontiguousarray(T, dtype=np.float64).reshape(16)
+        h = C.c_void_p()
+        self.ctx._check(self.ctx.lib.s3d_cloud_transform(self.ctx.h, self.handle, T.ctypes.data, C.byref(h)))
+        return Cloud(self.ctx, h)
 
     def free(self):
         if self.handle is not None:
@@ -192,6 +217,22 @@ class Context:
         h = C.c_void_p()
         self._check(self.lib.s3d_cloud_from_depth(self.h, d.ctypes.data, d.shape[1], d.shape[0], C.byref(camc),
                                                   C.c_float(z_max), C.byref(h)))
+        return Cloud(self, h)
+
+    def concat(self, clouds) -> Cloud:
+        n = len(clouds)
+        arr = (C.c_void_p * max(n, 1))(*[c.handle for c in clouds])
+        h = C.c_void_p()
+        self._check(self.lib.s3d_cloud_concat(self.h, arr, n, C.byref(h)))
+        return Cloud(self, h)
+
+    def map_fuse(self, clouds, poses, leaf: float, z_max: float) -> Cloud:
+        """The key-frame fusion loop of saveOutput (reference src/saveOutput.cpp:47-95)."""
+        n = len(clouds)
+        arr = (C.c_void_p * n)(*[c.handle for c in clouds])
+        P = np.ascontiguousarray(poses, dtype=np.float64).reshape(n, 16)
+        h = C.c_void_p()
+        self._check(self.lib.s3d_map_fuse(self.h, arr, P.ctypes.data, n, leaf, z_max, C.byref(h)))
         return Cloud(self, h)
 
     def register_batch(self, srcs, tgts, guess=None, params: _abi.IcpParams | None = None, raw: bool = False):

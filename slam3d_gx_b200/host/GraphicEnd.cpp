@@ -156,16 +156,20 @@ int GraphicEnd::readimage()
     vector<float> pts;
     int n = 0;
     if (!loadPCDFile(ss.str(), pts, n)) { cerr << "cannot read " << ss.str() << endl; exit(1); }
-    // PassThrough z in [0, z_filter] (:283-285), order preserved
-    int w = 0;
-    for (int i = 0; i < n; ++i) {
-        float z = pts[4 * i + 2];
-        if (z >= 0.f && z <= (float)_z_filter) { if (w != i) for (int k = 0; k < 4; ++k) pts[4 * w + k] = pts[4 * i + k]; ++w; }
+    // PassThrough z in [0, z_filter] (:283-285) and, on request, VoxelGrid(grid_leaf) (:287-295), both on the device.
+    // The reference always voxel-filters (its features do not need density); the ICP backend registers at full
+    // density unless parameters.yaml says `use_voxel_grid: yes`.
+    s3d_cloud *raw = 0, *c = 0;
+    S3D_CHECK(s3d_cloud_upload(_ctx, pts.data(), 4, n, &raw));
+    S3D_CHECK(s3d_cloud_passthrough_z(_ctx, raw, 0.0f, (float)_z_filter, &c));
+    s3d_cloud_free(_ctx, raw);
+    if (g_pParaReader->GetPara("use_voxel_grid") == string("yes")) {
+        double grid = atof(g_pParaReader->GetPara("grid_leaf").c_str());
+        s3d_cloud *v = 0;
+        S3D_CHECK(s3d_cloud_voxel_grid(_ctx, c, (float)grid, &v));
+        s3d_cloud_free(_ctx, c);
+        c = v;
     }
-    if (g_pParaReader->GetPara("use_voxel_grid") == string("yes"))
-        cerr << "use_voxel_grid: the VoxelGrid down-sampling (reference :287-295) is a later row of the scope table; clouds are registered at full density" << endl;
-    s3d_cloud *c = 0;
-    S3D_CHECK(s3d_cloud_upload(_ctx, pts.data(), 4, w, &c));
     _clouds.push_back(c);
     _currCloud = c;
     cout << "load ok." << endl;
