@@ -85,6 +85,21 @@ def test_grid_and_brute_agree_bitwise(ctx, small_pair):
     assert ok, err
 
 
+@pytest.mark.parametrize("k", [2, 3, 5, 9, 16])
+def test_skip_logic_is_exact(ctx, small_pair, k):
+    """Iteration k of a long run (correspondences kept by the triangle-inequality test, searches started from hints)
+    must equal a fresh first iteration started from the pose after k-1 iterations (every query searched from scratch):
+    same correspondences, same pose bits."""
+    p = small_pair
+    a, nna = _gpu_icp(ctx, p, _abi.icp_params(k))
+    b, _ = _gpu_icp(ctx, p, _abi.icp_params(k - 1))
+    c, nnc = _gpu_icp(ctx, p, _abi.icp_params(1), guess=b["T"])
+    assert np.array_equal(nna, nnc)
+    assert np.array_equal(a["T"], c["T"])
+    idx, _ = oracle.nn(p["src"], p["tgt"], b["T"])
+    assert np.array_equal(nna, idx)
+
+
 def test_icp_is_deterministic(ctx, small_pair):
     p = small_pair
     a, _ = _gpu_icp(ctx, p, _abi.icp_params(8))
@@ -207,6 +222,18 @@ def test_full_size_config1_gate(ctx, full_pair):
     r1, nn1 = _gpu_icp(ctx, p, _abi.icp_params(1))
     idx, _ = oracle.nn(p["src"], p["tgt"], None, nthreads=0)
     assert np.array_equal(nn1, idx)
+
+
+def test_full_size_skip_logic_is_exact(ctx, full_pair):
+    """Same check at 640x480 for a late iteration: the 12th iteration of a run equals a from-scratch iteration at that pose,
+    and its correspondences are the oracle's exact nearest neighbours."""
+    p = full_pair
+    a, nna = _gpu_icp(ctx, p, _abi.icp_params(12))
+    b, _ = _gpu_icp(ctx, p, _abi.icp_params(11))
+    c, nnc = _gpu_icp(ctx, p, _abi.icp_params(1), guess=b["T"])
+    assert np.array_equal(nna, nnc) and np.array_equal(a["T"], c["T"])
+    idx, _ = oracle.nn(p["src"], p["tgt"], b["T"], nthreads=0)
+    assert np.array_equal(nna, idx)
 
 
 def test_full_size_config2_30_iterations(ctx, full_pair):
