@@ -141,6 +141,13 @@ int  s3d_cloud_from_device(s3d_ctx *ctx, const void *d_xyzw, int n, s3d_cloud **
  * of src/GraphicEnd.cpp:283-285. depth is a HOST pointer. */
 int  s3d_cloud_from_depth(s3d_ctx *ctx, const uint16_t *depth, int width, int height,
                           const s3d_camera *cam, float z_max, s3d_cloud **out);
+/* depth image -> cloud WITH per-point normals from the organised image (scenes that are not a few big planes): the
+ * normal of a pixel is the normalised cross product of the central differences of the back-projected neighbours
+ * `step` pixels away, turned towards the camera; no normal (valid = 0) at borders, holes and where a neighbour is
+ * more than max_jump metres away in depth.  Same point set and order as s3d_cloud_from_depth
+ * (src/convert2PCD.cpp:54-80); the normals play the role of PLANE::coff (src/GraphicEnd.h:41-49) for the ICP. */
+int  s3d_cloud_from_depth_normals(s3d_ctx *ctx, const uint16_t *depth, int width, int height, const s3d_camera *cam,
+                                  float z_max, int step, float max_jump, s3d_cloud **out);
 /* per-point normals from the caller (host, stride>=3); valid flag set for finite non-zero normals */
 int  s3d_cloud_set_normals(s3d_ctx *ctx, s3d_cloud *cloud, const float *nrm, int stride_floats, int n);
 /* same with a device float4 array (nx,ny,nz,valid!=0) */

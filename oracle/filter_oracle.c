@@ -104,3 +104,55 @@ void oracle_transform(const float *xyzw, int n, const double *T16, float *out)
         out[4 * (size_t)i] = o[0]; out[4 * (size_t)i + 1] = o[1]; out[4 * (size_t)i + 2] = o[2]; out[4 * (size_t)i + 3] = 1.0f;
     }
 }
+
+/* ---- per-point normals from the organised depth image (same definition as csrc/filters.cu) -------------- */
+#include "../include/slam3d_b200.h"
+
+static int dn_valid(const uint16_t *depth, int w, int h, const s3d_camera *cam, float z_max, int u, int v)
+{
+    if (u < 0 || v < 0 || u >= w || v >= h) return 0;
+    uint16_t d = depth[(size_t)v * w + u];
+    if (d == 0) return 0;
+    if (z_max > 0.f) { float fz = (float)((double)d / cam->factor); return fz >= 0.f && fz <= z_max; }
+    return 1;
+}
+static void dn_point(const uint16_t *depth, int w, const s3d_camera *cam, int u, int v, float *o)
+{
+    double z = (double)depth[(size_t)v * w + u] / cam->factor;
+    double x = ((double)u - cam->cx) * z / cam->fx;
+    double y = ((double)v - cam->cy) * z / cam->fy;
+    o[0] = (float)x; o[1] = (float)y; o[2] = (float)z;
+}
+
+/* xyzw_out, nrm_out: capacity width*height*4 floats each; returns the number of points */
+int oracle_backproject_normals(const uint16_t *depth, int width, int height, const s3d_camera *cam, float z_max,
+                               int step, float max_jump, float *xyzw_out, float *nrm_out)
+{
+    int k = 0;
+    for (int v = 0; v < height; ++v) for (int u = 0; u < width; ++u) {
+        if (!dn_valid(depth, width, height, cam, z_max, u, v)) continue;
+        float p[3]; dn_point(depth, width, cam, u, v, p);
+        float *po = xyzw_out + 4 * (size_t)k, *no = nrm_out + 4 * (size_t)k;
+        po[0] = p[0]; po[1] = p[1]; po[2] = p[2]; po[3] = 1.0f;
+        no[0] = no[1] = no[2] = no[3] = 0.0f;
+        ++k;
+        const int s = step;
+        if (!(dn_valid(depth, width, height, cam, z_max, u - s, v) && dn_valid(depth, width, height, cam, z_max, u + s, v) &&
+              dn_valid(depth, width, height, cam, z_max, u, v - s) && dn_valid(depth, width, height, cam, z_max, u, v + s))) continue;
+        float l[3], r[3], t[3], b[3];
+        dn_point(depth, width, cam, u - s, v, l); dn_point(depth, width, cam, u + s, v, r);
+        dn_point(depth, width, cam, u, v - s, t); dn_point(depth, width, cam, u, v + s, b);
+        if (fabsf(l[2] - p[2]) > max_jump || fabsf(r[2] - p[2]) > max_jump || fabsf(t[2] - p[2]) > max_jump || fabsf(b[2] - p[2]) > max_jump) continue;
+        const float ax = r[0] - l[0], ay = r[1] - l[1], az = r[2] - l[2];
+        const float bx = b[0] - t[0], by = b[1] - t[1], bz = b[2] - t[2];
+        float nx = fmaf(ay, bz, -(az * by)), ny = fmaf(az, bx, -(ax * bz)), nz = fmaf(ax, by, -(ay * bx));
+        const float l2 = fmaf(nz, nz, fmaf(ny, ny, nx * nx));
+        if (!(l2 > 1e-24f)) continue;
+        const float inv = 1.0f / sqrtf(l2);
+        nx *= inv; ny *= inv; nz *= inv;
+        const float dp = fmaf(nz, p[2], fmaf(ny, p[1], nx * p[0]));
+        if (dp > 0.f) { nx = -nx; ny = -ny; nz = -nz; }
+        no[0] = nx; no[1] = ny; no[2] = nz; no[3] = 1.0f;
+    }
+    return k;
+}

@@ -150,6 +150,17 @@ def map_fuse(clouds, poses, leaf, z_max):
     return voxel_grid(np.concatenate(parts, axis=0), leaf)
 
 
+def backproject_normals(depth, cam, z_max=0.0, step=1, max_jump=0.05):
+    """Depth -> (cloud (n,4), normals (n,4) with w = valid) like s3d_cloud_from_depth_normals."""
+    depth = np.ascontiguousarray(depth, dtype=np.uint16)
+    pts = np.empty((depth.size, 4), np.float32)
+    nrm = np.empty((depth.size, 4), np.float32)
+    camc = _abi.camera_c(cam)
+    k = lib().oracle_backproject_normals(depth.ctypes.data_as(C.POINTER(C.c_uint16)), depth.shape[1], depth.shape[0], C.byref(camc),
+                                         C.c_float(z_max), int(step), C.c_float(max_jump), _fp(pts), _fp(nrm))
+    return pts[:k].copy(), nrm[:k].copy()
+
+
 def pose_norm(T):
     T = np.ascontiguousarray(T, dtype=np.float64)
     return lib().oracle_pose_norm(T.ctypes.data_as(C.POINTER(C.c_double)))

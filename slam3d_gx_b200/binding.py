@@ -33,7 +33,7 @@ EXPORTS = [
     "s3d_cloud_drop_index", "s3d_cloud_free", "s3d_segment_planes", "s3d_register_batch", "s3d_register_pair",
     "s3d_last_correspondences", "s3d_last_timing", "s3d_icp_params_default", "s3d_plane_params_default",
     "s3d_planar_keypoints", "s3d_gather_results", "s3d_cloud_passthrough_z", "s3d_cloud_voxel_grid", "s3d_cloud_transform",
-    "s3d_cloud_concat", "s3d_map_fuse",
+    "s3d_cloud_concat", "s3d_map_fuse", "s3d_cloud_from_depth_normals",
 ]
 
 
@@ -81,6 +81,7 @@ def load_library():
     lib.s3d_plane_params_default.restype = None
     lib.s3d_planar_keypoints.argtypes = [vp, vp, ci, ci, C.POINTER(_abi.CameraC), vp, ci, C.c_float, ci, C.c_uint64, vp]
     lib.s3d_gather_results.argtypes = [vp, vp, C.POINTER(_abi.Result), ci, ci, C.POINTER(_abi.Result)]
+    lib.s3d_cloud_from_depth_normals.argtypes = [vp, vp, ci, ci, C.POINTER(_abi.CameraC), C.c_float, ci, C.c_float, C.POINTER(vp)]
     lib.s3d_cloud_passthrough_z.argtypes = [vp, vp, C.c_float, C.c_float, C.POINTER(vp)]
     lib.s3d_cloud_voxel_grid.argtypes = [vp, vp, C.c_float, C.POINTER(vp)]
     lib.s3d_cloud_transform.argtypes = [vp, vp, vp, C.POINTER(vp)]
@@ -233,6 +234,15 @@ class Context:
         P = np.ascontiguousarray(poses, dtype=np.float64).reshape(n, 16)
         h = C.c_void_p()
         self._check(self.lib.s3d_map_fuse(self.h, arr, P.ctypes.data, n, leaf, z_max, C.byref(h)))
+        return Cloud(self, h)
+
+    def from_depth_normals(self, depth: np.ndarray, cam, z_max: float = 0.0, step: int = 1, max_jump: float = 0.05) -> Cloud:
+        """Depth image -> cloud with per-point normals from the organised image."""
+        d = np.ascontiguousarray(depth, dtype=np.uint16)
+        camc = _abi.camera_c(cam)
+        h = C.c_void_p()
+        self._check(self.lib.s3d_cloud_from_depth_normals(self.h, d.ctypes.data, d.shape[1], d.shape[0], C.byref(camc),
+                                                          C.c_float(z_max), step, C.c_float(max_jump), C.byref(h)))
         return Cloud(self, h)
 
     def register_batch(self, srcs, tgts, guess=None, params: _abi.IcpParams | None = None, raw: bool = False):

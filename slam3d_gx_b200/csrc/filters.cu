@@ -307,3 +307,107 @@ extern "C" int s3d_map_fuse(s3d_ctx *ctx, const s3d_cloud *const *clouds, const 
     if (sum) s3d_cloud_free(ctx, sum);
     return rc;
 }
+
+// ---- per-point normals from the organised depth image --------------------------
+// Companion of s3d_cloud_from_depth for scenes that are not made of a few big planes: the normal of pixel (u,v) is
+// the normalised cross product of the central differences of the back-projected neighbours `step` pixels away,
+// turned towards the camera.  A pixel gets no normal (w = 0) when a neighbour is missing (border, hole, outside
+// the z filter) or lies more than `max_jump` metres away in depth (an occlusion edge).  Back-projection in double
+// like reference src/convert2PCD.cpp:64-68, differences and cross product in float32 with the explicit
+// round-to-nearest intrinsics so that oracle/filter_oracle.c reproduces every bit.
+struct DepthNormalCtx {
+    const uint16_t *depth; int width, height; double fx, fy, cx, cy, factor; float z_max; int step; float max_jump;
+    __device__ bool valid(int u, int v) const
+    {
+        if (u < 0 || v < 0 || u >= width || v >= height) return false;
+        const uint16_t d = depth[v * width + u];
+        if (d == 0) return false;
+        if (z_max > 0.f) { const float fz = (float)__ddiv_rn((double)d, factor); return fz >= 0.f && fz <= z_max; }
+        return true;
+    }
+    __device__ float3 point(int u, int v) const
+    {
+        const double z = __ddiv_rn((double)depth[v * width + u], factor);
+        const double x = __ddiv_rn(__dmul_rn(__dsub_rn((double)u, cx), z), fx);
+        const double y = __ddiv_rn(__dmul_rn(__dsub_rn((double)v, cy), z), fy);
+        return make_float3((float)x, (float)y, (float)z);
+    }
+};
+struct DepthNormalPred {
+    DepthNormalCtx c;
+    __device__ bool operator()(int i) const { const int v = i / c.width; return c.valid(i - v * c.width, v); }
+};
+struct DepthNormalEmit {
+    DepthNormalCtx c; float4 *pts; float4 *nrm;
+    __device__ void operator()(int i, uint32_t pos) const
+    {
+        const int v = i / c.width, u = i - v * c.width;
+        const float3 p = c.point(u, v);
+        pts[pos] = make_float4(p.x, p.y, p.z, 1.0f);
+        float4 n = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int s = c.step;
+        if (c.valid(u - s, v) && c.valid(u + s, v) && c.valid(u, v - s) && c.valid(u, v + s)) {
+            const float3 l = c.point(u - s, v), r = c.point(u + s, v), t = c.point(u, v - s), b = c.point(u, v + s);
+            const bool jump = fabsf(__fsub_rn(l.z, p.z)) > c.max_jump || fabsf(__fsub_rn(r.z, p.z)) > c.max_jump ||
+                              fabsf(__fsub_rn(t.z, p.z)) > c.max_jump || fabsf(__fsub_rn(b.z, p.z)) > c.max_jump;
+            if (!jump) {
+                const float ax = __fsub_rn(r.x, l.x), ay = __fsub_rn(r.y, l.y), az = __fsub_rn(r.z, l.z);
+                const float bx = __fsub_rn(b.x, t.x), by = __fsub_rn(b.y, t.y), bz = __fsub_rn(b.z, t.z);
+                float nx = __fmaf_rn(ay, bz, -__fmul_rn(az, by));
+                float ny = __fmaf_rn(az, bx, -__fmul_rn(ax, bz));
+                float nz = __fmaf_rn(ax, by, -__fmul_rn(ay, bx));
+                const float l2 = __fmaf_rn(nz, nz, __fmaf_rn(ny, ny, __fmul_rn(nx, nx)));
+                if (l2 > 1e-24f) {
+                    const float inv = __fdiv_rn(1.0f, __fsqrt_rn(l2));
+                    nx = __fmul_rn(nx, inv); ny = __fmul_rn(ny, inv); nz = __fmul_rn(nz, inv);
+                    // towards the camera (the origin): n . p < 0
+                    const float dp = __fmaf_rn(nz, p.z, __fmaf_rn(ny, p.y, __fmul_rn(nx, p.x)));
+                    if (dp > 0.f) { nx = -nx; ny = -ny; nz = -nz; }
+                    n = make_float4(nx, ny, nz, 1.0f);
+                }
+            }
+        }
+        nrm[pos] = n;
+    }
+};
+
+extern "C" int s3d_cloud_from_depth_normals(s3d_ctx *ctx, const uint16_t *depth, int width, int height, const s3d_camera *cam,
+                                            float z_max, int step, float max_jump, s3d_cloud **out)
+{
+    if (!ctx || !out || !depth || !cam || width <= 0 || height <= 0 || step < 1 || !(max_jump > 0.f))
+        return s3d_fail(ctx, S3D_E_ARG, "s3d_cloud_from_depth_normals: bad argument");
+    cudaSetDevice(ctx->device);
+    const int npx = width * height;
+    const int nblocks = (npx + S3D_COMPACT_BLOCK - 1) / S3D_COMPACT_BLOCK;
+    uint16_t *d_depth = nullptr; uint32_t *d_counts = nullptr; float4 *d_tmp = nullptr, *d_tmpn = nullptr;
+    S3D_CUDA(ctx, s3d_dev_alloc_t(ctx, &d_depth, sizeof(uint16_t) * (size_t)npx));
+    S3D_CUDA(ctx, s3d_dev_alloc_t(ctx, &d_counts, sizeof(uint32_t) * (size_t)(nblocks + 1)));
+    S3D_CUDA(ctx, s3d_dev_alloc_t(ctx, &d_tmp, sizeof(float4) * (size_t)npx));
+    S3D_CUDA(ctx, s3d_dev_alloc_t(ctx, &d_tmpn, sizeof(float4) * (size_t)npx));
+    S3D_CUDA(ctx, cudaMemcpyAsync(d_depth, depth, sizeof(uint16_t) * (size_t)npx, cudaMemcpyHostToDevice, ctx->stream));
+    DepthNormalCtx c{d_depth, width, height, cam->fx, cam->fy, cam->cx, cam->cy, cam->factor, z_max, step, max_jump};
+    DepthNormalPred pred{c};
+    DepthNormalEmit emit{c, d_tmp, d_tmpn};
+    compact_count_kernel<<<nblocks, S3D_COMPACT_BLOCK, 0, ctx->stream>>>(npx, pred, d_counts); S3D_LAUNCHED(ctx);
+    compact_scan_kernel<<<1, 1024, 0, ctx->stream>>>(d_counts, nblocks, d_counts + nblocks); S3D_LAUNCHED(ctx);
+    compact_write_kernel<<<nblocks, S3D_COMPACT_BLOCK, 0, ctx->stream>>>(npx, pred, emit, NoDropF(), d_counts); S3D_LAUNCHED(ctx);
+    uint32_t total = 0;
+    S3D_CUDA(ctx, cudaMemcpyAsync(&total, d_counts + nblocks, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    S3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    s3d_cloud *cl = nullptr;
+    int rc = cloud_new(ctx, (int)total, &cl);
+    if (rc == S3D_OK) {
+        if (s3d_dev_alloc_t(ctx, &cl->d_nrm, sizeof(float4) * (size_t)std::max<uint32_t>(total, 1)) != cudaSuccess)
+            rc = s3d_fail(ctx, S3D_E_CUDA, "device allocation for normals");
+    }
+    if (rc == S3D_OK && total > 0) {
+        if (cudaMemcpyAsync(cl->d_pts, d_tmp, sizeof(float4) * (size_t)total, cudaMemcpyDeviceToDevice, ctx->stream) != cudaSuccess ||
+            cudaMemcpyAsync(cl->d_nrm, d_tmpn, sizeof(float4) * (size_t)total, cudaMemcpyDeviceToDevice, ctx->stream) != cudaSuccess)
+            rc = s3d_fail(ctx, S3D_E_CUDA, "copy compacted cloud");
+    }
+    cudaStreamSynchronize(ctx->stream);
+    s3d_dev_free(ctx, d_depth); s3d_dev_free(ctx, d_counts); s3d_dev_free(ctx, d_tmp); s3d_dev_free(ctx, d_tmpn);
+    if (rc) { if (cl) { s3d_dev_free(ctx, cl->d_pts); s3d_dev_free(ctx, cl->d_nrm); delete cl; } return rc; }
+    *out = cl;
+    return S3D_OK;
+}

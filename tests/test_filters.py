@@ -109,3 +109,40 @@ def test_map_fusion_full_size_matches_oracle(ctx):
     assert 0.02 * len(frames[0]) < len(fused) < len(frames[0])
     for h in clouds + [fused, again]:
         h.free()
+
+
+# ---- per-point normals from the organised depth image -----------------------------------------
+
+def test_oracle_depth_normals_recover_the_planes(small_cam):
+    p = synth.make_pair(5, cam=small_cam, quantize=True)
+    pts, nrm = oracle.backproject_normals(p["tgt_depth"], small_cam, 0.0, 1, 0.08)
+    assert np.array_equal(pts, p["tgt"])
+    ok = nrm[:, 3] > 0
+    assert ok.mean() > 0.8
+    cosang = np.abs((nrm[ok, :3] * p["tgt_normals"][ok, :3]).sum(1))
+    assert np.median(cosang) > 0.99                       # 2 mm noise + 1 mm quantisation over a 2-pixel baseline (~5 cm at this resolution)
+    assert np.all((nrm[ok, :3] * pts[ok, :3]).sum(1) <= 0)     # turned towards the camera
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("step,z_max", [(1, 3.5), (3, 0.0)])
+def test_depth_normals_bit_exact_and_usable_for_icp(ctx, small_cam, step, z_max):
+    from slam3d_gx_b200 import _abi
+    p = synth.make_pair(6, cam=small_cam, quantize=True, holes=0.1)
+    ct = ctx.from_depth_normals(p["tgt_depth"], small_cam, z_max, step, 0.08)
+    got = ct.download(xyz=True, normals=True)
+    pts, nrm = oracle.backproject_normals(p["tgt_depth"], small_cam, z_max, step, 0.08)
+    assert np.array_equal(got["xyz"], pts[:, :3]) and np.array_equal(got["normals"], nrm[:, :3])
+    if step == 1:
+        cs = ctx.from_depth(p["src_depth"], small_cam, z_max)
+        src = oracle.backproject(p["src_depth"], small_cam, z_max)
+        prm = _abi.icp_params(15, max_corr_dist=0.2)
+        r = ctx.register(cs, ct, None, prm)
+        o = oracle.icp(src, pts, nrm, params=prm)
+        assert r["status"] == o["status"] == 0 and r["inliers"] == o["inliers"]
+        rot, trans = synth.pose_error(r["T"], o["T"])
+        assert rot <= 1e-4 and trans <= 1e-4
+        rot, trans = synth.pose_error(r["T"], p["T_gt"])
+        assert rot <= 2e-2 and trans <= 3e-2
+        cs.free()
+    ct.free()
