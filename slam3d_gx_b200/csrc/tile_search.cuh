@@ -130,6 +130,20 @@ __device__ __forceinline__ void tile_compare_pass(uint32_t sbuf, int m, int sub,
     float pd0 = INFINITY, ps0 = INFINITY, pd1 = INFINITY, ps1 = INFINITY;
     int pk0 = -1, pk1 = -1;
     int k = sub;
+    for (; k + 3 * step < m; k += 4 * step) {          // four candidates per turn, two per chain
+        const float4 a = ts_lds128(sbuf + 16u * (uint32_t)k), b = ts_lds128(sbuf + 16u * (uint32_t)(k + step));
+        const float4 c = ts_lds128(sbuf + 16u * (uint32_t)(k + 2 * step)), e = ts_lds128(sbuf + 16u * (uint32_t)(k + 3 * step));
+        const float da = s3d_dist2(qx, qy, qz, a.x, a.y, a.z), db = s3d_dist2(qx, qy, qz, b.x, b.y, b.z);
+        const float dc = s3d_dist2(qx, qy, qz, c.x, c.y, c.z), de = s3d_dist2(qx, qy, qz, e.x, e.y, e.z);
+        bool la = da < pd0, lbb = db < pd1;
+        ps0 = fminf(ps0, fmaxf(pd0, da)); ps1 = fminf(ps1, fmaxf(pd1, db));
+        pd0 = fminf(pd0, da); pd1 = fminf(pd1, db);
+        pk0 = la ? k : pk0; pk1 = lbb ? k + step : pk1;
+        la = dc < pd0; lbb = de < pd1;
+        ps0 = fminf(ps0, fmaxf(pd0, dc)); ps1 = fminf(ps1, fmaxf(pd1, de));
+        pd0 = fminf(pd0, dc); pd1 = fminf(pd1, de);
+        pk0 = la ? k + 2 * step : pk0; pk1 = lbb ? k + 3 * step : pk1;
+    }
     for (; k + step < m; k += 2 * step) {
         const float4 a = ts_lds128(sbuf + 16u * (uint32_t)k), b = ts_lds128(sbuf + 16u * (uint32_t)(k + step));
         const float da = s3d_dist2(qx, qy, qz, a.x, a.y, a.z), db = s3d_dist2(qx, qy, qz, b.x, b.y, b.z);
@@ -233,9 +247,8 @@ __device__ __noinline__ TileOut tile_search(const TileCfg *cfg, float px, float 
         const int ny_s = hiy - loy + 1, nz_s = hiz - loz + 1;
         const int rows = gp.n_points > 0 ? ny_s * nz_s : 0;
         // ---- work split: NS query slots (power of two >= nin), 32/NS lanes per slot ----
-        int NS = 1;
-        while (NS < nin) NS <<= 1;
-        const int step = 32 / NS, slot = lane & (NS - 1), sub = lane / NS;
+        const int lgNS = nin > 1 ? 32 - __clz(nin - 1) : 0;             // NS = 1 << lgNS
+        const int NS = 1 << lgNS, step = 32 >> lgNS, slot = lane & (NS - 1), sub = lane >> lgNS;
         const int src = (slot < nin) ? (int)__fns(inmask, 0, slot + 1) : 0;
         const float qx = __shfl_sync(full, px, src), qy = __shfl_sync(full, py, src), qz = __shfl_sync(full, pz, src);
         const bool work = slot < nin;
@@ -254,7 +267,8 @@ __device__ __noinline__ TileOut tile_search(const TileCfg *cfg, float px, float 
                 const int t = t0 + lane;
                 rs = 0u; cnt = 0u;
                 if (t < rows) {
-                    const int zi = t / ny_s;
+                    // t / ny_s without an integer division (t < 2^22, exact in float with the half-step offset)
+                    const int zi = __float2int_rz(__fdividef((float)t + 0.5f, (float)ny_s));
                     const size_t base = ((size_t)(loz + zi) * gp.ny + (loy + (t - zi * ny_s))) * gp.nx;
                     rs = __ldg(&cell_start[base + lox]);
                     cnt = __ldg(&cell_start[base + hix + 1]) - rs;
@@ -284,8 +298,14 @@ __device__ __noinline__ TileOut tile_search(const TileCfg *cfg, float px, float 
             {
                 const uint32_t dst = sbuf + 16u * ((uint32_t)fill + excl);
                 const float4 *srcp = sp + rs;
-                for (uint32_t k = 0; k < take; ++k)
-                    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + 16u * k), "l"(srcp + k) : "memory");
+                for (uint32_t k = 0; k < take; k += 4) {          // four per turn: the loop overhead was 11 % of all instructions
+                    const uint32_t d0 = dst + 16u * k;
+                    const float4 *s0 = srcp + k;
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d0), "l"(s0) : "memory");
+                    if (k + 1 < take) asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d0 + 16u), "l"(s0 + 1) : "memory");
+                    if (k + 2 < take) asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d0 + 32u), "l"(s0 + 2) : "memory");
+                    if (k + 3 < take) asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d0 + 48u), "l"(s0 + 3) : "memory");
+                }
             }
 #endif
             rs += take; cnt -= take;
