@@ -834,9 +834,20 @@ __global__ void __launch_bounds__(TS_BLOCK, 1) icp_persist_kernel(const PersistA
             PHASE(10);
             // every CTA: the same fixed-order sum of the group's rows, then the same solve
             {
+                // (loads of up to 10 rows in flight per thread, added in row order)
                 double s = 0.0;
-                if (lane < 29)
-                    for (int c = warp; c < a.group_ctas; c += TS_WARPS) s += __ldcg(&rows[(size_t)c * S3D_NACC + lane]);
+                if (lane < 29) {
+                    for (int c0 = warp; c0 < a.group_ctas; c0 += 10 * TS_WARPS) {
+                        double v[10];
+                        #pragma unroll
+                        for (int j = 0; j < 10; ++j) {
+                            const int c = c0 + j * TS_WARPS;
+                            v[j] = c < a.group_ctas ? __ldcg(&rows[(size_t)c * S3D_NACC + lane]) : 0.0;
+                        }
+                        #pragma unroll
+                        for (int j = 0; j < 10; ++j) s += v[j];
+                    }
+                }
                 tail[warp][lane] = s;
             }
             __syncthreads();
