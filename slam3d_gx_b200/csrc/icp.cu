@@ -572,6 +572,7 @@ __global__ void __launch_bounds__(ICP_BLOCK, ICP_MIN_BLOCKS) icp_iter_kernel(con
 // ------------------------------------------------------------------------------------------------
 #define TS_BLOCK 512
 #define TS_WARPS (TS_BLOCK / 32)
+#define TS_STAGE (TS_CAP / 128)     // chunks of per-query state (32 lanes x 4 float4) a warp's tile holds
 
 #if defined(S3D_STATS) || defined(S3D_PHASES)
 #define PHASE_T0() long long ph_t = clock64()
@@ -687,29 +688,36 @@ __global__ void __launch_bounds__(TS_BLOCK, 1) icp_persist_kernel(const PersistA
 #endif
 
             // Streaming part: each warp walks its chunks of 32 consecutive queries (fixed assignment: the same thread
-            // sees the same query every iteration).  The four 16-byte loads of the NEXT chunk are issued before the
-            // current one is processed, so a late iteration (nearly every query keeps its correspondence) is one pass
-            // over 64 B/point with the latency of one chunk exposed, not of every chunk.
-            int kc = 0;
-            float4 n_p = make_float4(0.f, 0.f, 0.f, 0.f), n_q = n_p, n_xl = n_p, n_nv = n_p;
-            {
-                const int u0 = CHUNK_UNIT(0), i0 = (u0 << 3) + (lane & 7);
-                if (u0 < nunits && i0 < d.n_src) {
-                    n_p = d.src[i0];
-                    if (it > 0) { n_q = my_cq[i0]; n_xl = my_xl[i0]; if (EST == S3D_ESTIMATOR_POINT_TO_PLANE) n_nv = my_cn[i0]; }
+            // sees the same query every iteration).  The per-query state of up to TS_STAGE chunks (4 x 16 B per query:
+            // point, correspondence, search position + bound, normal) is brought into the warp's tile by cp.async up
+            // front, every load in flight at once and no registers spent on prefetching: a late iteration (nearly every
+            // query keeps its correspondence) is one pass over 64 B/point with one memory latency exposed.  A search
+            // uses the tile itself, so what was staged beyond the current chunk is staged again afterwards (then only
+            // one chunk ahead: in the first iterations every chunk searches).
+            const uint32_t sbuf = ts_smem_u32(buf);
+            int staged_hi = 0, stage_lo = 0, stage_depth = TS_STAGE;
+            for (int kc = 0; wslot + W * 4 * kc < nunits; ++kc) {          // warp-uniform: the chunk's first octet exists
+                if (kc >= staged_hi) {
+                    stage_lo = kc;
+                    staged_hi = kc + stage_depth;
+                    for (int c = 0; c < stage_depth; ++c) {
+                        const int us = CHUNK_UNIT(kc + c), is = (us << 3) + (lane & 7);
+                        if (us < nunits && is < d.n_src) {
+                            const uint32_t dst = sbuf + 16u * (uint32_t)(c * 128 + lane);
+                            ts_cp_async16_s(dst, &d.src[is]);
+                            if (it > 0) {
+                                ts_cp_async16_s(dst + 512u, &my_cq[is]);
+                                ts_cp_async16_s(dst + 1024u, &my_xl[is]);
+                                if (EST == S3D_ESTIMATOR_POINT_TO_PLANE) ts_cp_async16_s(dst + 1536u, &my_cn[is]);
+                            }
+                        }
+                    }
+                    ts_cp_async_wait_all();
                 }
-            }
-            for (; wslot + W * 4 * kc < nunits; ++kc) {          // warp-uniform: the chunk's first octet exists
                 const int u = CHUNK_UNIT(kc), i = (u << 3) + (lane & 7);
                 const bool in = u < nunits && i < d.n_src;
-                const float4 p = n_p, q_old = n_q, xl = n_xl, nv_old = n_nv;
-                {
-                    const int u1 = CHUNK_UNIT(kc + 1), i1 = (u1 << 3) + (lane & 7);
-                    if (u1 < nunits && i1 < d.n_src) {
-                        n_p = d.src[i1];
-                        if (it > 0) { n_q = my_cq[i1]; n_xl = my_xl[i1]; if (EST == S3D_ESTIMATOR_POINT_TO_PLANE) n_nv = my_cn[i1]; }
-                    }
-                }
+                const uint32_t sl = sbuf + 16u * (uint32_t)((kc - stage_lo) * 128 + lane);
+                const float4 p = ts_lds128(sl), q_old = ts_lds128(sl + 512u), xl = ts_lds128(sl + 1024u), nv_old = ts_lds128(sl + 1536u);
                 float3 x = make_float3(0.f, 0.f, 0.f);
                 float4 q = make_float4(0.f, 0.f, 0.f, __int_as_float(-1)), nv = make_float4(0.f, 0.f, 0.f, 1.f);
                 float d2q = INFINITY, r = 1.5f * cell;
@@ -746,6 +754,7 @@ __global__ void __launch_bounds__(TS_BLOCK, 1) icp_persist_kernel(const PersistA
                     }
                 }
                 if (__any_sync(full, pending)) {
+                    staged_hi = kc + 1; stage_depth = 1;        // the search uses the tile: stage the next chunk afresh
 #if defined(S3D_STATS) || defined(S3D_PHASES)
                     const long long s_t0 = clock64();
 #endif

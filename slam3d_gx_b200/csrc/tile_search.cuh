@@ -34,7 +34,7 @@
 #include "search.cuh"
 
 #ifndef TS_CAP
-#define TS_CAP 512            // candidates per warp tile (8 KiB)
+#define TS_CAP 640            // candidates per warp tile (10 KiB): also 5 staged chunks of per-query state (icp.cu)
 #endif
 #define TS_GROUP 8            // queries per box: an aligned octet of lanes
 #define TS_MAX_TRIES 64
@@ -88,6 +88,10 @@ __device__ __forceinline__ void ts_fence_proxy_async()
 __device__ __forceinline__ void ts_cp_async16(void *dst, const void *src)
 {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(ts_smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void ts_cp_async16_s(uint32_t saddr, const void *src)     // destination given as a shared address
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(src) : "memory");
 }
 __device__ __forceinline__ void ts_cp_async_wait_all()
 {
