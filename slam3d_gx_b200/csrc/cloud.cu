@@ -118,7 +118,7 @@ extern "C" void s3d_destroy(s3d_ctx *ctx)
     cudaFree(ctx->d_desc); cudaFreeHost(ctx->h_desc);
     cudaFree(ctx->d_state); cudaFreeHost(ctx->h_state);
     cudaFree(ctx->d_partials); cudaFree(ctx->d_nn_idx); cudaFree(ctx->d_nn_d2); cudaFree(ctx->d_nn_pos); cudaFree(ctx->d_last_nn);
-    cudaFree(ctx->d_cq); cudaFree(ctx->d_cn); cudaFree(ctx->d_lb); cudaFree(ctx->d_barriers);
+    cudaFree(ctx->d_cq); cudaFree(ctx->d_cn); cudaFree(ctx->d_lb); cudaFree(ctx->d_cq2); cudaFree(ctx->d_barriers);
     cudaFree(ctx->d_seg);
     s3d_dev_pool_release(ctx);
     for (auto &kv : ctx->pool_live) cudaFree(kv.first);     // handles the caller never freed

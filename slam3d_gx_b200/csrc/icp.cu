@@ -588,6 +588,7 @@ struct PersistArgs {
     unsigned *barriers;          // [groups], zero at launch, monotonic
     float4 *cq;                  // per query: its correspondence (x,y,z, original target index; -1: none)
     float4 *cn;                  // per query: the correspondence's normal (nx,ny,nz,valid)   (point-to-plane)
+    float4 *cq2;                 // per query with a near tie (xl.w < 0): the runner-up (x,y,z, original index)
     float4 *xl;                  // per query: its transformed position when it was last searched (x,y,z) and, in .w, the lower
                                  // bound found then on its distance to every target point other than the correspondence
     long long nn_stride;         // queries per pair in the three arrays above
@@ -602,6 +603,28 @@ __device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned *p)      // po
     unsigned v;
     asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
+}
+
+
+// Near tie (rare path of the skip test, a real call to keep it out of the streaming loop's registers): the runner-up q2
+// of the query's last search was kept, and every target point other than q and q2 is at least `bound3` away from the
+// query's present position.  Both are evaluated; the nearer (lower original index on equality) is the exact nearest
+// neighbour if it beats that bound.  When the two swap roles the stored state is swapped too.
+template <int EST>
+__device__ __noinline__ int resolve_near_tie(float4 *cq, float4 *cq2, float4 *cn, const float4 *tgt_nrm, int i, float x, float y, float z,
+                                             float bound3, float4 q, float d2q)
+{
+    // returns 0: not settled (search), 1: q stays, 2: q2 took over (cq/cq2/cn of the query rewritten; the caller reloads them).
+    // Everything by value: nothing of the caller's streaming loop has its address taken.
+    const float4 q2 = __ldcg(&cq2[i]);
+    const float d2b = s3d_dist2(x, y, z, q2.x, q2.y, q2.z);
+    const bool second = d2b < d2q || (d2b == d2q && __float_as_int(q2.w) < __float_as_int(q.w));
+    const float dw = sqrtf(second ? d2b : d2q);
+    if (!(dw * 1.000002f + 2e-7f < bound3)) return 0;
+    if (!second) return 1;
+    cq[i] = q2; cq2[i] = q;
+    if (EST == S3D_ESTIMATOR_POINT_TO_PLANE) cn[i] = __ldg(&tgt_nrm[__float_as_int(q2.w)]);
+    return 2;
 }
 
 template <int EST>
@@ -652,6 +675,7 @@ __global__ void __launch_bounds__(TS_BLOCK, 1) icp_persist_kernel(const PersistA
         float4 *my_cq = a.cq + (size_t)pair * a.nn_stride;
         float4 *my_cn = a.cn + (size_t)pair * a.nn_stride;
         float4 *my_xl = a.xl + (size_t)pair * a.nn_stride;
+        float4 *my_cq2 = a.cq2 + (size_t)pair * a.nn_stride;
         // Work is dealt out in OCTETS (8 consecutive source points = 128 contiguous bytes of every per-query array):
         // octet u belongs to warp slot (u mod W) of the group (W = all its warps; slot = rank + group_ctas * warp, so
         // consecutive octets go to different CTAs).  A warp's k-th chunk is its octets 4k..4k+3, one per 8 lanes: every
@@ -664,18 +688,14 @@ __global__ void __launch_bounds__(TS_BLOCK, 1) icp_persist_kernel(const PersistA
 
         for (int it = 0; it < a.iterations; ++it) {
             if (st.status != 0) break;            // failed pairs stop; every CTA of the group sees the same state
-            float T[12];                          // (the previous pose stays in shared memory: it is needed on rare paths only)
-            #pragma unroll
-            for (int k = 0; k < 12; ++k) T[k] = st.Tf[k];
+            const float *T = st.Tf;               // the pose is read from shared memory where it is used: 12 registers less in a
+                                                  // loop that also carries 29 double accumulators
             const bool last = (it == a.iterations - 1);
             // float pose bitwise unchanged since the previous iteration: every transformed point is bitwise the same,
             // so every correspondence of the previous iteration is still the exact answer
             bool same_pose = it > 0;
             #pragma unroll
             for (int k = 0; k < 12; ++k) same_pose = same_pose && (__float_as_uint(T[k]) == __float_as_uint(st.Tf_prev[k]));
-            double acc[29];
-            #pragma unroll
-            for (int k = 0; k < 29; ++k) acc[k] = 0.0;
             PHASE_T0();
 #if defined(S3D_STATS) || defined(S3D_PHASES)
             if (blockIdx.x == 0 && threadIdx.x == 0 && same_pose) atomicAdd(&g_stats[30], 1ull);
@@ -687,13 +707,16 @@ __global__ void __launch_bounds__(TS_BLOCK, 1) icp_persist_kernel(const PersistA
 #endif
 #endif
 
-            // Streaming part: each warp walks its chunks of 32 consecutive queries (fixed assignment: the same thread
-            // sees the same query every iteration).  The per-query state of up to TS_STAGE chunks (4 x 16 B per query:
-            // point, correspondence, search position + bound, normal) is brought into the warp's tile by cp.async up
-            // front, every load in flight at once and no registers spent on prefetching: a late iteration (nearly every
-            // query keeps its correspondence) is one pass over 64 B/point with one memory latency exposed.  A search
-            // uses the tile itself, so what was staged beyond the current chunk is staged again afterwards (then only
-            // one chunk ahead: in the first iterations every chunk searches).
+            // Every warp walks its chunks of 32 queries twice per iteration (fixed assignment: the same thread sees the same
+            // query every iteration):
+            //   decide pass      skip test / near-tie check / search; what changes is written to the per-query state.  No
+            //                    accumulator is alive here, so the searches (real calls) cost no spills in the hot loops.
+            //   accumulate pass  re-reads point, correspondence and normal, forms the 29 sums: no call, no branch on the search.
+            // The per-query state of up to TS_STAGE chunks (16 B per query and array) is brought into the warp's tile by
+            // cp.async up front, every load in flight at once and no registers spent on prefetching: a late iteration
+            // (nearly every query keeps its correspondence) exposes two memory latencies in all.  A search uses the tile
+            // itself, so what was staged beyond the current chunk is staged again afterwards (then only one chunk ahead: in
+            // the first iterations every chunk searches).
             const uint32_t sbuf = ts_smem_u32(buf);
             int staged_hi = 0, stage_lo = 0, stage_depth = TS_STAGE;
             for (int kc = 0; wslot + W * 4 * kc < nunits; ++kc) {          // warp-uniform: the chunk's first octet exists
@@ -708,7 +731,6 @@ __global__ void __launch_bounds__(TS_BLOCK, 1) icp_persist_kernel(const PersistA
                             if (it > 0) {
                                 ts_cp_async16_s(dst + 512u, &my_cq[is]);
                                 ts_cp_async16_s(dst + 1024u, &my_xl[is]);
-                                if (EST == S3D_ESTIMATOR_POINT_TO_PLANE) ts_cp_async16_s(dst + 1536u, &my_cn[is]);
                             }
                         }
                     }
@@ -717,9 +739,9 @@ __global__ void __launch_bounds__(TS_BLOCK, 1) icp_persist_kernel(const PersistA
                 const int u = CHUNK_UNIT(kc), i = (u << 3) + (lane & 7);
                 const bool in = u < nunits && i < d.n_src;
                 const uint32_t sl = sbuf + 16u * (uint32_t)((kc - stage_lo) * 128 + lane);
-                const float4 p = ts_lds128(sl), q_old = ts_lds128(sl + 512u), xl = ts_lds128(sl + 1024u), nv_old = ts_lds128(sl + 1536u);
+                const float4 p = ts_lds128(sl), q_old = ts_lds128(sl + 512u), xl = ts_lds128(sl + 1024u);
                 float3 x = make_float3(0.f, 0.f, 0.f);
-                float4 q = make_float4(0.f, 0.f, 0.f, __int_as_float(-1)), nv = make_float4(0.f, 0.f, 0.f, 1.f);
+                float4 q = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
                 float d2q = INFINITY, r = 1.5f * cell;
                 bool pending = in;
                 if (in) {
@@ -728,18 +750,21 @@ __global__ void __launch_bounds__(TS_BLOCK, 1) icp_persist_kernel(const PersistA
                         q = q_old;
                         if (same_pose) {
                             pending = false;
-                            if (__float_as_int(q.w) >= 0) { d2q = s3d_dist2(x.x, x.y, x.z, q.x, q.y, q.z); if (EST == S3D_ESTIMATOR_POINT_TO_PLANE) nv = nv_old; }
                             STAT(1, 1);
                         } else if (__float_as_int(q.w) >= 0) {
                             // Triangle inequality against the state of the last search of this query: it was at xl.xyz, and every
                             // target point other than q was at least xl.w away from there.
                             d2q = s3d_dist2(x.x, x.y, x.z, q.x, q.y, q.z);
                             const float mv = sqrtf(s3d_dist2(x.x, x.y, x.z, xl.x, xl.y, xl.z));
-                            const float lbm = xl.w - (mv * 1.000002f + 5e-8f);
+                            const float moved = mv * 1.000002f + 5e-8f;
                             const float dq = sqrtf(d2q);
-                            if (dq * 1.000002f + 2e-7f < lbm) {       // still the exact nearest neighbour: no search, no state update
+                            bool keep = dq * 1.000002f + 2e-7f < xl.w - moved;       // still the exact nearest neighbour
+                            if (!keep && xl.w < 0.f) {        // near tie (rare): settle it with the runner-up that was kept
+                                const int rc = resolve_near_tie<EST>(my_cq, my_cq2, my_cn, d.tgt_nrm, i, x.x, x.y, x.z, -xl.w - moved, q, d2q);
+                                keep = rc != 0;               // (rc == 2: the runner-up took over, the helper rewrote the state)
+                            }
+                            if (keep) {                                               // no search
                                 pending = false;
-                                if (EST == S3D_ESTIMATOR_POINT_TO_PLANE) nv = nv_old;
                                 STAT(1, 1);
                             } else {
                                 // The old correspondence is a real target point, so dq bounds the ball.  After a small move it is
@@ -763,9 +788,9 @@ __global__ void __launch_bounds__(TS_BLOCK, 1) icp_persist_kernel(const PersistA
                     for (int level = (it == 0 && have_coarse) ? 0 : 1; level < 2; ++level) {
                         STAT(level ? 0 : 6, pending);
 #ifdef TS_USE_TMA
-                        b = tile_search(&cfg[level], x.x, x.y, x.z, level ? r : ccell, pending, buf, lane, bar_w, &parity TS_TM_PASS);
+                        b = tile_search(&cfg[level], x.x, x.y, x.z, level ? r : ccell, pending, buf, lane, level == 1 && it >= 4, bar_w, &parity TS_TM_PASS);
 #else
-                        b = tile_search(&cfg[level], x.x, x.y, x.z, level ? r : ccell, pending, buf, lane TS_TM_PASS);
+                        b = tile_search(&cfg[level], x.x, x.y, x.z, level ? r : ccell, pending, buf, lane, level == 1 && it >= 4 TS_TM_PASS);
 #endif
                         if (level == 0 && pending && b.bd < INFINITY) r = sqrtf(b.bd) * 1.00001f + slack;
                     }
@@ -773,20 +798,50 @@ __global__ void __launch_bounds__(TS_BLOCK, 1) icp_persist_kernel(const PersistA
                     if (pending) {
                         q = b.bq; d2q = b.bd;
                         if (!(b.bd < INFINITY)) q.w = __int_as_float(-1);      // nothing within reach
-                        my_cq[i] = q; my_xl[i] = make_float4(x.x, x.y, x.z, lbv);
-                        if (EST == S3D_ESTIMATOR_POINT_TO_PLANE && __float_as_int(q.w) >= 0) {
-                            nv = __ldg(&d.tgt_nrm[__float_as_int(q.w)]);
-                            my_cn[i] = nv;
-                        }
+                        my_cq[i] = q;
+                        if (b.lb3 > 0.f) { my_cq2[i] = b.q2; my_xl[i] = make_float4(x.x, x.y, x.z, -b.lb3); }     // near tie: keep the runner-up too
+                        else my_xl[i] = make_float4(x.x, x.y, x.z, lbv);
+                        if (EST == S3D_ESTIMATOR_POINT_TO_PLANE && __float_as_int(q.w) >= 0)
+                            my_cn[i] = __ldg(&d.tgt_nrm[__float_as_int(q.w)]);
                     }
 #if defined(S3D_STATS) || defined(S3D_PHASES)
                     ws_t += clock64() - s_t0; ++ws_n;
 #endif
                 }
-                const int j = __float_as_int(q.w);
-                const bool ok = in && (j >= 0) && (d2q <= a.max_d2) && (nv.w != 0.f);
-                if (ok) accumulate_d<EST>(acc, x.x, x.y, x.z, q, nv, d2q);
-                if (last && a.nn_out && in) a.nn_out[i] = ok ? j : -1;
+            }
+
+            // ---- accumulate pass ----
+            double acc[29];
+            #pragma unroll
+            for (int k = 0; k < 29; ++k) acc[k] = 0.0;
+            for (int kc0 = 0; wslot + W * 4 * kc0 < nunits; kc0 += TS_STAGE) {
+                #pragma unroll
+                for (int c = 0; c < TS_STAGE; ++c) {
+                    const int us = CHUNK_UNIT(kc0 + c), is = (us << 3) + (lane & 7);
+                    if (us < nunits && is < d.n_src) {
+                        const uint32_t dst = sbuf + 16u * (uint32_t)(c * 128 + lane);
+                        ts_cp_async16_s(dst, &d.src[is]);
+                        ts_cp_async16_s(dst + 512u, &my_cq[is]);
+                        if (EST == S3D_ESTIMATOR_POINT_TO_PLANE) ts_cp_async16_s(dst + 1024u, &my_cn[is]);
+                    }
+                }
+                ts_cp_async_wait_all();
+                #pragma unroll
+                for (int c = 0; c < TS_STAGE; ++c) {
+                    const int u = CHUNK_UNIT(kc0 + c), i = (u << 3) + (lane & 7);
+                    if (u < nunits && i < d.n_src) {
+                        const uint32_t sl = sbuf + 16u * (uint32_t)(c * 128 + lane);
+                        const float4 p = ts_lds128(sl), q = ts_lds128(sl + 512u);
+                        float4 nv = make_float4(0.f, 0.f, 0.f, 1.f);
+                        if (EST == S3D_ESTIMATOR_POINT_TO_PLANE) nv = ts_lds128(sl + 1024u);
+                        const float3 x = s3d_xform(T, p.x, p.y, p.z);
+                        const int j = __float_as_int(q.w);
+                        const float d2q = s3d_dist2(x.x, x.y, x.z, q.x, q.y, q.z);    // same expression as in the search: identical bits
+                        const bool ok = (j >= 0) && (d2q <= a.max_d2) && (nv.w != 0.f);
+                        if (ok) accumulate_d<EST>(acc, x.x, x.y, x.z, q, nv, d2q);
+                        if (last && a.nn_out) a.nn_out[i] = ok ? j : -1;
+                    }
+                }
             }
 
 #if defined(S3D_STATS) || defined(S3D_PHASES)
@@ -1001,10 +1056,11 @@ extern "C" int s3d_register_batch(s3d_ctx *ctx, const s3d_cloud *const *src, con
     if (persist) {
         size_t need = (size_t)n_pairs * std::max(n_max, 1);
         if (need > ctx->cap_tile_nn) {
-            cudaFree(ctx->d_cq); cudaFree(ctx->d_cn); cudaFree(ctx->d_lb);
-            ctx->d_cq = nullptr; ctx->d_cn = nullptr; ctx->d_lb = nullptr; ctx->cap_tile_nn = 0;
+            cudaFree(ctx->d_cq); cudaFree(ctx->d_cn); cudaFree(ctx->d_lb); cudaFree(ctx->d_cq2);
+            ctx->d_cq = nullptr; ctx->d_cn = nullptr; ctx->d_lb = nullptr; ctx->d_cq2 = nullptr; ctx->cap_tile_nn = 0;
             S3D_CUDA(ctx, cudaMalloc(&ctx->d_cq, sizeof(float4) * need));
             S3D_CUDA(ctx, cudaMalloc(&ctx->d_cn, sizeof(float4) * need));
+            S3D_CUDA(ctx, cudaMalloc(&ctx->d_cq2, sizeof(float4) * need));
             S3D_CUDA(ctx, cudaMalloc(&ctx->d_lb, sizeof(float4) * need));
             ctx->cap_tile_nn = need;
         }
@@ -1054,7 +1110,7 @@ extern "C" int s3d_register_batch(s3d_ctx *ctx, const s3d_cloud *const *src, con
         S3D_CUDA(ctx, cudaMemsetAsync(ctx->d_barriers, 0, sizeof(unsigned) * p_groups, ctx->stream));
         PersistArgs pa;
         pa.descs = ctx->d_desc; pa.states = ctx->d_state; pa.partials = ctx->d_partials; pa.barriers = ctx->d_barriers;
-        pa.cq = ctx->d_cq; pa.cn = ctx->d_cn; pa.xl = ctx->d_lb; pa.nn_stride = std::max(n_max, 1);
+        pa.cq = ctx->d_cq; pa.cn = ctx->d_cn; pa.cq2 = ctx->d_cq2; pa.xl = ctx->d_lb; pa.nn_stride = std::max(n_max, 1);
         pa.n_pairs = n_pairs; pa.groups = p_groups; pa.group_ctas = p_group_ctas; pa.iterations = prm->max_iterations;
         pa.max_d2 = max_d2; pa.min_corr = min_corr; pa.pivot_eps = pivot_eps; pa.nn_out = nn_out;
         { static const char *e = getenv("S3D_HINT_CELLS"); pa.hint_cells = e ? (float)atof(e) : 1.0f; }

@@ -127,8 +127,11 @@ __device__ __forceinline__ void tile_best_merge(TileBest &a, const float4 obq, f
 }
 
 // One lane's share of the tile: candidates sub, sub+step, ... < m against the query (qx,qy,qz); result merged into W.
+// EXCL: the candidate whose original index is `excl` is left out (second pass that looks for the runner-up).
+#define TS_D2(c) (EXCL && __float_as_int((c).w) == excl ? INFINITY : s3d_dist2(qx, qy, qz, (c).x, (c).y, (c).z))
+template <bool EXCL>
 __device__ __forceinline__ void tile_compare_pass(uint32_t sbuf, int m, int sub, int step,
-                                                  float qx, float qy, float qz, TileBest &W)
+                                                  float qx, float qy, float qz, TileBest &W, int excl)
 {
     // two independent running minima (even / odd visits) halve the dependent chain
     float pd0 = INFINITY, ps0 = INFINITY, pd1 = INFINITY, ps1 = INFINITY;
@@ -137,8 +140,8 @@ __device__ __forceinline__ void tile_compare_pass(uint32_t sbuf, int m, int sub,
     for (; k + 3 * step < m; k += 4 * step) {          // four candidates per turn, two per chain
         const float4 a = ts_lds128(sbuf + 16u * (uint32_t)k), b = ts_lds128(sbuf + 16u * (uint32_t)(k + step));
         const float4 c = ts_lds128(sbuf + 16u * (uint32_t)(k + 2 * step)), e = ts_lds128(sbuf + 16u * (uint32_t)(k + 3 * step));
-        const float da = s3d_dist2(qx, qy, qz, a.x, a.y, a.z), db = s3d_dist2(qx, qy, qz, b.x, b.y, b.z);
-        const float dc = s3d_dist2(qx, qy, qz, c.x, c.y, c.z), de = s3d_dist2(qx, qy, qz, e.x, e.y, e.z);
+        const float da = TS_D2(a), db = TS_D2(b);
+        const float dc = TS_D2(c), de = TS_D2(e);
         bool la = da < pd0, lbb = db < pd1;
         ps0 = fminf(ps0, fmaxf(pd0, da)); ps1 = fminf(ps1, fmaxf(pd1, db));
         pd0 = fminf(pd0, da); pd1 = fminf(pd1, db);
@@ -150,7 +153,7 @@ __device__ __forceinline__ void tile_compare_pass(uint32_t sbuf, int m, int sub,
     }
     for (; k + step < m; k += 2 * step) {
         const float4 a = ts_lds128(sbuf + 16u * (uint32_t)k), b = ts_lds128(sbuf + 16u * (uint32_t)(k + step));
-        const float da = s3d_dist2(qx, qy, qz, a.x, a.y, a.z), db = s3d_dist2(qx, qy, qz, b.x, b.y, b.z);
+        const float da = TS_D2(a), db = TS_D2(b);
         const bool la = da < pd0, lbb = db < pd1;
         ps0 = fminf(ps0, fmaxf(pd0, da)); ps1 = fminf(ps1, fmaxf(pd1, db));
         pd0 = fminf(pd0, da); pd1 = fminf(pd1, db);
@@ -158,7 +161,7 @@ __device__ __forceinline__ void tile_compare_pass(uint32_t sbuf, int m, int sub,
     }
     if (k < m) {
         const float4 a = ts_lds128(sbuf + 16u * (uint32_t)k);
-        const float da = s3d_dist2(qx, qy, qz, a.x, a.y, a.z);
+        const float da = TS_D2(a);
         const bool la = da < pd0;
         ps0 = fminf(ps0, fmaxf(pd0, da)); pd0 = fminf(pd0, da); pk0 = la ? k : pk0;
     }
@@ -166,13 +169,13 @@ __device__ __forceinline__ void tile_compare_pass(uint32_t sbuf, int m, int sub,
     const float pd = fminf(pd0, pd1);
     const float ps = fminf(fminf(ps0, ps1), fmaxf(pd0, pd1));
     int pk = (pd1 < pd0) ? pk1 : pk0;
-    if (pk < 0) return;                                   // this lane saw no candidate
+    if (pk < 0 || !(pd < INFINITY)) return;               // this lane saw no (admissible) candidate
     if (ps == pd) {
         // equal distances: the lowest original index wins (rare; rescan this lane's share)
         int bi = INT_MAX;
         for (int kk = sub; kk < m; kk += step) {
             const float4 q = ts_lds128(sbuf + 16u * (uint32_t)kk);
-            const float d2 = s3d_dist2(qx, qy, qz, q.x, q.y, q.z);
+            const float d2 = TS_D2(q);
             const int qi = __float_as_int(q.w);
             if (d2 == pd && qi < bi) { bi = qi; pk = kk; }
         }
@@ -190,7 +193,8 @@ __device__ __forceinline__ void tile_compare_pass(uint32_t sbuf, int m, int sub,
 struct TileCfg {              // one search level (fine grid / decimated grid); lives in shared memory
     GridParams gp; const uint32_t *cell_start; const float4 *pts; float slack; float gate_r;
 };
-struct TileOut { float4 bq; float bd; float lb; };
+struct TileOut { float4 bq; float bd; float lb; float4 q2; float lb3; };     // q2/lb3: runner-up and bound on all others (near ties)
+#define TS_TIE_GAP 1e-5f       // a nearest/runner-up gap below this (metres) is a near tie: the runner-up is kept too
 
 #ifdef TS_USE_TMA
 #define TS_BAR_ARG , uint64_t *bar, uint32_t *parity_p
@@ -202,7 +206,7 @@ struct TileOut { float4 bq; float bd; float lb; };
 // call the search spills them only around itself (the rare path of a late iteration) instead of raising the
 // register pressure of the whole streaming loop.
 __device__ __noinline__ TileOut tile_search(const TileCfg *cfg, float px, float py, float pz, float r, bool pending,
-                                            float4 *__restrict__ buf, int lane TS_BAR_ARG TS_TM_ARG)
+                                            float4 *__restrict__ buf, int lane, bool want2 TS_BAR_ARG TS_TM_ARG)
 {
     TS_T0();
     const unsigned full = 0xffffffffu;
@@ -211,6 +215,7 @@ __device__ __noinline__ TileOut tile_search(const TileCfg *cfg, float px, float 
     const float slack = cfg->slack, gate_r = cfg->gate_r;
     TileBest B; float lbound = 0.f;
     tile_best_init(B);
+    float4 Q2 = make_float4(0.f, 0.f, 0.f, __int_as_float(-1)); float LB3 = 0.f;
 #ifdef TS_USE_TMA
     uint32_t parity = *parity_p;
 #endif
@@ -263,7 +268,7 @@ __device__ __noinline__ TileOut tile_search(const TileCfg *cfg, float px, float 
         // ---- gather the rows into the tile by TMA, compare whenever it is full ----
         // 32 rows per round (one per lane): two cell-start loads give the row's point range, one bulk copy moves it.
         // What does not fit into the tile stays with its lane for the next turn (`carry`): rows of any length go through.
-        int fill = 0, t0 = 0;
+        int fill = 0, t0 = 0, nfills = 0, last_fill = 0;
         uint32_t rs = 0u, cnt = 0u;
         bool carry = false;
         while (carry || t0 < rows) {
@@ -325,7 +330,8 @@ __device__ __noinline__ TileOut tile_search(const TileCfg *cfg, float px, float 
                 ts_cp_async_wait_all();
                 __syncwarp();
 #endif
-                if (work) tile_compare_pass(sbuf, fill, sub, step, qx, qy, qz, W);
+                if (work) tile_compare_pass<false>(sbuf, fill, sub, step, qx, qy, qz, W, -1);
+                ++nfills; last_fill = fill;
                 STAT(3, work ? fill / step : 0);
                 __syncwarp();
                 TS_CNT(26, fill);
@@ -358,12 +364,41 @@ __device__ __noinline__ TileOut tile_search(const TileCfg *cfg, float px, float 
             const bool done = (R.bd <= margin * margin) || (margin >= gate_r) || !(mc < INFINITY);
             if (done) {
                 B = R;
-                lbound = fminf(sqrtf(R.sd), margin) * 0.999998f - 5e-8f;
+                lbound = fmaxf(fminf(sqrtf(R.sd), margin) * 0.999998f - 5e-8f, 0.f);
                 todo = false;
+                LB3 = 0.f;
             } else {
                 // what was found is a valid bound; a query that found nothing doubles its hint
                 r = (R.bd < INFINITY) ? sqrtf(R.bd) * 1.00001f + slack : 2.f * r + slack;
                 r = fminf(r, gate_r * 1.00001f + 1e-6f);
+            }
+        }
+        // ---- near ties: a query whose runner-up is within TS_TIE_GAP of its nearest neighbour would fail the caller's
+        // skip test in every later iteration (the float noise of the test is ~1e-6 m) and be searched again and again.
+        // For those the runner-up itself and a bound on everything else are returned: the caller then settles the
+        // order of the two by evaluating both.  One more pass over the tile (still in place when it was filled once),
+        // leaving out the winner.
+        {
+            const bool tie = want2 && inbox && !todo && nfills == 1 && R.sd < INFINITY &&
+                             sqrtf(R.sd) - sqrtf(R.bd) < TS_TIE_GAP && sqrtf(R.sd) < margin;
+            if (__any_sync(full, tie)) {
+                TileBest W2; tile_best_init(W2);
+                const int excl = __float_as_int(W.bq.w);           // the slot's winner (all lanes of a slot hold it)
+                if (work) tile_compare_pass<true>(sbuf, last_fill, sub, step, qx, qy, qz, W2, excl);
+                for (int o = NS; o < 32; o <<= 1) {
+                    const float4 obq = make_float4(__shfl_xor_sync(full, W2.bq.x, o), __shfl_xor_sync(full, W2.bq.y, o),
+                                                   __shfl_xor_sync(full, W2.bq.z, o), __shfl_xor_sync(full, W2.bq.w, o));
+                    const float obd = __shfl_xor_sync(full, W2.bd, o), osd = __shfl_xor_sync(full, W2.sd, o);
+                    tile_best_merge(W2, obq, obd, osd);
+                }
+                const float4 r2 = make_float4(__shfl_sync(full, W2.bq.x, myslot), __shfl_sync(full, W2.bq.y, myslot),
+                                              __shfl_sync(full, W2.bq.z, myslot), __shfl_sync(full, W2.bq.w, myslot));
+                const float rd2 = __shfl_sync(full, W2.bd, myslot), td2 = __shfl_sync(full, W2.sd, myslot);
+                if (tie && rd2 < INFINITY) {
+                    const float lb3 = fminf(sqrtf(td2), margin) * 0.999998f - 5e-8f;
+                    if (lb3 > sqrtf(rd2) + 1e-6f) { Q2 = r2; LB3 = lb3; }      // worth it only if the third is clearly behind
+                }
+                __syncwarp();
             }
         }
         TS_T(4);
@@ -372,6 +407,6 @@ __device__ __noinline__ TileOut tile_search(const TileCfg *cfg, float px, float 
     *parity_p = parity;
 #endif
     TileOut o;
-    o.bq = B.bq; o.bd = B.bd; o.lb = lbound;
+    o.bq = B.bq; o.bd = B.bd; o.lb = lbound; o.q2 = Q2; o.lb3 = LB3;
     return o;
 }
