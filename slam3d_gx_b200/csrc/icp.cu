@@ -570,7 +570,10 @@ __global__ void __launch_bounds__(ICP_BLOCK, ICP_MIN_BLOCKS) icp_iter_kernel(con
 // ------------------------------------------------------------------------------------------------
 // the persistent kernel: all iterations of all pairs in one cooperative launch
 // ------------------------------------------------------------------------------------------------
+#ifndef TS_BLOCK
 #define TS_BLOCK 512
+#endif
+static_assert(TS_CAP * 16 >= 29 * 33 * 8, "the warp tile also carries the transposed 29 x 33 double reduction");
 #define TS_WARPS (TS_BLOCK / 32)
 #define TS_STAGE (TS_CAP / 128)     // chunks of per-query state (32 lanes x 4 float4) a warp's tile holds
 
