@@ -599,6 +599,8 @@ struct PersistArgs {
     float max_d2; int min_corr; double pivot_eps;
     int32_t *nn_out;             // correspondences of the last iteration (single pair) or null
     float hint_cells;            // first-guess search radius after a big pose update, in cells
+    float first_cells;           // first-guess search radius of the first iteration when the decimated index is not used, in cells
+    int use_coarse;              // first iteration: bound the search with the nearest point of the decimated index
 };
 
 __device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned *p)      // polling load: no L1 invalidate per poll
@@ -661,7 +663,7 @@ __global__ void __launch_bounds__(TS_BLOCK, 1) icp_persist_kernel(const PersistA
 
     for (int pair = group; pair < a.n_pairs; pair += a.groups) {
         const PairDesc d = a.descs[pair];
-        const bool have_coarse = d.coarse_grid != nullptr;
+        const bool have_coarse = d.coarse_grid != nullptr && a.use_coarse;
         __syncthreads();
         if (threadIdx.x == 0) {
             st = a.states[pair];
@@ -745,7 +747,7 @@ __global__ void __launch_bounds__(TS_BLOCK, 1) icp_persist_kernel(const PersistA
                 const float4 p = ts_lds128(sl), q_old = ts_lds128(sl + 512u), xl = ts_lds128(sl + 1024u);
                 float3 x = make_float3(0.f, 0.f, 0.f);
                 float4 q = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
-                float d2q = INFINITY, r = 1.5f * cell;
+                float d2q = INFINITY, r = a.first_cells * cell;
                 bool pending = in;
                 if (in) {
                     x = s3d_xform(T, p.x, p.y, p.z);
@@ -1117,6 +1119,8 @@ extern "C" int s3d_register_batch(s3d_ctx *ctx, const s3d_cloud *const *src, con
         pa.n_pairs = n_pairs; pa.groups = p_groups; pa.group_ctas = p_group_ctas; pa.iterations = prm->max_iterations;
         pa.max_d2 = max_d2; pa.min_corr = min_corr; pa.pivot_eps = pivot_eps; pa.nn_out = nn_out;
         { static const char *e = getenv("S3D_HINT_CELLS"); pa.hint_cells = e ? (float)atof(e) : 1.0f; }
+        { static const char *e = getenv("S3D_FIRST_CELLS"); pa.first_cells = e ? (float)atof(e) : 1.5f; }
+        { static const char *e = getenv("S3D_USE_COARSE"); pa.use_coarse = e ? atoi(e) : 1; }
         void *kargs[] = {&pa};
         const void *fn = plane ? (const void *)icp_persist_kernel<S3D_ESTIMATOR_POINT_TO_PLANE> : (const void *)icp_persist_kernel<S3D_ESTIMATOR_SVD>;
         S3D_CUDA(ctx, cudaLaunchCooperativeKernel(fn, dim3(p_groups * p_group_ctas), dim3(TS_BLOCK), kargs, p_smem, ctx->stream));
