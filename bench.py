@@ -167,28 +167,27 @@ def main():
     from slam3d_gx_b200 import sharding
     rec_bytes = _abi.RESULT_BYTES
 
-    # Pose gather over NCCL: the only collective of the path.  The 160-byte record of every rank's
-    # step is all-gathered asynchronously on NCCL's stream, so the gather of step i overlaps the registration of
-    # step i+1; all gathers are waited for (and decoded) before the timed region ends.
-    gathers = []
-    pin_rec = torch.empty(rec_bytes, dtype=torch.uint8).pin_memory() if world > 1 else None
+    # Pose gather over NCCL: the only collective of the path.  Like config 4 (a batch of pairs sharded over the
+    # ranks, ONE all-gather of the pose records when the batch is done), the records of a rank's steps are collected on the
+    # host and all-gathered in one NCCL call at the end of the timed region, inside it.  (A per-step NCCL kernel cannot run
+    # beside the registration kernel, which holds every SM's register file; it would serialise the ranks on each other.)
+    records = []
 
     def step(i):
         k = i % args.pool
         res = ctx.register_batch([src[k]], [tgt[k]], None, prm, raw=True)
         if world > 1:
-            pin_rec.copy_(torch.frombuffer(bytearray(bytes(res[0])), dtype=torch.uint8))
-            send = pin_rec.to("cuda", non_blocking=True)
-            recv = torch.empty(world * rec_bytes, dtype=torch.uint8, device="cuda")
-            gathers.append((dist.all_gather_into_tensor(recv, send, async_op=True), recv))
+            records.append(bytes(res[0]))
         return res[0]
 
     def finish_gathers():
-        n = 0
-        for work, recv in gathers:
-            work.wait()
-            n += len(sharding.bytes_to_records(recv.cpu().numpy()))
-        gathers.clear()
+        if world == 1 or not records:
+            return 0
+        send = torch.frombuffer(bytearray(b"".join(records)), dtype=torch.uint8).to("cuda")
+        recv = torch.empty(world * send.numel(), dtype=torch.uint8, device="cuda")
+        dist.all_gather_into_tensor(recv, send)
+        n = len(sharding.bytes_to_records(recv.cpu().numpy()))
+        records.clear()
         return n
 
     for k in range(args.pool):      # prime every pair once (first-use device allocations of its index), untimed
