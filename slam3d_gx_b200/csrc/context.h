@@ -98,7 +98,8 @@ struct s3d_ctx {
     size_t cap_seg = 0;
     void *d_seg = nullptr;
     void *h_pinned = nullptr; size_t cap_pinned = 0;
-    std::map<uint64_t, cudaGraphExec_t> graphs;
+    std::map<uint64_t, cudaGraphExec_t> graphs;     // index-build launch sequences (grid.cu), keyed by the buffers they touch
+    std::map<uint64_t, int> graph_nodes;
     // caching device allocator: clouds and search indices come and go per frame, cudaMalloc/cudaFree of their
     // 10..40 MB buffers costs milliseconds; freed blocks are kept and handed out again (same stream => ordered)
     std::map<void *, size_t> pool_live;

@@ -225,9 +225,8 @@ __global__ void __launch_bounds__(256) decimate_kernel(const float4 *__restrict_
     }
 }
 
-// Build (or rebuild) an index over n device points.  max_cells bounds the dense cell array.
-static int grid_build_raw(s3d_ctx *ctx, GridIndex &g, const float4 *d_pts, const float4 *d_nrm, int n, float cell, float scale,
-                          uint32_t max_cells)
+// Buffers of an index over n device points (max_cells bounds the dense cell array); allocation only.
+static int grid_ensure_buffers(s3d_ctx *ctx, GridIndex &g, bool with_normals, int n, uint32_t max_cells)
 {
     size_t np = (size_t)(n > 0 ? n : 1);
     if (g.cap_points < n || g.cap_cells < max_cells || !g.d_params) {
@@ -241,7 +240,14 @@ static int grid_build_raw(s3d_ctx *ctx, GridIndex &g, const float4 *d_pts, const
         S3D_CUDA(ctx, s3d_dev_alloc_t(ctx, &g.d_rowmask, sizeof(uint32_t) * ((size_t)max_cells / 8 + 8192)));
         g.cap_points = n; g.cap_cells = max_cells;
     }
-    if (d_nrm && !g.d_sorted_nrm) S3D_CUDA(ctx, s3d_dev_alloc_t(ctx, &g.d_sorted_nrm, sizeof(float4) * (size_t)(g.cap_points > 0 ? g.cap_points : 1)));
+    if (with_normals && !g.d_sorted_nrm) S3D_CUDA(ctx, s3d_dev_alloc_t(ctx, &g.d_sorted_nrm, sizeof(float4) * (size_t)(g.cap_points > 0 ? g.cap_points : 1)));
+    return S3D_OK;
+}
+
+// The launches that build (or rebuild) the index: nothing but kernel launches on ctx->stream, so the sequence can be captured.
+static int grid_launch(s3d_ctx *ctx, GridIndex &g, const float4 *d_pts, const float4 *d_nrm, int n, float cell, float scale,
+                       uint32_t max_cells)
+{
     cudaStream_t st = ctx->stream;
     const int wide = ctx->sm_count * 8;
     const int scan_blocks = (int)(max_cells / SCAN_TILE) + 1;
@@ -258,28 +264,87 @@ static int grid_build_raw(s3d_ctx *ctx, GridIndex &g, const float4 *d_pts, const
                                                                            g.d_sorted_pts, d_nrm ? g.d_sorted_nrm : nullptr);
         S3D_LAUNCHED(ctx);
     }
-    g.valid = true; g.has_normals = d_nrm != nullptr; g.requested_cell = cell; g.n = n;
     return S3D_OK;
 }
 
+static int build_launches(s3d_ctx *ctx, s3d_cloud *c, float cell, float scale, bool want_coarse, int nc)
+{
+    int rc = grid_launch(ctx, c->grid, c->d_pts, c->d_nrm, c->n, cell, scale, S3D_GRID_MAX_CELLS);
+    if (rc) return rc;
+    if (want_coarse) {
+        // coarse seeding index over every S3D_COARSE_STRIDE-th point (first-iteration seeds, see icp.cu)
+        decimate_kernel<<<std::min(ctx->sm_count * 8, (nc + 255) / 256), 256, 0, ctx->stream>>>(c->d_pts, nc, S3D_COARSE_STRIDE, c->d_coarse_pts);
+        S3D_LAUNCHED(ctx);
+        rc = grid_launch(ctx, c->coarse, c->d_coarse_pts, nullptr, nc, 0.f, scale, S3D_COARSE_MAX_CELLS);
+    }
+    return rc;
+}
+
+static uint64_t fnv(uint64_t h, const void *p, size_t n)
+{
+    const unsigned char *b = (const unsigned char *)p;
+    for (size_t i = 0; i < n; ++i) { h ^= b[i]; h *= 0x100000001b3ull; }
+    return h;
+}
+
+// The build is ~19 small kernels whose parameters are all device resident: issued one by one they are bound by the host's
+// launch rate (~5 us each).  The sequence is therefore captured into a CUDA graph, keyed by every pointer and size it
+// touches (the caching allocator hands the same buffers to the next frame's cloud, so steady state replays one graph).
 int s3d_grid_build(s3d_ctx *ctx, s3d_cloud *c, float cell)
 {
     static const float scale = auto_scale_from_env();
-    int rc = grid_build_raw(ctx, c->grid, c->d_pts, c->d_nrm, c->n, cell, scale, S3D_GRID_MAX_CELLS);
+    static const bool use_graph = []() { const char *e = getenv("S3D_INDEX_GRAPH"); return !e || atoi(e) != 0; }();
+    const bool want_coarse = c->n >= S3D_COARSE_MIN_POINTS;
+    const int nc = c->n / S3D_COARSE_STRIDE;
+    int rc = grid_ensure_buffers(ctx, c->grid, c->d_nrm != nullptr, c->n, S3D_GRID_MAX_CELLS);
     if (rc) return rc;
-    // coarse seeding index over every S3D_COARSE_STRIDE-th point (first-iteration seeds, see icp.cu)
     c->coarse.valid = false;
-    if (c->n >= S3D_COARSE_MIN_POINTS) {
-        int nc = c->n / S3D_COARSE_STRIDE;
+    if (want_coarse) {
         if (c->cap_coarse_pts < nc) {
             s3d_dev_free(ctx, c->d_coarse_pts); c->d_coarse_pts = nullptr;
             S3D_CUDA(ctx, s3d_dev_alloc_t(ctx, &c->d_coarse_pts, sizeof(float4) * (size_t)nc));
             c->cap_coarse_pts = nc;
         }
-        decimate_kernel<<<std::min(ctx->sm_count * 8, (nc + 255) / 256), 256, 0, ctx->stream>>>(c->d_pts, nc, S3D_COARSE_STRIDE, c->d_coarse_pts);
-        S3D_LAUNCHED(ctx);
-        rc = grid_build_raw(ctx, c->coarse, c->d_coarse_pts, nullptr, nc, 0.f, scale, S3D_COARSE_MAX_CELLS);
+        rc = grid_ensure_buffers(ctx, c->coarse, false, nc, S3D_COARSE_MAX_CELLS);
         if (rc) return rc;
     }
+    bool done = false;
+    if (use_graph) {
+        const void *ptrs[] = {c->d_pts, c->d_nrm, c->d_coarse_pts, c->grid.d_params, c->grid.d_cell_start, c->grid.d_sorted_pts,
+                              c->grid.d_sorted_nrm, c->grid.d_rank, c->grid.d_bbox, c->grid.d_block_sums, c->grid.d_rowmask,
+                              c->coarse.d_params, c->coarse.d_cell_start, c->coarse.d_sorted_pts, c->coarse.d_rank, c->coarse.d_bbox,
+                              c->coarse.d_block_sums, c->coarse.d_rowmask, (const void *)ctx->stream};
+        uint64_t key = fnv(0xcbf29ce484222325ull, ptrs, sizeof(ptrs));
+        const int ints[] = {c->n, (int)want_coarse, nc};
+        key = fnv(key, ints, sizeof(ints)); key = fnv(key, &cell, sizeof(cell)); key = fnv(key, &scale, sizeof(scale));
+        auto it = ctx->graphs.find(key);
+        if (it == ctx->graphs.end()) {
+            if (ctx->graphs.size() > 256) { for (auto &kv : ctx->graphs) cudaGraphExecDestroy(kv.second); ctx->graphs.clear(); }
+            cudaGraph_t graph = nullptr; cudaGraphExec_t exec = nullptr;
+            const int64_t l0 = ctx->launches;
+            if (cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+                rc = build_launches(ctx, c, cell, scale, want_coarse, nc);
+                cudaError_t e = cudaStreamEndCapture(ctx->stream, &graph);
+                ctx->launches = l0;                              // captured, not launched
+                if (rc == S3D_OK && e == cudaSuccess && graph && cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess) {
+                    it = ctx->graphs.emplace(key, exec).first;
+                    ctx->graph_nodes[key] = want_coarse ? 19 : 9;
+                }
+                if (graph) cudaGraphDestroy(graph);
+                cudaGetLastError();
+                rc = S3D_OK;
+            }
+        }
+        if (it != ctx->graphs.end() && cudaGraphLaunch(it->second, ctx->stream) == cudaSuccess) {
+            ctx->launches += ctx->graph_nodes[key];
+            done = true;
+        }
+    }
+    if (!done) {
+        rc = build_launches(ctx, c, cell, scale, want_coarse, nc);
+        if (rc) return rc;
+    }
+    c->grid.valid = true; c->grid.has_normals = c->d_nrm != nullptr; c->grid.requested_cell = cell; c->grid.n = c->n;
+    if (want_coarse) { c->coarse.valid = true; c->coarse.has_normals = false; c->coarse.requested_cell = 0.f; c->coarse.n = nc; }
     return S3D_OK;
 }
