@@ -601,6 +601,7 @@ struct PersistArgs {
     float hint_cells;            // first-guess search radius after a big pose update, in cells
     float first_cells;           // first-guess search radius of the first iteration when the decimated index is not used, in cells
     int use_coarse;              // first iteration: bound the search with the nearest point of the decimated index
+    float slack_cells;           // extra search radius beyond the seed distance, in cells: buys the skip test its margin
 };
 
 __device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned *p)      // polling load: no L1 invalidate per poll
@@ -668,7 +669,7 @@ __global__ void __launch_bounds__(TS_BLOCK, 1) icp_persist_kernel(const PersistA
         if (threadIdx.x == 0) {
             st = a.states[pair];
             cfg[1].gp = *d.grid; cfg[1].cell_start = d.cell_start; cfg[1].pts = d.sorted_pts;
-            cfg[1].slack = 0.2f * cfg[1].gp.cell; cfg[1].gate_r = gate_r;
+            cfg[1].slack = a.slack_cells * cfg[1].gp.cell; cfg[1].gate_r = gate_r;
             cfg[0] = cfg[1];
             if (have_coarse) {
                 cfg[0].gp = *d.coarse_grid; cfg[0].cell_start = d.coarse_cell_start; cfg[0].pts = d.coarse_pts;
@@ -1121,6 +1122,7 @@ extern "C" int s3d_register_batch(s3d_ctx *ctx, const s3d_cloud *const *src, con
         { static const char *e = getenv("S3D_HINT_CELLS"); pa.hint_cells = e ? (float)atof(e) : 1.0f; }
         { static const char *e = getenv("S3D_FIRST_CELLS"); pa.first_cells = e ? (float)atof(e) : 1.5f; }
         { static const char *e = getenv("S3D_USE_COARSE"); pa.use_coarse = e ? atoi(e) : 1; }
+        { static const char *e = getenv("S3D_SLACK_CELLS"); pa.slack_cells = e ? (float)atof(e) : 0.08f; }
         void *kargs[] = {&pa};
         const void *fn = plane ? (const void *)icp_persist_kernel<S3D_ESTIMATOR_POINT_TO_PLANE> : (const void *)icp_persist_kernel<S3D_ESTIMATOR_SVD>;
         S3D_CUDA(ctx, cudaLaunchCooperativeKernel(fn, dim3(p_groups * p_group_ctas), dim3(TS_BLOCK), kargs, p_smem, ctx->stream));
