@@ -196,6 +196,28 @@ def test_batch_shared_target_matches_single(ctx, small_cam):
     tgt.free()
 
 
+def test_batch_with_more_pairs_than_ctas(ctx):
+    """More pairs than co-resident CTAs: the groups of the persistent kernel walk the pair list (one CTA per pair, several
+    pairs per CTA one after the other); every pair must come out exactly as when it is registered alone."""
+    cam = synth.Camera().scaled(0.1)                      # 64 x 48 = 3072 points per cloud
+    pairs = [synth.make_pair(200 + i, cam=cam) for i in range(12)]
+    srcs = [ctx.upload(p["src"]) for p in pairs]
+    tgts = [ctx.upload(p["tgt"], p["tgt_normals"]) for p in pairs]
+    prm = _abi.icp_params(8)
+    singles = [ctx.register(s, t, None, prm) for s, t in zip(srcs, tgts)]
+    n = 192                                               # > 148 co-resident CTAs, a multiple of 12
+    idx = [i % 12 for i in range(n)]
+    res = ctx.register_batch([srcs[i] for i in idx], [tgts[i] for i in idx], None, prm)
+    assert len(res) == n
+    for k, i in enumerate(idx):
+        assert res[k]["status"] == singles[i]["status"] == 0
+        assert res[k]["inliers"] == singles[i]["inliers"]
+        ok, err = pose_close(res[k]["T"], singles[i]["T"], 1e-9, 1e-9)
+        assert ok, (k, err)
+    for c in srcs + tgts:
+        c.free()
+
+
 def test_batch_mixed_status(ctx, small_cam, small_pair):
     good = small_pair
     bad = synth.make_pair(3, cam=small_cam, scene="S0")
