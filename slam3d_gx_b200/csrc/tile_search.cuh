@@ -9,11 +9,9 @@
 //   * Consecutive source points (a piece of a scan line of an organised cloud) are neighbours in space, so
 //     their search balls overlap.  The warp takes the bounding box (in cell space) of the balls of a group of
 //     pending queries; every row of cells (fixed y,z; contiguous along x in the cell-sorted target) that
-//     crosses the box is ONE contiguous range of float4 points: two cell-start loads per row, then an
-//     asynchronous copy into the warp's tile: per-lane 16-byte cp.async (LDGSTS) by default -- rows are short
-//     (~10 points) and a TMA bulk copy needs warp-uniform operands, so one cp.async.bulk per row costs a
-//     ~10-instruction serialised issue per lane (measured: 13 % of all instructions); -DTS_USE_TMA keeps that
-//     variant (completion counted by the warp's mbarrier) for comparison.
+//     crosses the box is ONE contiguous range of float4 points: two cell-start loads per row, then one TMA
+//     bulk copy (cp.async.bulk, completion counted by the warp's mbarrier) per row into the warp's tile.
+//     (-DTS_USE_CPASYNC: per-lane 16-byte cp.async instead; the two measure the same.)
 //   * The 32 lanes split the tile between them: with n queries in the group, 32/n lanes work on each query
 //     (a lone pending query of a late iteration is served by all 32 lanes), partial results merged by
 //     shuffles.  Shared-memory reads are broadcasts, there is no divergence, ~11 FP32-pipe instructions per
@@ -28,6 +26,11 @@
 //     it to skip the search altogether on later iterations (triangle inequality, see icp.cu).
 #pragma once
 #include <limits.h>
+// Row copies into the tile: TMA bulk copies (cp.async.bulk + mbarrier) by default; -DTS_USE_CPASYNC selects per-lane 16-byte
+// cp.async (LDGSTS) instead.  Measured on the config-2 pair: 1051 us vs 1047 us per 30-iteration registration -- a tie.
+#ifndef TS_USE_CPASYNC
+#define TS_USE_TMA 1
+#endif
 #include "context.h"
 #include "common.cuh"
 #include "grid.cuh"
