@@ -277,7 +277,7 @@ extern "C" int s3d_segment_planes(s3d_ctx *ctx, s3d_cloud *cloud, const s3d_plan
         S3D_LAUNCHED(ctx);
         plane_select_kernel<<<1, 32, 0, st>>>(coefs, valid, counts, n_cand, n_rem, prm->max_iterations, (double)prm->probability, sel);
         S3D_LAUNCHED(ctx);
-        plane_refit_kernel<<<g_wide, PLANE_BLOCK, 0, st>>>(rem, n_rem, prm->distance_threshold, sel, partials);
+        plane_refit_kernel<<<ctx->sm_count, PLANE_BLOCK, 0, st>>>(rem, n_rem, prm->distance_threshold, sel, partials);   // one CTA per SM: the kernel is mostly its reduction
         S3D_LAUNCHED(ctx);
         const int nb = (n_rem + S3D_COMPACT_BLOCK - 1) / S3D_COMPACT_BLOCK;
         KeepPred pred{rem, sel, prm->distance_threshold};
