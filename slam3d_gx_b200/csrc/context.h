@@ -9,7 +9,9 @@
 
 #define S3D_GRID_MAX_CELLS (1u << 23)   // dense cell-start array budget per target (32 MiB)
 #define S3D_GRID_MAX_DIM 2040           // per-axis cap: keeps the float cell coordinate error < 1e-3 cells
+#ifndef S3D_COARSE_STRIDE
 #define S3D_COARSE_STRIDE 16            // the coarse seeding index holds every 16th target point
+#endif
 #define S3D_COARSE_MIN_POINTS 4096      // smaller targets are searched without seeds
 #define S3D_COARSE_MAX_CELLS (1u << 20)
 
