@@ -1,0 +1,22 @@
+"""Scratch driver for compute-sanitizer: a small registration (all search modes), plane extraction, filters."""
+import sys, os
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import slam3d_gx_b200 as s3d
+from slam3d_gx_b200 import synth, _abi
+cam = synth.Camera().scaled(0.25)
+p = synth.make_pair(0, cam=cam, quantize=True, holes=0.1)
+ctx = s3d.Context(0)
+src = ctx.upload(p["src"]); tgt = ctx.upload(p["tgt"], p["tgt_normals"])
+for mode in (_abi.SEARCH_GRID, _abi.SEARCH_GRID_LANE):
+    r = ctx.register(src, tgt, None, _abi.icp_params(8, search=mode, reuse_index=0))
+    print("mode", mode, r["status"], r["inliers"])
+r = ctx.register(src, tgt, None, _abi.icp_params(6, max_corr_dist=0.05, estimator=_abi.ESTIMATOR_SVD))
+print("svd gate", r["status"], r["inliers"])
+res = ctx.register_batch([src] * 5, [tgt] * 5, None, _abi.icp_params(5))
+print("batch", [x["status"] for x in res])
+t2 = ctx.from_depth_normals(p["tgt_depth"], cam, 3.5, 1, 0.08)
+print("planes", len(t2.segment_planes(_abi.plane_params())))
+v = t2.voxel_grid(0.03); z = v.passthrough_z(0.0, 3.0); print("filters", len(v), len(z))
+for c in (src, tgt, t2, v, z): c.free()
+ctx.close()
