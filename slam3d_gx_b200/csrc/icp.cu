@@ -10,14 +10,15 @@
 //                   T <- dT * T
 // Three exact search back ends (bit-identical results, tests/test_gpu_parity.py):
 //   S3D_SEARCH_GRID       (default) icp_persist_kernel: ONE cooperative launch runs every iteration of
-//                         every pair.  A group of CTAs owns a pair; each warp owns 32 consecutive source
-//                         points, finds their exact neighbours in a shared-memory tile gathered from the
-//                         target's grid (tile_search.cuh), accumulates the 29 sums in registers; the CTAs of
-//                         the group exchange one row of 29 doubles through L2, meet at a group barrier, and
-//                         every CTA sums the rows in the same fixed order and solves the 6x6 (or Kabsch)
-//                         in double: no host round trip, no kernel boundary between iterations, and from
-//                         the ~4th iteration on >99% of the queries keep their correspondence by the
-//                         triangle-inequality test, so an iteration is one streaming pass over 52 B/point.
+//                         every pair.  A group of CTAs owns a pair; each warp owns octets of 8 consecutive source
+//                         points.  Per iteration: a decide pass (triangle-inequality skip test, near-tie check,
+//                         else exact search in a TMA-staged shared-memory tile gathered from the target's grid,
+//                         tile_search.cuh) and a call-free accumulate pass (29 double sums in registers); the CTAs
+//                         of the group exchange one row of 29 doubles through L2, meet at a group barrier, and
+//                         every CTA sums the rows in the same fixed order and solves the 6x6 (or Kabsch) in
+//                         double: no host round trip, no kernel boundary between iterations.  From the ~6th
+//                         iteration on >99.9% of the queries keep their correspondence and an iteration is two
+//                         streaming passes over 48 B/point each.
 //   S3D_SEARCH_GRID_LANE  icp_iter_kernel, one launch per iteration, per-lane ball search (search.cuh);
 //                         the last CTA to finish (atomic ticket) solves.  Kept as an independent check.
 //   S3D_SEARCH_BRUTE      all targets streamed through shared memory by TMA bulk copies
