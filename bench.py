@@ -233,24 +233,35 @@ def main():
     plane_prm = _abi.plane_params()
     e2e_prm = _abi.icp_params(ITERS, reuse_index=0)
 
-    def e2e_step(i):
+    # Every step uploads its own two clouds from pinned host memory, extracts the target's planes, registers and reads
+    # the result back.  The upload of step i+1 is issued (s3d_cloud_upload_async, the ctx copy stream) before the compute of
+    # step i, so the copy engine works while the SMs do: one upload per step, all of them inside the timed region.
+    def e2e_upload(i):
         a, b = pin[i % len(pin)]
-        cs = ctx.upload(a.numpy())
-        ct = ctx.upload(b.numpy())
+        return ctx.upload_async(a.numpy()), ctx.upload_async(b.numpy())
+
+    def e2e_compute(cs, ct):
         planes = ct.segment_planes(plane_prm)
         r = ctx.register_batch([cs], [ct], None, e2e_prm, raw=True)[0]
         cs.free(); ct.free()
         return r, planes
 
+    def e2e_run(first, count):
+        nxt = e2e_upload(first)
+        for i in range(count):
+            cs, ct = nxt
+            if i + 1 < count:
+                nxt = e2e_upload(first + i + 1)
+            r, planes = e2e_compute(cs, ct)
+        return r, planes
+
     e2e_steps = max(4, min(args.steps, 16))
-    for i in range(3):
-        e2e_step(i)
+    e2e_run(0, 8)      # warm-up: also lets the index build capture its few launch graphs (one per recurring set of buffers)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     t0 = time.perf_counter()
-    for i in range(e2e_steps):
-        r, planes = e2e_step(3 + i)
+    r, planes = e2e_run(8, e2e_steps)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     assert r.status == 0 and len(planes) == 3
@@ -289,7 +300,7 @@ def main():
                        "pool_pairs_per_gpu": args.pool, "l2": "inputs larger than L2: a pool of %d pairs (>%d MB) rotates" % (args.pool, args.pool * 40),
                        "parallelism": "pairs sharded over %d GPU(s), NCCL all_gather of pose records" % world},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": e2e_steps, "includes": "pinned-host upload of both clouds, RANSAC plane extraction of the target, index build, 30 iterations, result read-back"},
+                    "steps": e2e_steps, "includes": "pinned-host upload of both clouds (step i+1's copy overlaps step i's compute), RANSAC plane extraction of the target, index build, 30 iterations, result read-back"},
             "gpu_launches": total_launches,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

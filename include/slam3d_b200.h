@@ -134,6 +134,14 @@ int64_t s3d_launch_count(const s3d_ctx *ctx);
 
 /* host xyz, stride in floats between points (>=3; 4 for PCD "x y z rgba" rows) */
 int  s3d_cloud_upload(s3d_ctx *ctx, const float *xyz, int stride_floats, int n, s3d_cloud **out);
+/* The same upload without waiting for it: the copy runs on a second stream of the ctx, so the copy engine moves the
+ * NEXT frame while the SMs register the current one (the reference loads frame k+1 only after frame k is done,
+ * src/GraphicEnd.cpp:266-281 from run():150-160).  xyz must stay valid and unchanged until the cloud has been used by
+ * another call of this ABI or s3d_cloud_wait returned; page-locked memory is needed for a truly asynchronous copy.
+ * Every other entry point orders itself behind the upload; nothing else changes for the caller. */
+int  s3d_cloud_upload_async(s3d_ctx *ctx, const float *xyz, int stride_floats, int n, s3d_cloud **out);
+/* block the host until the cloud's asynchronous upload has finished (no-op for other clouds) */
+int  s3d_cloud_wait(s3d_ctx *ctx, const s3d_cloud *cloud);
 /* device-resident float4 array (x,y,z,ignored); copied device-to-device */
 int  s3d_cloud_from_device(s3d_ctx *ctx, const void *d_xyzw, int n, s3d_cloud **out);
 /* depth image -> cloud: non-zero pixels, row-major, x=(u-cx)z/fx, y=(v-cy)z/fy, z=d/factor

@@ -33,7 +33,7 @@ EXPORTS = [
     "s3d_cloud_drop_index", "s3d_cloud_free", "s3d_segment_planes", "s3d_register_batch", "s3d_register_pair",
     "s3d_last_correspondences", "s3d_last_timing", "s3d_icp_params_default", "s3d_plane_params_default",
     "s3d_planar_keypoints", "s3d_gather_results", "s3d_cloud_passthrough_z", "s3d_cloud_voxel_grid", "s3d_cloud_transform",
-    "s3d_cloud_concat", "s3d_map_fuse", "s3d_cloud_from_depth_normals",
+    "s3d_cloud_concat", "s3d_map_fuse", "s3d_cloud_from_depth_normals", "s3d_cloud_upload_async", "s3d_cloud_wait",
 ]
 
 
@@ -59,6 +59,8 @@ def load_library():
     lib.s3d_launch_count.argtypes = [vp]
     lib.s3d_launch_count.restype = C.c_int64
     lib.s3d_cloud_upload.argtypes = [vp, vp, ci, ci, C.POINTER(vp)]
+    lib.s3d_cloud_upload_async.argtypes = [vp, vp, ci, ci, C.POINTER(vp)]
+    lib.s3d_cloud_wait.argtypes = [vp, vp]
     lib.s3d_cloud_from_device.argtypes = [vp, vp, ci, C.POINTER(vp)]
     lib.s3d_cloud_from_depth.argtypes = [vp, vp, ci, ci, C.POINTER(_abi.CameraC), C.c_float, C.POINTER(vp)]
     lib.s3d_cloud_set_normals.argtypes = [vp, vp, vp, ci, ci]
@@ -103,6 +105,10 @@ class Cloud:
     @property
     def has_normals(self) -> bool:
         return bool(self.ctx.lib.s3d_cloud_has_normals(self.handle))
+
+    def wait(self):
+        """Block until an asynchronous upload of this cloud has finished."""
+        self.ctx._check(self.ctx.lib.s3d_cloud_wait(self.ctx.h, self.handle))
 
     def set_normals(self, normals: np.ndarray):
         a = np.ascontiguousarray(normals, dtype=np.float32)
@@ -205,6 +211,17 @@ class Context:
         c = Cloud(self, h)
         if normals is not None:
             c.set_normals(normals)
+        return c
+
+    def upload_async(self, xyz: np.ndarray) -> Cloud:
+        """Upload on the context's copy stream without waiting (s3d_cloud_upload_async): the next frame crosses PCIe while
+        the current one is registered.  `xyz` must be float32, C-contiguous (ideally page-locked) and is kept alive by
+        the returned Cloud; do not modify it before the cloud has been used or `wait()`ed for."""
+        assert xyz.dtype == np.float32 and xyz.ndim == 2 and xyz.shape[1] >= 3 and xyz.flags["C_CONTIGUOUS"]
+        h = C.c_void_p()
+        self._check(self.lib.s3d_cloud_upload_async(self.h, xyz.ctypes.data, xyz.shape[1], xyz.shape[0], C.byref(h)))
+        c = Cloud(self, h)
+        c._host = xyz
         return c
 
     def from_device(self, dptr: int, n: int) -> Cloud:

@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstring>
 #include <cmath>
+#include <iterator>
 #include "context.h"
 #include "compact.cuh"
 
@@ -46,6 +47,10 @@ cudaError_t s3d_dev_alloc(s3d_ctx *ctx, void **out, size_t bytes)
     const size_t want = pool_round(bytes);
     auto it = ctx->pool_free.lower_bound(want);
     if (it != ctx->pool_free.end() && it->first <= want + want / 4) {
+        // last in, first out among blocks of one size: a caller that repeats the same sequence of uploads, registrations
+        // and frees per frame (also with the next frame's upload in flight) then sees the same few sets of addresses
+        // again and again, which is what lets the index build replay its captured graphs (grid.cu)
+        it = std::prev(ctx->pool_free.upper_bound(it->first));
         *out = it->second;
         ctx->pool_live[it->second] = it->first;
         ctx->pool_cached -= it->first;
@@ -125,6 +130,7 @@ extern "C" void s3d_destroy(s3d_ctx *ctx)
     ctx->pool_live.clear();
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     for (int i = 0; i < 4; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); cudaEventDestroy(ctx->copy_fence); }
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
@@ -199,6 +205,67 @@ extern "C" int s3d_cloud_upload(s3d_ctx *ctx, const float *xyz, int stride_float
         S3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     }
     *out = c;
+    return S3D_OK;
+}
+
+int s3d_cloud_ready(s3d_ctx *ctx, const s3d_cloud *cloud)
+{
+    if (!cloud || !cloud->ready) return S3D_OK;
+    S3D_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, cloud->ready, 0));
+    if (cloud->unpacked_stride) {
+        const float *rows = cloud->d_stage ? cloud->d_stage : (const float *)cloud->d_pts;
+        pack_xyz_kernel<<<(cloud->n + 255) / 256, 256, 0, ctx->stream>>>(rows, cloud->unpacked_stride, cloud->n, cloud->d_pts);
+        S3D_LAUNCHED(ctx);
+        cloud->unpacked_stride = 0;
+    }
+    return S3D_OK;
+}
+
+// Same result as s3d_cloud_upload, but the copy runs on the ctx copy stream and the call returns at once: the copy
+// engine moves frame k+1 while the SMs register frame k (the registration kernel occupies every SM, a DMA transfer
+// needs none).  Only copies go to the copy stream: a kernel there would queue behind the registration kernel and hold
+// back the copies after it, so the float4 packing of the rows is left to the first use of the cloud, on the ctx stream.
+// Truly asynchronous only from page-locked host memory; from pageable memory the driver stages the copy and the call is
+// merely correct.
+extern "C" int s3d_cloud_upload_async(s3d_ctx *ctx, const float *xyz, int stride_floats, int n, s3d_cloud **out)
+{
+    if (!ctx || !out || n < 0 || stride_floats < 3 || (n > 0 && !xyz)) return s3d_fail(ctx, S3D_E_ARG, "s3d_cloud_upload_async: bad argument");
+    cudaSetDevice(ctx->device);
+    if (!ctx->copy_stream) {
+        S3D_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        S3D_CUDA(ctx, cudaEventCreateWithFlags(&ctx->copy_fence, cudaEventDisableTiming));
+    }
+    s3d_cloud *c = nullptr;
+    int rc = cloud_alloc(ctx, n, &c);
+    if (rc) return rc;
+    // Blocks of the pool were last used on the ctx stream: the copy starts behind whatever that stream has been given
+    // so far (nothing, when the caller pipelines frame k+1 behind a finished frame k-1).
+    rc = [&]() -> int {
+        S3D_CUDA(ctx, cudaEventRecord(ctx->copy_fence, ctx->stream));
+        S3D_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_fence, 0));
+        S3D_CUDA(ctx, cudaEventCreateWithFlags(&c->ready, cudaEventDisableTiming));
+        if (n > 0) {
+            const size_t bytes = sizeof(float) * (size_t)n * stride_floats;
+            void *dst = c->d_pts;
+            if (stride_floats != 4) {
+                S3D_CUDA(ctx, s3d_dev_alloc_t(ctx, &c->d_stage, bytes));
+                dst = c->d_stage;
+            }
+            S3D_CUDA(ctx, cudaMemcpyAsync(dst, xyz, bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+            c->unpacked_stride = stride_floats;
+        }
+        S3D_CUDA(ctx, cudaEventRecord(c->ready, ctx->copy_stream));
+        return S3D_OK;
+    }();
+    if (rc) { s3d_cloud_free(ctx, c); return rc; }
+    *out = c;
+    return S3D_OK;
+}
+
+extern "C" int s3d_cloud_wait(s3d_ctx *ctx, const s3d_cloud *cloud)
+{
+    if (!ctx || !cloud) return s3d_fail(ctx, S3D_E_ARG, "s3d_cloud_wait: bad argument");
+    if (cloud->ready) S3D_CUDA(ctx, cudaEventSynchronize(cloud->ready));
     return S3D_OK;
 }
 
@@ -290,7 +357,9 @@ extern "C" int s3d_cloud_set_normals(s3d_ctx *ctx, s3d_cloud *cloud, const float
 {
     if (!ctx || !cloud || !nrm || stride_floats < 3 || n != cloud->n) return s3d_fail(ctx, S3D_E_ARG, "s3d_cloud_set_normals: bad argument");
     cudaSetDevice(ctx->device);
-    int rc = ensure_normals(ctx, cloud);
+    int rc = s3d_cloud_ready(ctx, cloud);
+    if (rc) return rc;
+    rc = ensure_normals(ctx, cloud);
     if (rc) return rc;
     if (n > 0) {
         float *tmp = nullptr;
@@ -310,7 +379,9 @@ extern "C" int s3d_cloud_set_normals_device(s3d_ctx *ctx, s3d_cloud *cloud, cons
 {
     if (!ctx || !cloud || !d_nrm || n != cloud->n) return s3d_fail(ctx, S3D_E_ARG, "s3d_cloud_set_normals_device: bad argument");
     cudaSetDevice(ctx->device);
-    int rc = ensure_normals(ctx, cloud);
+    int rc = s3d_cloud_ready(ctx, cloud);
+    if (rc) return rc;
+    rc = ensure_normals(ctx, cloud);
     if (rc) return rc;
     if (n > 0) {
         pack_normals_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>((const float *)d_nrm, 4, n, cloud->d_nrm);
@@ -329,6 +400,7 @@ extern "C" int s3d_cloud_download(s3d_ctx *ctx, const s3d_cloud *cloud, float *x
     cudaSetDevice(ctx->device);
     int n = cloud->n;
     if (n == 0) return S3D_OK;
+    { int rc = s3d_cloud_ready(ctx, cloud); if (rc) return rc; }
     std::vector<float4> tmp((size_t)n);
     if (xyz) {
         S3D_CUDA(ctx, cudaMemcpyAsync(tmp.data(), cloud->d_pts, sizeof(float4) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
@@ -361,6 +433,8 @@ extern "C" void s3d_cloud_free(s3d_ctx *ctx, s3d_cloud *cloud)
     if (!cloud) return;
     if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
     if (!ctx) { delete cloud; return; }     // cannot return device memory without its context (leak rather than crash)
+    if (cloud->ready) { cudaEventSynchronize(cloud->ready); cudaEventDestroy(cloud->ready); }   // an upload may still be writing it
+    s3d_dev_free(ctx, cloud->d_stage);
     s3d_grid_free(ctx, cloud->grid);
     s3d_grid_free(ctx, cloud->coarse);
     s3d_dev_free(ctx, cloud->d_coarse_pts);

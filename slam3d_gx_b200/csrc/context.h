@@ -51,6 +51,11 @@ struct s3d_cloud {
     GridIndex grid;               // all points: the exact search index
     GridIndex coarse;             // every 16th point: first-iteration seeds
     float4 *d_coarse_pts = nullptr; int cap_coarse_pts = 0;
+    // asynchronous upload (s3d_cloud_upload_async): recorded on the ctx copy stream behind the host-to-device copy;
+    // every entry point that touches the cloud orders the ctx stream behind it first (s3d_cloud_ready)
+    cudaEvent_t ready = nullptr;
+    float *d_stage = nullptr;     // rows as the host holds them (stride != 4), until the cloud is freed
+    mutable int unpacked_stride = 0;   // != 0: the rows still have to be packed into float4 (x,y,z,1), on the ctx stream, at first use
 };
 
 // one registration unit as the kernels see it
@@ -78,6 +83,8 @@ struct s3d_ctx {
     int sm_count = 0;
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;   // uploads of the NEXT frame while the ctx stream registers the current one
+    cudaEvent_t copy_fence = nullptr;     // orders the copy stream behind what the ctx stream has been given so far
     std::string err;
     int64_t launches = 0;
     // batch scratch (grown on demand)
@@ -118,6 +125,8 @@ cudaError_t s3d_dev_alloc(s3d_ctx *ctx, void **out, size_t bytes);
 void s3d_dev_free(s3d_ctx *ctx, void *p);
 void s3d_dev_pool_release(s3d_ctx *ctx);
 template <typename T> static inline cudaError_t s3d_dev_alloc_t(s3d_ctx *ctx, T **out, size_t bytes) { return s3d_dev_alloc(ctx, reinterpret_cast<void **>(out), bytes); }
+// cloud.cu: orders the ctx stream behind a cloud's asynchronous upload and packs its rows (no-op for every other cloud)
+int s3d_cloud_ready(s3d_ctx *ctx, const s3d_cloud *cloud);
 // grid.cu
 int s3d_grid_build(s3d_ctx *ctx, s3d_cloud *cloud, float cell);
 void s3d_grid_free(s3d_ctx *ctx, GridIndex &g);

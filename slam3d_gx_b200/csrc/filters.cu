@@ -74,6 +74,7 @@ extern "C" int s3d_cloud_passthrough_z(s3d_ctx *ctx, const s3d_cloud *cloud, flo
 {
     if (!ctx || !cloud || !out) return s3d_fail(ctx, S3D_E_ARG, "s3d_cloud_passthrough_z: bad argument");
     cudaSetDevice(ctx->device);
+    { int rc = s3d_cloud_ready(ctx, cloud); if (rc) return rc; }
     return compact_cloud(ctx, cloud, ZPred{cloud->d_pts, z_min, z_max}, out);
 }
 
@@ -176,6 +177,7 @@ extern "C" int s3d_cloud_voxel_grid(s3d_ctx *ctx, const s3d_cloud *cloud, float 
     cudaSetDevice(ctx->device);
     const int n = cloud->n;
     if (n == 0) return cloud_new(ctx, 0, out);
+    { int rc = s3d_cloud_ready(ctx, cloud); if (rc) return rc; }
     cudaStream_t st = ctx->stream;
     const int nblocks = (n + S3D_COMPACT_BLOCK - 1) / S3D_COMPACT_BLOCK;
     uint32_t *d_bbox = nullptr, *d_keys = nullptr, *d_vals = nullptr, *d_keys2 = nullptr, *d_vals2 = nullptr, *d_counts = nullptr, *d_seg = nullptr;
@@ -251,7 +253,9 @@ extern "C" int s3d_cloud_transform(s3d_ctx *ctx, const s3d_cloud *cloud, const d
     if (!ctx || !cloud || !T16 || !out) return s3d_fail(ctx, S3D_E_ARG, "s3d_cloud_transform: bad argument");
     cudaSetDevice(ctx->device);
     s3d_cloud *c = nullptr;
-    int rc = cloud_new(ctx, cloud->n, &c);
+    int rc = s3d_cloud_ready(ctx, cloud);
+    if (rc) return rc;
+    rc = cloud_new(ctx, cloud->n, &c);
     if (rc) return rc;
     Pose12f T;
     for (int k = 0; k < 12; ++k) T.m[k] = (float)T16[k];
@@ -276,6 +280,7 @@ extern "C" int s3d_cloud_concat(s3d_ctx *ctx, const s3d_cloud *const *clouds, in
     size_t off = 0;
     for (int i = 0; i < n_clouds; ++i) {
         if (clouds[i]->n == 0) continue;
+        if ((rc = s3d_cloud_ready(ctx, clouds[i])) != S3D_OK) { s3d_cloud_free(ctx, c); return rc; }
         S3D_CUDA(ctx, cudaMemcpyAsync(c->d_pts + off, clouds[i]->d_pts, sizeof(float4) * (size_t)clouds[i]->n, cudaMemcpyDeviceToDevice, ctx->stream));
         off += (size_t)clouds[i]->n;
     }

@@ -603,6 +603,9 @@ struct PersistArgs {
     float first_cells;           // first-guess search radius of the first iteration when the decimated index is not used, in cells
     int use_coarse;              // first iteration: bound the search with the nearest point of the decimated index
     float slack_cells;           // extra search radius beyond the seed distance, in cells: buys the skip test its margin
+    int dyn_octets;              // octets handed out at a time (1, 2 or 4: one per 8 lanes of the taking warp)
+    int dyn_div;                 // octets are handed out dynamically while more than 1/dyn_div of a CTA's queries needed a search
+                                 // in its previous iteration (0: always the fixed assignment)
 };
 
 __device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned *p)      // polling load: no L1 invalidate per poll
@@ -643,6 +646,9 @@ __global__ void __launch_bounds__(TS_BLOCK, 1) icp_persist_kernel(const PersistA
     __shared__ double wsum[TS_WARPS][S3D_NACC];
     __shared__ double tail[TS_WARPS][S3D_NACC];
     __shared__ TileCfg cfg[2];                                    // search levels of the current pair: [0] decimated grid, [1] full grid
+    __shared__ int dyn_next;                                      // dynamic decide pass: next octet of this CTA to hand out
+    __shared__ float4 dyn_pre[TS_WARPS][96];                      // ... and the state of each warp's NEXT item (32 x point, correspondence, search state)
+    __shared__ int n_pending, n_pending_prev;                     // queries of this CTA that needed a search: this / the previous iteration
 #ifdef TS_USE_TMA
     __shared__ __align__(8) uint64_t tile_bar[TS_WARPS];         // one mbarrier per warp: completion of its TMA row copies
 #endif
@@ -669,6 +675,7 @@ __global__ void __launch_bounds__(TS_BLOCK, 1) icp_persist_kernel(const PersistA
         __syncthreads();
         if (threadIdx.x == 0) {
             st = a.states[pair];
+            dyn_next = 0; n_pending = 0; n_pending_prev = 0;
             cfg[1].gp = *d.grid; cfg[1].cell_start = d.cell_start; cfg[1].pts = d.sorted_pts;
             cfg[1].slack = a.slack_cells * cfg[1].gp.cell; cfg[1].gate_r = gate_r;
             cfg[0] = cfg[1];
@@ -724,9 +731,55 @@ __global__ void __launch_bounds__(TS_BLOCK, 1) icp_persist_kernel(const PersistA
             // (nearly every query keeps its correspondence) exposes two memory latencies in all.  A search uses the tile
             // itself, so what was staged beyond the current chunk is staged again afterwards (then only one chunk ahead: in
             // the first iterations every chunk searches).
+            // While most queries still need a search (the first iterations) the cost of an octet varies several-fold with
+            // depth and surface orientation, and a fixed assignment leaves warps waiting for the slowest one of their CTA
+            // (and CTAs for the slowest CTA): 32 % of the warp time of the first build of this kernel.  In those iterations
+            // (`dyn`, decided per CTA from its own count of the previous iteration) the CTA's octets are handed out one
+            // at a time from a shared-memory counter, lanes 0..7 of the taking warp hold the queries and all 32 lanes
+            // search for them.  The per-query state lives in global memory and an octet always belongs to the same CTA, so
+            // who decides it changes nothing in what is found.
+            const int cta_units = rank < nunits ? (nunits - rank + a.group_ctas - 1) / a.group_ctas : 0;      // octets rank, rank + group_ctas, ...
+            const bool dyn = !same_pose && a.dyn_div > 0 && (it == 0 || (long long)n_pending_prev * a.dyn_div > (long long)cta_units * 8);
+            int npend = 0, dyn_m = 0;
+            const uint32_t spre = ts_smem_u32(&dyn_pre[warp][0]) + 16u * (uint32_t)lane;
+            // an item = a.dyn_octets (1, 2 or 4) consecutive octets of this CTA, one per 8 lanes
+            auto dyn_take_and_stage = [&]() -> int {
+                int m = 0;
+                if (lane == 0) m = atomicAdd(&dyn_next, a.dyn_octets);
+                m = __shfl_sync(full, m, 0);
+                const int mo = m + (lane >> 3);
+                const int is = ((rank + a.group_ctas * mo) << 3) + (lane & 7);
+                if (mo < cta_units && lane < 8 * a.dyn_octets && is < d.n_src) {
+                    ts_cp_async16_s(spre, &d.src[is]);
+                    if (it > 0) {
+                        ts_cp_async16_s(spre + 512u, &my_cq[is]);
+                        ts_cp_async16_s(spre + 1024u, &my_xl[is]);
+                    }
+                }
+                return m;
+            };
             const uint32_t sbuf = ts_smem_u32(buf);
             int staged_hi = 0, stage_lo = 0, stage_depth = TS_STAGE;
-            for (int kc = 0; wslot + W * 4 * kc < nunits; ++kc) {          // warp-uniform: the chunk's first octet exists
+            for (int kc = 0; dyn || wslot + W * 4 * kc < nunits; ++kc) {   // warp-uniform: the chunk's first octet exists
+                int u, i; bool in;
+                float4 p, q_old, xl;
+                if (dyn) {
+                    // the octet worked on now was staged while the previous one was searched; the next one is taken and
+                    // staged (cp.async: no registers held across the search call) before this one is worked on
+                    if (kc == 0) dyn_m = dyn_take_and_stage();
+                    const int m = dyn_m;
+                    if (m >= cta_units) break;
+                    ts_cp_async_wait_all();
+                    u = rank + a.group_ctas * (m + (lane >> 3)); i = (u << 3) + (lane & 7);
+                    in = m + (lane >> 3) < cta_units && lane < 8 * a.dyn_octets && i < d.n_src;
+                    p = q_old = xl = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (in) {
+                        p = ts_lds128(spre);
+                        if (it > 0) { q_old = ts_lds128(spre + 512u); xl = ts_lds128(spre + 1024u); }
+                    }
+                    __syncwarp();
+                    dyn_m = dyn_take_and_stage();
+                } else {
                 if (kc >= staged_hi) {
                     stage_lo = kc;
                     staged_hi = kc + stage_depth;
@@ -743,10 +796,11 @@ __global__ void __launch_bounds__(TS_BLOCK, 1) icp_persist_kernel(const PersistA
                     }
                     ts_cp_async_wait_all();
                 }
-                const int u = CHUNK_UNIT(kc), i = (u << 3) + (lane & 7);
-                const bool in = u < nunits && i < d.n_src;
+                u = CHUNK_UNIT(kc); i = (u << 3) + (lane & 7);
+                in = u < nunits && i < d.n_src;
                 const uint32_t sl = sbuf + 16u * (uint32_t)((kc - stage_lo) * 128 + lane);
-                const float4 p = ts_lds128(sl), q_old = ts_lds128(sl + 512u), xl = ts_lds128(sl + 1024u);
+                p = ts_lds128(sl); q_old = ts_lds128(sl + 512u); xl = ts_lds128(sl + 1024u);
+                }
                 float3 x = make_float3(0.f, 0.f, 0.f);
                 float4 q = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
                 float d2q = INFINITY, r = a.first_cells * cell;
@@ -785,7 +839,9 @@ __global__ void __launch_bounds__(TS_BLOCK, 1) icp_persist_kernel(const PersistA
                         }
                     }
                 }
-                if (__any_sync(full, pending)) {
+                const unsigned pendmask = __ballot_sync(full, pending);
+                npend += __popc(pendmask);
+                if (pendmask) {
                     staged_hi = kc + 1; stage_depth = 1;        // the search uses the tile: stage the next chunk afresh
 #if defined(S3D_STATS) || defined(S3D_PHASES)
                     const long long s_t0 = clock64();
@@ -816,6 +872,10 @@ __global__ void __launch_bounds__(TS_BLOCK, 1) icp_persist_kernel(const PersistA
 #endif
                 }
             }
+
+            if (lane == 0 && npend) atomicAdd(&n_pending, npend);
+            // the accumulate pass keeps the fixed assignment: after a dynamic decide pass it reads what other warps of the CTA wrote
+            if (dyn) __syncthreads();
 
             // ---- accumulate pass ----
             double acc[29];
@@ -888,6 +948,7 @@ __global__ void __launch_bounds__(TS_BLOCK, 1) icp_persist_kernel(const PersistA
                 for (int w = 0; w < TS_WARPS; ++w) s += wsum[w][threadIdx.x];
                 __stcg(&rows[(size_t)rank * S3D_NACC + threadIdx.x], s);
             }
+            if (threadIdx.x == 32) { n_pending_prev = n_pending; n_pending = 0; dyn_next = 0; }     // every warp is past its decide pass
             // group barrier (all CTAs are co-resident: cooperative launch)
             ++epoch;
             __syncthreads();
@@ -1006,6 +1067,9 @@ extern "C" int s3d_register_batch(s3d_ctx *ctx, const s3d_cloud *const *src, con
         if (!src[i] || !tgt[i]) return s3d_fail(ctx, S3D_E_ARG, "null cloud in batch");
         if (plane && !tgt[i]->d_nrm) return s3d_fail(ctx, S3D_E_STATE, "point-to-plane needs target normals: call s3d_segment_planes or s3d_cloud_set_normals on the target first");
         n_max = std::max(n_max, src[i]->n);
+        int rc = s3d_cloud_ready(ctx, src[i]);
+        if (rc == S3D_OK) rc = s3d_cloud_ready(ctx, tgt[i]);
+        if (rc) return rc;
     }
     const int64_t launches0 = ctx->launches;
     // launch geometry: every CTA of the launch is resident at once (ICP_MIN_BLOCKS per SM), and a lone pair is
@@ -1124,6 +1188,8 @@ extern "C" int s3d_register_batch(s3d_ctx *ctx, const s3d_cloud *const *src, con
         { static const char *e = getenv("S3D_FIRST_CELLS"); pa.first_cells = e ? (float)atof(e) : 1.5f; }
         { static const char *e = getenv("S3D_USE_COARSE"); pa.use_coarse = e ? atoi(e) : 1; }
         { static const char *e = getenv("S3D_SLACK_CELLS"); pa.slack_cells = e ? (float)atof(e) : 0.08f; }
+        { static const char *e = getenv("S3D_DYN_DIV"); pa.dyn_div = e ? atoi(e) : 8; }
+        { static const char *e = getenv("S3D_DYN_OCTETS"); const int v = e ? atoi(e) : 2; pa.dyn_octets = v >= 4 ? 4 : v >= 2 ? 2 : 1; }
         void *kargs[] = {&pa};
         const void *fn = plane ? (const void *)icp_persist_kernel<S3D_ESTIMATOR_POINT_TO_PLANE> : (const void *)icp_persist_kernel<S3D_ESTIMATOR_SVD>;
         S3D_CUDA(ctx, cudaLaunchCooperativeKernel(fn, dim3(p_groups * p_group_ctas), dim3(TS_BLOCK), kargs, p_smem, ctx->stream));

@@ -235,6 +235,7 @@ extern "C" int s3d_segment_planes(s3d_ctx *ctx, s3d_cloud *cloud, const s3d_plan
         return s3d_fail(ctx, S3D_E_ARG, "s3d_segment_planes: parameter out of range");
     cudaSetDevice(ctx->device);
     *n_planes_out = 0;
+    { int rc = s3d_cloud_ready(ctx, cloud); if (rc) return rc; }
     const int n = cloud->n;
     const size_t np = (size_t)(n > 0 ? n : 1);
     if (!cloud->d_nrm) S3D_CUDA(ctx, s3d_dev_alloc_t(ctx, &cloud->d_nrm, sizeof(float4) * np));

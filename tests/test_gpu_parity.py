@@ -36,6 +36,41 @@ def test_correspondences_bit_exact(ctx, small_pair, search):
     assert abs(r["fitness"] - o["fitness"]) <= 1e-6 * o["fitness"]
 
 
+@pytest.mark.parametrize("stride", [3, 4])
+def test_async_upload_pipeline_matches_blocking_upload(ctx, small_pair, stride):
+    """s3d_cloud_upload_async: frame k+1 is uploaded on the copy stream while frame k is registered; every result is
+    bitwise the one of the blocking upload (correspondences, pose, downloaded points)."""
+    import torch
+    p = small_pair
+    prm = _abi.icp_params(6)
+    ref, ref_nn = _gpu_icp(ctx, p, prm)
+
+    def rows(a):
+        out = np.zeros((len(a), stride), np.float32)
+        out[:, :3] = a[:, :3]
+        if stride == 4:
+            out[:, 3] = 123.0      # PCD rgba column: ignored
+        return torch.from_numpy(out).pin_memory().numpy()
+
+    hs, ht = rows(p["src"]), rows(p["tgt"])
+    nxt = (ctx.upload_async(hs), ctx.upload_async(ht))
+    for k in range(3):
+        cs, ct = nxt
+        if k < 2:
+            nxt = (ctx.upload_async(hs), ctx.upload_async(ht))      # in flight during the registration below
+        if k == 0:
+            assert np.array_equal(cs.download()["xyz"], p["src"][:, :3])
+        ct.set_normals(p["tgt_normals"])
+        r = ctx.register(cs, ct, None, prm)
+        nn = ctx.last_correspondences(len(p["src"]))
+        cs.free(); ct.free()
+        assert np.array_equal(nn, ref_nn)
+        assert np.array_equal(r["T"], ref["T"]) and r["inliers"] == ref["inliers"]
+    c = ctx.upload_async(hs)
+    c.wait()
+    c.free()                                                       # freed without ever being used
+
+
 @pytest.mark.parametrize("cell", [0.0, 0.005, 0.05, 0.5, 5.0])
 def test_grid_search_exact_for_any_cell_size(ctx, small_pair, cell):
     """Exactness must not depend on the grid resolution (ring expansion / clamping)."""
