@@ -18,7 +18,7 @@ for seed in (0, 5):
             r = ctx.register(src, tgt, None, prm)
             ts.append(ctx.last_timing()["iterate_ms"])
         nn = ctx.last_correspondences(len(p["src"]))
-        h = hashlib.sha1(nn.tobytes() + np.asarray(r["T"]).tobytes()).hexdigest()[:10]
+        h = hashlib.sha1(nn.tobytes()).hexdigest()[:6] + "." + hashlib.sha1(np.asarray(r["T"]).tobytes()).hexdigest()[:4]
         out.append(f"{k}:{np.median(ts[2:])*1e3:.0f}us/{h}")
     src.free(); tgt.free()
-print("DYN_DIV=%s " % os.environ.get("S3D_DYN_DIV", "default") + " ".join(out), flush=True)
+print("DYN_DIV=%s FUSED_DIV=%s " % (os.environ.get("S3D_DYN_DIV", "default"), os.environ.get("S3D_FUSED_DIV", "default")) + " ".join(out), flush=True)
