@@ -23,6 +23,7 @@
 #ifndef SLAM3D_B200_H
 #define SLAM3D_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -142,6 +143,9 @@ int  s3d_cloud_upload(s3d_ctx *ctx, const float *xyz, int stride_floats, int n, 
 int  s3d_cloud_upload_async(s3d_ctx *ctx, const float *xyz, int stride_floats, int n, s3d_cloud **out);
 /* block the host until the cloud's asynchronous upload has finished (no-op for other clouds) */
 int  s3d_cloud_wait(s3d_ctx *ctx, const s3d_cloud *cloud);
+/* page-locked host memory for the buffers handed to s3d_cloud_upload_async (a C/C++ host needs no CUDA headers) */
+int  s3d_host_alloc(s3d_ctx *ctx, size_t bytes, void **out);
+void s3d_host_free(s3d_ctx *ctx, void *p);
 /* device-resident float4 array (x,y,z,ignored); copied device-to-device */
 int  s3d_cloud_from_device(s3d_ctx *ctx, const void *d_xyzw, int n, s3d_cloud **out);
 /* depth image -> cloud: non-zero pixels, row-major, x=(u-cx)z/fx, y=(v-cy)z/fy, z=d/factor

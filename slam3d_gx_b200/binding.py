@@ -33,7 +33,7 @@ EXPORTS = [
     "s3d_cloud_drop_index", "s3d_cloud_free", "s3d_segment_planes", "s3d_register_batch", "s3d_register_pair",
     "s3d_last_correspondences", "s3d_last_timing", "s3d_icp_params_default", "s3d_plane_params_default",
     "s3d_planar_keypoints", "s3d_gather_results", "s3d_cloud_passthrough_z", "s3d_cloud_voxel_grid", "s3d_cloud_transform",
-    "s3d_cloud_concat", "s3d_map_fuse", "s3d_cloud_from_depth_normals", "s3d_cloud_upload_async", "s3d_cloud_wait",
+    "s3d_cloud_concat", "s3d_map_fuse", "s3d_cloud_from_depth_normals", "s3d_cloud_upload_async", "s3d_cloud_wait", "s3d_host_alloc", "s3d_host_free",
 ]
 
 
@@ -61,6 +61,9 @@ def load_library():
     lib.s3d_cloud_upload.argtypes = [vp, vp, ci, ci, C.POINTER(vp)]
     lib.s3d_cloud_upload_async.argtypes = [vp, vp, ci, ci, C.POINTER(vp)]
     lib.s3d_cloud_wait.argtypes = [vp, vp]
+    lib.s3d_host_alloc.argtypes = [vp, C.c_size_t, C.POINTER(vp)]
+    lib.s3d_host_free.argtypes = [vp, vp]
+    lib.s3d_host_free.restype = None
     lib.s3d_cloud_from_device.argtypes = [vp, vp, ci, C.POINTER(vp)]
     lib.s3d_cloud_from_depth.argtypes = [vp, vp, ci, ci, C.POINTER(_abi.CameraC), C.c_float, C.POINTER(vp)]
     lib.s3d_cloud_set_normals.argtypes = [vp, vp, vp, ci, ci]

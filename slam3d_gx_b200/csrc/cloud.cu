@@ -269,6 +269,21 @@ extern "C" int s3d_cloud_wait(s3d_ctx *ctx, const s3d_cloud *cloud)
     return S3D_OK;
 }
 
+extern "C" int s3d_host_alloc(s3d_ctx *ctx, size_t bytes, void **out)
+{
+    if (!ctx || !out) return s3d_fail(ctx, S3D_E_ARG, "s3d_host_alloc: bad argument");
+    cudaSetDevice(ctx->device);
+    *out = nullptr;
+    S3D_CUDA(ctx, cudaMallocHost(out, bytes > 0 ? bytes : 1));
+    return S3D_OK;
+}
+
+extern "C" void s3d_host_free(s3d_ctx *ctx, void *p)
+{
+    if (ctx) cudaSetDevice(ctx->device);
+    if (p) cudaFreeHost(p);
+}
+
 extern "C" int s3d_cloud_from_device(s3d_ctx *ctx, const void *d_xyzw, int n, s3d_cloud **out)
 {
     if (!ctx || !out || n < 0 || (n > 0 && !d_xyzw)) return s3d_fail(ctx, S3D_E_ARG, "s3d_cloud_from_device: bad argument");

@@ -2,6 +2,8 @@
 // references below point at the statement being mirrored.
 #include "GraphicEnd.h"
 #include "PCD.h"
+#include <cstring>
+#include <fstream>
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
@@ -13,7 +15,8 @@ using namespace std;
 #define S3D_CHECK(call) do { int rc__ = (call); if (rc__ != S3D_OK) { cerr << BOLDRED << "slam3d_b200: " #call " failed (" << rc__ << "): " \
     << s3d_last_error(_ctx) << RESET << endl; exit(1); } } while (0)
 
-GraphicEnd::GraphicEnd() : _pSLAMEnd(0), _currCloud(0), _lost(0), _index(0), _moreLoops(0), _ctx(0), _have_guess(false), _use_guess(false)
+GraphicEnd::GraphicEnd() : _pSLAMEnd(0), _currCloud(0), _lost(0), _index(0), _moreLoops(0), _ctx(0), _nextRaw(0), _nextIndex(-1), _pinned(0), _pinnedFloats(0),
+                           _have_guess(false), _use_guess(false)
 {
     g_pParaReader = new ParameterReader(parameter_file_addr);                       // :62
     int seed = atoi(g_pParaReader->GetPara("random_seed").c_str());
@@ -28,6 +31,8 @@ GraphicEnd::GraphicEnd() : _pSLAMEnd(0), _currCloud(0), _lost(0), _index(0), _mo
 GraphicEnd::~GraphicEnd()
 {
     for (size_t i = 0; i < _clouds.size(); ++i) s3d_cloud_free(_ctx, _clouds[i]);
+    if (_nextRaw) s3d_cloud_free(_ctx, _nextRaw);
+    s3d_host_free(_ctx, _pinned);
     s3d_destroy(_ctx);
     delete g_pParaReader;
     g_pParaReader = 0;
@@ -153,14 +158,20 @@ int GraphicEnd::readimage()
     cout << "loading image " << _index << endl;
     ss.str(""); ss.clear();
     ss << _pclPath << _index << ".pcd";                                                             // :279
-    vector<float> pts;
-    int n = 0;
-    if (!loadPCDFile(ss.str(), pts, n)) { cerr << "cannot read " << ss.str() << endl; exit(1); }
+    s3d_cloud *raw = 0, *c = 0;
+    if (_nextRaw && _nextIndex == _index) {
+        raw = _nextRaw;                  // uploaded while the previous frame was being registered
+        _nextRaw = 0;
+    } else {
+        if (_nextRaw) { s3d_cloud_free(_ctx, _nextRaw); _nextRaw = 0; }      // the run jumped: the prefetched frame is not the one wanted
+        vector<float> pts;
+        int n = 0;
+        if (!loadPCDFile(ss.str(), pts, n)) { cerr << "cannot read " << ss.str() << endl; exit(1); }
+        S3D_CHECK(s3d_cloud_upload(_ctx, pts.data(), 4, n, &raw));
+    }
     // PassThrough z in [0, z_filter] (:283-285) and, on request, VoxelGrid(grid_leaf) (:287-295), both on the device.
     // The reference always voxel-filters (its features do not need density); the ICP backend registers at full
     // density unless parameters.yaml says `use_voxel_grid: yes`.
-    s3d_cloud *raw = 0, *c = 0;
-    S3D_CHECK(s3d_cloud_upload(_ctx, pts.data(), 4, n, &raw));
     S3D_CHECK(s3d_cloud_passthrough_z(_ctx, raw, 0.0f, (float)_z_filter, &c));
     s3d_cloud_free(_ctx, raw);
     if (g_pParaReader->GetPara("use_voxel_grid") == string("yes")) {
@@ -173,7 +184,34 @@ int GraphicEnd::readimage()
     _clouds.push_back(c);
     _currCloud = c;
     cout << "load ok." << endl;
+    prefetch(_index + 1);
     return 0;
+}
+
+// Starts the upload of frame `index` on the context's copy stream: the transfer crosses PCIe while the SMs extract planes and
+// register the frame just loaded.  (The reference loads frame k+1 only when run() is called for it, src/GraphicEnd.cpp:266-281.)
+// A missing file is not an error here: the caller decides where the sequence ends.
+void GraphicEnd::prefetch(int index)
+{
+    stringstream path;
+    path << _pclPath << index << ".pcd";
+    ifstream probe(path.str().c_str(), ios::binary);
+    if (!probe.good()) return;
+    probe.close();
+    vector<float> pts;
+    int n = 0;
+    if (!loadPCDFile(path.str(), pts, n) || n <= 0) return;
+    if (pts.size() > _pinnedFloats) {
+        // the staging rows of the frame before were consumed by readimage() (its pass-through returned with the stream drained)
+        s3d_host_free(_ctx, _pinned);
+        _pinned = 0; _pinnedFloats = 0;
+        void *h = 0;
+        if (s3d_host_alloc(_ctx, pts.size() * sizeof(float), &h) != S3D_OK) return;
+        _pinned = (float *)h; _pinnedFloats = pts.size();
+    }
+    memcpy(_pinned, pts.data(), pts.size() * sizeof(float));
+    if (s3d_cloud_upload_async(_ctx, _pinned, 4, n, &_nextRaw) != S3D_OK) { _nextRaw = 0; return; }
+    _nextIndex = index;
 }
 
 void GraphicEnd::addEdge(int from, int to, const Isometry3d &T, double info, bool robust)

@@ -96,12 +96,18 @@ class GraphicEnd
     s3d_plane_params _seg;
     double _icp_max_rmse, _icp_min_inlier_ratio;
     std::vector<s3d_cloud *> _clouds;   // every cloud uploaded so far (keyframes keep theirs resident in HBM)
+    // the NEXT frame's cloud, uploaded on the copy stream while this frame is registered (s3d_cloud_upload_async)
+    s3d_cloud *_nextRaw;
+    int _nextIndex;
+    float *_pinned;                     // page-locked staging rows of the prefetched frame
+    size_t _pinnedFloats;
     std::stringstream ss;
     bool _have_guess, _use_guess;       // tracking: last successful key-frame -> frame pose as the next initial guess
     Isometry3d _guess;
 
  protected:
     RESULT_OF_MULTIPNP toResult(const s3d_result &r, int n_src, int minimum_inliers);
+    void prefetch(int index);
     void addEdge(int from, int to, const Isometry3d &T, double info, bool robust);
 };
 
