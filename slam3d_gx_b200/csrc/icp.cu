@@ -16,9 +16,10 @@
 //                         tile_search.cuh) and a call-free accumulate pass (29 double sums in registers); the CTAs
 //                         of the group exchange one row of 29 doubles through L2, meet at a group barrier, and
 //                         every CTA sums the rows in the same fixed order and solves the 6x6 (or Kabsch) in
-//                         double: no host round trip, no kernel boundary between iterations.  From the ~6th
-//                         iteration on >99.9% of the queries keep their correspondence and an iteration is two
-//                         streaming passes over 48 B/point each.
+//                         double: no host round trip, no kernel boundary between iterations.  While most
+//                         queries still search (first iterations) a CTA hands its octets out dynamically from a
+//                         shared-memory counter; from the ~6th iteration on >99.9% of the queries keep their
+//                         correspondence and an iteration is two streaming passes over 48 B/point each.
 //   S3D_SEARCH_GRID_LANE  icp_iter_kernel, one launch per iteration, per-lane ball search (search.cuh);
 //                         the last CTA to finish (atomic ticket) solves.  Kept as an independent check.
 //   S3D_SEARCH_BRUTE      all targets streamed through shared memory by TMA bulk copies
@@ -735,8 +736,8 @@ __global__ void __launch_bounds__(TS_BLOCK, 1) icp_persist_kernel(const PersistA
             // depth and surface orientation, and a fixed assignment leaves warps waiting for the slowest one of their CTA
             // (and CTAs for the slowest CTA): 32 % of the warp time of the first build of this kernel.  In those iterations
             // (`dyn`, decided per CTA from its own count of the previous iteration) the CTA's octets are handed out one
-            // at a time from a shared-memory counter, lanes 0..7 of the taking warp hold the queries and all 32 lanes
-            // search for them.  The per-query state lives in global memory and an octet always belongs to the same CTA, so
+            // or two at a time (a.dyn_octets) from a shared-memory counter, one per 8 lanes of the taking warp, and all 32
+            // lanes search for them.  The per-query state lives in global memory and an octet always belongs to the same CTA, so
             // who decides it changes nothing in what is found.
             const int cta_units = rank < nunits ? (nunits - rank + a.group_ctas - 1) / a.group_ctas : 0;      // octets rank, rank + group_ctas, ...
             const bool dyn = !same_pose && a.dyn_div > 0 && (it == 0 || (long long)n_pending_prev * a.dyn_div > (long long)cta_units * 8);
