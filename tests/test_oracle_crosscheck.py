@@ -163,3 +163,23 @@ def test_planar_keypoints_oracle(small_cam):
         if (patch == patch[0, 0]).all():
             inner.append(f)
     assert len(inner) > 50 and np.mean(inner) > 0.95     # single-plane patches are planar (1 mm noise vs 1 cm threshold)
+
+
+def test_exp1_2_error_protocol_on_the_oracle(tmp_path, small_cam):
+    """The reference's registration-error log (src/exp1/exp1_2.cpp:268-295: f1 f2 |t(Tr)| angle(Tr) |t(Terror)| angle(Terror) inliers),
+    produced by tools/exp1_2_protocol.py with the CPU oracle on 160x120 pairs: the error stays at the depth-noise floor while the
+    true motion grows with the frame offset."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("exp1_2_protocol", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                                                                                  "tools", "exp1_2_protocol.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    out = tmp_path / "error.log"
+    lines = mod.run(tests=2, offsets=[1, 2], impl="oracle", cam=small_cam, iterations=20, out=str(out))
+    assert len(lines) == 4 and out.read_text().count("\n") == 4
+    rows = np.array([[float(x) for x in ln.split()] for ln in lines])
+    assert np.all(rows[:, 1] - rows[:, 0] == np.array([1, 2, 1, 2]))
+    assert np.all(rows[:, 2] > 0.005) and np.all(rows[:, 3] > 0.005)          # the true motion
+    assert np.all(rows[:, 4] < 5e-3) and np.all(rows[:, 5] < 2e-3)            # what is left after registration
+    assert np.all(rows[:, 6] > 0.9 * small_cam.width * small_cam.height)
