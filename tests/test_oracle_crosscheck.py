@@ -176,7 +176,8 @@ def test_exp1_2_error_protocol_on_the_oracle(tmp_path, small_cam):
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     out = tmp_path / "error.log"
-    lines = mod.run(tests=2, offsets=[1, 2], impl="oracle", cam=small_cam, iterations=20, out=str(out))
+    lines = mod.run(tests=2, offsets=[1, 2], register=lambda p, prm: oracle.icp(p["src"], p["tgt"], p["tgt_normals"], params=prm),
+                    cam=small_cam, iterations=20, out=str(out))
     assert len(lines) == 4 and out.read_text().count("\n") == 4
     rows = np.array([[float(x) for x in ln.split()] for ln in lines])
     assert np.all(rows[:, 1] - rows[:, 0] == np.array([1, 2, 1, 2]))
