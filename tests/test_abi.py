@@ -74,3 +74,14 @@ def test_product_package_does_not_import_oracle():
                     or f.endswith((".cu", ".cuh", ".h")), f
                 assert "import oracle" not in txt and "from oracle" not in txt, f"{f} imports the oracle"
                 assert "liboracle" not in txt, f"{f} links the oracle"
+
+
+def test_only_the_checkers_touch_the_oracle():
+    """oracle/ is test infrastructure: besides tests/, only bench.py (cpu_baseline / reference arm) and
+    __graft_entry__.py (smoke check, build of the checker) may import it -- tools/ and the host shell may not."""
+    for sub in ("tools", "include", os.path.join("slam3d_gx_b200", "host")):
+        for dirpath, _, files in os.walk(os.path.join(ROOT, sub)):
+            for f in files:
+                if f.endswith((".py", ".cpp", ".h", ".hpp", ".c")):
+                    txt = open(os.path.join(dirpath, f), errors="ignore").read()
+                    assert "import oracle" not in txt and "from oracle" not in txt and "liboracle" not in txt, os.path.join(dirpath, f)
