@@ -84,13 +84,30 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
+def config_dict(world, pool):
+    """The `config` object of the JSON line: the same for the GPU arm and the reference arm (same workload)."""
+    return {"workload": WORKLOAD, "pairs_per_step_per_gpu": 1, "icp_iterations": ITERS, "points": [N_PTS, N_PTS],
+            "pool_pairs_per_gpu": pool, "l2": "inputs larger than L2: a pool of %d pairs (>%d MB) rotates" % (pool, pool * 40),
+            "parallelism": "pairs sharded over %d GPU(s), NCCL all_gather of pose records" % world}
+
+
+def host_threads():
+    """Every hardware thread this process may run on.  torchrun exports OMP_NUM_THREADS=1; the CPU arm must not inherit that."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def run_reference(args, rank):
     """Reference arm: the CPU restatement of the reference's PCL path with all host threads (rank 0 only)."""
     if rank != 0:
         return
+    threads = host_threads()
+    os.environ["OMP_NUM_THREADS"] = str(threads)       # before the OpenMP runtime of the oracle library starts
     from slam3d_gx_b200 import synth, _abi
     from oracle import oracle
-    threads = oracle.max_threads()
+    assert threads > 1 or (os.cpu_count() or 1) == 1, "reference arm would run single-threaded on a multi-core box"
     pairs = [synth.make_pair(i) for i in range(min(2, max(1, args.steps)))]
     prm = _abi.icp_params(ITERS)
     for w in range(args.warmup):
@@ -108,7 +125,8 @@ def run_reference(args, rank):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / max(1, args.steps) * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "note": "CPU restatement of the reference's PCL-1.7 ICP (reference cannot be built: no PCL)"},
+        "config": config_dict(args.gpus, args.pool),
+        "note": "CPU restatement of the reference's PCL-1.7 ICP (oracle/icp_oracle.c; the reference itself cannot be built: no PCL), rank 0 only",
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -123,6 +141,9 @@ def main():
     ap.add_argument("--pool", type=int, default=POOL)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-batch-regime", action="store_true")
+    ap.add_argument("--no-config4", action="store_true")
+    ap.add_argument("--config4-pairs", type=int, default=64, help="pairs per GPU of the config-4 leg (512 / 8)")
+    ap.add_argument("--config4-steps", type=int, default=3)
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -153,7 +174,11 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     ctx = s3d.Context(local_rank)
-    stream = torch.cuda.current_stream()
+    # an explicit (non-default) torch stream: its handle is what the library launches on, so the CUDA events recorded on it
+    # below bracket the kernels themselves (handle 0, torch's default stream, would mean "the ctx's own stream" to the ABI)
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     ctx.set_stream(stream.cuda_stream)
     W = max(3, args.warmup)
 
@@ -168,28 +193,31 @@ def main():
     from slam3d_gx_b200 import sharding
     rec_bytes = _abi.RESULT_BYTES
 
-    # Pose gather over NCCL: the only collective of the path.  Like config 4 (a batch of pairs sharded over the
-    # ranks, ONE all-gather of the pose records when the batch is done), the records of a rank's steps are collected on the
-    # host and all-gathered in one NCCL call at the end of the timed region, inside it.  (A per-step NCCL kernel cannot run
+    # Pose gather over NCCL: the only collective of the path, through the product's own C ABI
+    # (s3d_comm_create / s3d_gather_results: persistent device + page-locked buffers inside the ctx).  Like config 4 (a batch
+    # of pairs sharded over the ranks, ONE all-gather of the pose records when the batch is done), the records of a rank's
+    # steps are all-gathered in one NCCL call at the end of the timed region, inside it.  (A per-step NCCL kernel cannot run
     # beside the registration kernel, which holds every SM's register file; it would serialise the ranks on each other.)
+    uid = [s3d.Context.comm_unique_id() if rank == 0 else None]
+    if world > 1:
+        dist.broadcast_object_list(uid, src=0)
+    comm = ctx.comm_create(uid[0], world, rank)
     records = []
 
     def step(i):
         k = i % args.pool
         res = ctx.register_batch([src[k]], [tgt[k]], None, prm, raw=True)
         if world > 1:
-            records.append(bytes(res[0]))
+            records.append(res[0])
         return res[0]
 
     def finish_gathers():
         if world == 1 or not records:
             return 0
-        send = torch.frombuffer(bytearray(b"".join(records)), dtype=torch.uint8).to("cuda")
-        recv = torch.empty(world * send.numel(), dtype=torch.uint8, device="cuda")
-        dist.all_gather_into_tensor(recv, send)
-        n = len(sharding.bytes_to_records(recv.cpu().numpy()))
+        local = (_abi.Result * len(records))(*records)
+        allr = ctx.gather_results(comm, local, world)
         records.clear()
-        return n
+        return len(allr)
 
     for k in range(args.pool):      # prime every pair once (first-use device allocations of its index), untimed
         step(k)
@@ -306,14 +334,70 @@ def main():
                         "algorithmic_GBps": nb * B_ALG / per_it_s / 1e9, "read_GBps": nb * N_PTS * 96 / per_it_s / 1e9,
                         "bytes_read_per_query": 96}
 
+    # ---- config 4 (BASELINE.json configs[3]): 512*N/8 independent pairs block-partitioned over the N ranks, 10 iterations,
+    # ONE s3d_register_batch_gather per step and rank: the shard goes through the persistent kernel as one batch, the pose
+    # records are formed on the device in the all-gather send buffer, ncclAllGather follows on the same stream, one
+    # device-to-host copy returns the world's records.  Search indices rebuilt inside the step (like the headline).
+    config4 = None
+    if not args.no_config4:
+        C4_ITERS, per_rank = 10, args.config4_pairs
+        n_total = per_rank * world
+        mine = sharding.partition(n_total, world, rank)
+        c4_src, c4_tgt = [], []
+        for i in mine:
+            if i - mine.start < len(src) and rank * args.pool + (i - mine.start) == i:
+                k = i - mine.start                       # the headline pool already holds this pair (single-GPU run)
+                c4_src.append(src[k]); c4_tgt.append(tgt[k])
+            else:
+                p = synth.make_pair(i)
+                c4_src.append(ctx.upload(p["src"])); c4_tgt.append(ctx.upload(p["tgt"], p["tgt_normals"]))
+        c4_prm = _abi.icp_params(C4_ITERS, reuse_index=0)
+        n_slot = max(len(sharding.partition(n_total, world, r)) for r in range(world))
+        c4_steps, c4_warm = args.config4_steps, 2
+        for _ in range(c4_warm):
+            allr = ctx.register_batch_gather(comm, c4_src, c4_tgt, world, n_slot, None, c4_prm, raw=True)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        c4_l0 = ctx.launch_count
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record(stream)
+        c4_dev_ms = 0.0
+        for _ in range(c4_steps):
+            allr = ctx.register_batch_gather(comm, c4_src, c4_tgt, world, n_slot, None, c4_prm, raw=True)
+            tm = ctx.last_timing()
+            c4_dev_ms += tm["iterate_ms"] + tm["index_ms"]
+        c1.record(stream)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        c4_ms = c0.elapsed_time(c1)
+        ok = [allr[r * n_slot + k].status for r in range(world) for k in range(len(sharding.partition(n_total, world, r)))]
+        assert len(ok) == n_total and all(st == 0 for st in ok), "config 4: a pair failed or a record is missing"
+        # every rank holds every record: pair 0's pose as rank 0 computed it must be what this rank received
+        config4 = {"ms": c4_ms, "dev_ms": c4_dev_ms, "launches": ctx.launch_count - c4_l0, "steps": c4_steps, "pairs_total": n_total,
+                   "pairs_per_gpu": per_rank, "iterations": C4_ITERS, "T0": [allr[0].T[k] for k in range(12)]}
+
     # ---- max over ranks --------------------------------------------------------------------------------
-    t = torch.tensor([elapsed_ms, e2e_s * 1e3, iter_ms], dtype=torch.float64, device="cuda")
-    cnt = torch.tensor([float(launches)], dtype=torch.float64, device="cuda")
+    t = torch.tensor([elapsed_ms, e2e_s * 1e3, iter_ms, config4["ms"] if config4 else 0.0], dtype=torch.float64, device="cuda")
+    tmin = torch.tensor([elapsed_ms, config4["ms"] if config4 else 0.0, config4["dev_ms"] if config4 else 0.0], dtype=torch.float64, device="cuda")
+    tmax2 = tmin.clone()
+    cnt = torch.tensor([float(launches), float(config4["launches"]) if config4 else 0.0], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
+        dist.all_reduce(tmax2, op=dist.ReduceOp.MAX)
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
-    elapsed_ms, e2e_ms, iter_ms_max = [float(x) for x in t.tolist()]
-    total_launches = int(cnt.item())
+        if config4:
+            t0c = torch.tensor(config4["T0"], dtype=torch.float64, device="cuda")
+            t0ref = t0c.clone()
+            dist.broadcast(t0ref, src=0)
+            assert torch.equal(t0c, t0ref), "config 4: gathered records differ between ranks"
+    elapsed_rank_ms = elapsed_ms
+    elapsed_ms, e2e_ms, iter_ms_max, c4_ms_max = [float(x) for x in t.tolist()]
+    total_launches = int(cnt[0].item())
 
     if rank == 0:
         peak, peak_src = measured_peak()
@@ -334,9 +418,7 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
             "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "pairs_per_step_per_gpu": 1, "icp_iterations": ITERS, "points": [N_PTS, N_PTS],
-                       "pool_pairs_per_gpu": args.pool, "l2": "inputs larger than L2: a pool of %d pairs (>%d MB) rotates" % (args.pool, args.pool * 40),
-                       "parallelism": "pairs sharded over %d GPU(s), NCCL all_gather of pose records" % world},
+            "config": config_dict(world, args.pool),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "host_ms_per_step": {k: v / e2e_steps * 1e3 for k, v in e2e_t.items()}, "includes": "pinned-host upload of both clouds (step i+1's copy overlaps step i's compute), RANSAC plane extraction of the target, index build, 30 iterations, result read-back"},
             "gpu_launches": total_launches,
@@ -347,7 +429,21 @@ def main():
                          "avg_launch_us": per_launch_s * 1e6,
                          "note": "achieved = algorithmic bytes (16N+32M per iteration, SURVEY.md 8d) / measured kernel time; the single-pair working set (~45 MB) is L2 resident, so the kernel is bound by search issue slots and per-iteration barrier latency, not by HBM"},
             "breakdown_ms_per_step": {"index_build": index_ms / args.steps, "iterations": iter_ms / args.steps},
+            "elapsed_ms_ranks": {"min": float(tmin[0].item()), "max": float(tmax2[0].item())},
         }
+        if config4:
+            c4_its = config4["pairs_total"] * config4["iterations"] * config4["steps"] / (c4_ms_max * 1e-3)
+            out["config4"] = {
+                "workload": "config4: %d independent 640x480 pairs block-partitioned over %d GPU(s) (%d per GPU), 10 point-to-plane ICP iterations, "
+                            "one s3d_register_batch_gather per rank and step (search indices rebuilt, records packed on the device, ncclAllGather, one D2H)"
+                            % (config4["pairs_total"], world, config4["pairs_per_gpu"]),
+                "iterations_per_s": c4_its, "ms_per_step": c4_ms_max / config4["steps"], "steps": config4["steps"],
+                "pairs_total": config4["pairs_total"], "pairs_per_gpu": config4["pairs_per_gpu"], "icp_iterations": config4["iterations"],
+                "elapsed_ms_ranks": {"min": float(tmin[1].item()), "max": float(tmax2[1].item())},
+                "device_ms_ranks": {"min": float(tmin[2].item()), "max": float(tmax2[2].item())},
+                "gathered_records": config4["pairs_total"], "record_bytes": rec_bytes, "gpu_launches": int(cnt[1].item()),
+                "roofline_frac_algorithmic": B_ALG * config4["pairs_per_gpu"] * config4["iterations"] * config4["steps"] / (float(tmax2[2].item()) * 1e-3) / 1e9 / peak,
+            }
         if batch_regime:
             batch_regime["frac_algorithmic"] = batch_regime["algorithmic_GBps"] / peak
             batch_regime["frac_read"] = batch_regime["read_GBps"] / peak
@@ -371,6 +467,7 @@ def main():
             out["cpu_baseline"] = None
         real_stdout.write(json.dumps(out) + "\n")
         real_stdout.flush()
+    ctx.comm_destroy(comm)
     if world > 1:
         dist.destroy_process_group()
 

@@ -45,7 +45,8 @@ enum {
     S3D_PAIR_OK = 0,
     S3D_PAIR_FEW_CORRESPONDENCES = 1, /* PCL: "Not enough correspondences found" (< min_correspondences) */
     S3D_PAIR_DEGENERATE = 2,          /* normal equations rank deficient (planar sliding) */
-    S3D_PAIR_NONFINITE = 3
+    S3D_PAIR_NONFINITE = 3,
+    S3D_PAIR_ABSENT = -1              /* padding slot of a gathered shard (s3d_register_batch_gather): no pair here */
 };
 
 enum { S3D_ESTIMATOR_POINT_TO_PLANE = 0,   /* PCL TransformationEstimationPointToPlaneLLS */
@@ -168,8 +169,11 @@ int  s3d_cloud_size(const s3d_cloud *cloud);
 int  s3d_cloud_has_normals(const s3d_cloud *cloud);
 /* any of the outputs may be NULL; xyz: n*3 floats, normals: n*3 floats, labels: n int32 (-1 = none) */
 int  s3d_cloud_download(s3d_ctx *ctx, const s3d_cloud *cloud, float *xyz, float *normals, int32_t *labels);
-/* drop the cached search index of a cloud (it is rebuilt on next use as a target) */
+/* drop the cached search index of a cloud and return its buffers to the ctx pool (it is rebuilt on next use as a target) */
 int  s3d_cloud_drop_index(s3d_ctx *ctx, s3d_cloud *cloud);
+/* device memory of the ctx's clouds and indices: bytes handed out now, their high-water mark, bytes cached for reuse
+ * (any pointer may be NULL).  A long run keeps only its key frames resident (reference: _keyframes, src/GraphicEnd.h:150). */
+int  s3d_memory_stats(const s3d_ctx *ctx, size_t *live_bytes, size_t *peak_live_bytes, size_t *cached_bytes);
 void s3d_cloud_free(s3d_ctx *ctx, s3d_cloud *cloud);
 
 /* ---- filters and map fusion (the steps either side of the registration path) ------------------ */
@@ -220,11 +224,27 @@ int  s3d_planar_keypoints(s3d_ctx *ctx, const uint16_t *depth, int width, int he
                           const s3d_camera *cam, const int32_t *uv, int n,
                           float threshold, int min_inliers, uint64_t seed, uint8_t *flags_out);
 
-/* ---- multi-GPU pose gather (no reference counterpart: the reference is single process) ------- */
+/* ---- multi-GPU: pairs sharded over ranks, one pose gather (no reference counterpart: the reference is a single
+ *      process; the independence that is sharded is the candidate loop of src/GraphicEnd.cpp:729-761) ------------- */
+/* NCCL communicator plumbing for hosts that have none (a C++ host needs no NCCL headers; NCCL is resolved with dlopen).
+ * s3d_comm_unique_id: 128 bytes (ncclUniqueId) created on one rank and handed to the others by the caller's own means
+ * (file, socket, MPI, torch.distributed ...); s3d_comm_create: ncclCommInitRank on the ctx's device. */
+#define S3D_COMM_ID_BYTES 128
+int  s3d_comm_unique_id(void *id_out /*[S3D_COMM_ID_BYTES]*/);
+int  s3d_comm_create(s3d_ctx *ctx, const void *id /*[S3D_COMM_ID_BYTES]*/, int world, int rank, void **comm_out);
+void s3d_comm_destroy(s3d_ctx *ctx, void *comm);
 /* All-gather n_local result records from every rank into all_out (world*n_local records) with
- * ncclAllGather on the ctx stream. nccl_comm is an ncclComm_t created by the caller. */
+ * ncclAllGather on the ctx stream. nccl_comm is an ncclComm_t (s3d_comm_create or the caller's own). */
 int  s3d_gather_results(s3d_ctx *ctx, void *nccl_comm, const s3d_result *local, int n_local,
                         int world, s3d_result *all_out);
+/* One rank's shard of a sharded batch, registered and gathered in one call: the n_local pairs go through the same
+ * device path as s3d_register_batch, the result records are formed ON THE DEVICE in the all-gather send buffer,
+ * ncclAllGather runs on the same stream right behind the last iteration, and the only device-to-host copy is the
+ * gathered world*n_slot records.  n_slot >= n_local is the (rank-uniform) number of record slots per rank; slots
+ * beyond a rank's n_local come back with status S3D_PAIR_ABSENT.  all_out[r*n_slot + k] = pair k of rank r. */
+int  s3d_register_batch_gather(s3d_ctx *ctx, void *nccl_comm, const s3d_cloud *const *src, const s3d_cloud *const *tgt,
+                               const double *guess, int n_local, int n_slot, const s3d_icp_params *params,
+                               int world, s3d_result *all_out);
 
 #ifdef __cplusplus
 }

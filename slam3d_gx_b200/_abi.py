@@ -37,6 +37,7 @@ class Timing(C.Structure):
 ESTIMATOR_POINT_TO_PLANE, ESTIMATOR_SVD = 0, 1
 SEARCH_GRID, SEARCH_BRUTE, SEARCH_GRID_LANE = 0, 1, 2
 PAIR_OK, PAIR_FEW, PAIR_DEGENERATE, PAIR_NONFINITE = 0, 1, 2, 3
+PAIR_ABSENT = -1
 PLANE_CANDIDATES_EXTRA = 14
 RESULT_BYTES = C.sizeof(Result)
 

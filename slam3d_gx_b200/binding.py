@@ -34,7 +34,9 @@ EXPORTS = [
     "s3d_last_correspondences", "s3d_last_timing", "s3d_icp_params_default", "s3d_plane_params_default",
     "s3d_planar_keypoints", "s3d_gather_results", "s3d_cloud_passthrough_z", "s3d_cloud_voxel_grid", "s3d_cloud_transform",
     "s3d_cloud_concat", "s3d_map_fuse", "s3d_cloud_from_depth_normals", "s3d_cloud_upload_async", "s3d_cloud_wait", "s3d_host_alloc", "s3d_host_free",
+    "s3d_memory_stats", "s3d_comm_unique_id", "s3d_comm_create", "s3d_comm_destroy", "s3d_register_batch_gather",
 ]
+COMM_ID_BYTES = 128
 
 
 def load_library():
@@ -86,6 +88,13 @@ def load_library():
     lib.s3d_plane_params_default.restype = None
     lib.s3d_planar_keypoints.argtypes = [vp, vp, ci, ci, C.POINTER(_abi.CameraC), vp, ci, C.c_float, ci, C.c_uint64, vp]
     lib.s3d_gather_results.argtypes = [vp, vp, C.POINTER(_abi.Result), ci, ci, C.POINTER(_abi.Result)]
+    lib.s3d_memory_stats.argtypes = [vp, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
+    lib.s3d_comm_unique_id.argtypes = [vp]
+    lib.s3d_comm_create.argtypes = [vp, vp, ci, ci, C.POINTER(vp)]
+    lib.s3d_comm_destroy.argtypes = [vp, vp]
+    lib.s3d_comm_destroy.restype = None
+    lib.s3d_register_batch_gather.argtypes = [vp, vp, C.POINTER(vp), C.POINTER(vp), vp, ci, ci, C.POINTER(_abi.IcpParams), ci,
+                                              C.POINTER(_abi.Result)]
     lib.s3d_cloud_from_depth_normals.argtypes = [vp, vp, ci, ci, C.POINTER(_abi.CameraC), C.c_float, ci, C.c_float, C.POINTER(vp)]
     lib.s3d_cloud_passthrough_z.argtypes = [vp, vp, C.c_float, C.c_float, C.POINTER(vp)]
     lib.s3d_cloud_voxel_grid.argtypes = [vp, vp, C.c_float, C.POINTER(vp)]
@@ -281,6 +290,65 @@ class Context:
         if raw:
             return res
         return [_abi.result_to_dict(res[i]) for i in range(n)]
+
+    # ---- multi-GPU: one shard per rank, one pose gather -------------------------------------------
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        """128-byte NCCL unique id (create on one rank, hand to the others, e.g. with torch.distributed broadcast)."""
+        buf = C.create_string_buffer(COMM_ID_BYTES)
+        rc = load_library().s3d_comm_unique_id(buf)
+        if rc != 0:
+            raise S3DError(f"s3d_comm_unique_id rc={rc}: NCCL not loadable")
+        return buf.raw
+
+    def comm_create(self, uid: bytes, world: int, rank: int):
+        assert len(uid) == COMM_ID_BYTES
+        h = C.c_void_p()
+        self._check(self.lib.s3d_comm_create(self.h, C.c_char_p(uid), world, rank, C.byref(h)))
+        return h
+
+    def comm_destroy(self, comm):
+        self.lib.s3d_comm_destroy(self.h, comm)
+
+    def gather_results(self, comm, local, world: int):
+        """s3d_gather_results: all-gather already computed records (ctypes array of s3d_result)."""
+        n = len(local)
+        out = (_abi.Result * (n * world))()
+        self._check(self.lib.s3d_gather_results(self.h, comm, local, n, world, out))
+        return out
+
+    def register_batch_gather(self, comm, srcs, tgts, world: int, n_slot: int | None = None, guess=None,
+                              params: _abi.IcpParams | None = None, raw: bool = False):
+        """This rank's shard of a sharded batch + the pose gather in one device-side sequence (s3d_register_batch_gather).
+        Returns world * n_slot records in rank order (padding slots have status PAIR_ABSENT)."""
+        params = params or _abi.icp_params()
+        n = len(srcs)
+        assert n == len(tgts)
+        n_slot = n if n_slot is None else n_slot
+        sa = (C.c_void_p * max(n, 1))(*[s.handle for s in srcs])
+        ta = (C.c_void_p * max(n, 1))(*[t.handle for t in tgts])
+        g = None
+        if guess is not None:
+            g = np.ascontiguousarray(guess, dtype=np.float64).reshape(n, 16)
+        res = (_abi.Result * (n_slot * world))()
+        self._check(self.lib.s3d_register_batch_gather(self.h, comm, sa, ta, g.ctypes.data if g is not None else None, n, n_slot,
+                                                       C.byref(params), world, res))
+        if raw:
+            return res
+        return [_abi.result_to_dict(res[i]) for i in range(n_slot * world)]
+
+    def memory_stats(self) -> dict:
+        a, b, c = C.c_size_t(), C.c_size_t(), C.c_size_t()
+        self._check(self.lib.s3d_memory_stats(self.h, C.byref(a), C.byref(b), C.byref(c)))
+        return dict(live_bytes=a.value, peak_live_bytes=b.value, cached_bytes=c.value)
+
+    def host_alloc(self, nbytes: int) -> int:
+        h = C.c_void_p()
+        self._check(self.lib.s3d_host_alloc(self.h, nbytes, C.byref(h)))
+        return h.value
+
+    def host_free(self, ptr: int):
+        self.lib.s3d_host_free(self.h, C.c_void_p(ptr))
 
     def register(self, src: Cloud, tgt: Cloud, guess=None, params: _abi.IcpParams | None = None) -> dict:
         return self.register_batch([src], [tgt], None if guess is None else [guess], params)[0]

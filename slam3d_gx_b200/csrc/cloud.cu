@@ -53,6 +53,8 @@ cudaError_t s3d_dev_alloc(s3d_ctx *ctx, void **out, size_t bytes)
         it = std::prev(ctx->pool_free.upper_bound(it->first));
         *out = it->second;
         ctx->pool_live[it->second] = it->first;
+        ctx->pool_live_bytes += it->first;
+        if (ctx->pool_live_bytes > ctx->pool_peak_bytes) ctx->pool_peak_bytes = ctx->pool_live_bytes;
         ctx->pool_cached -= it->first;
         ctx->pool_free.erase(it);
         return cudaSuccess;
@@ -63,7 +65,11 @@ cudaError_t s3d_dev_alloc(s3d_ctx *ctx, void **out, size_t bytes)
         s3d_dev_pool_release(ctx);
         e = cudaMalloc(out, want);
     }
-    if (e == cudaSuccess) ctx->pool_live[*out] = want;
+    if (e == cudaSuccess) {
+        ctx->pool_live[*out] = want;
+        ctx->pool_live_bytes += want;
+        if (ctx->pool_live_bytes > ctx->pool_peak_bytes) ctx->pool_peak_bytes = ctx->pool_live_bytes;
+    }
     return e;
 }
 
@@ -74,6 +80,7 @@ void s3d_dev_free(s3d_ctx *ctx, void *p)
     if (it == ctx->pool_live.end()) { cudaFree(p); return; }
     const size_t sz = it->second;
     ctx->pool_live.erase(it);
+    ctx->pool_live_bytes -= sz;
     if (ctx->pool_cached + sz > S3D_POOL_MAX_CACHED) { cudaFree(p); return; }
     ctx->pool_free.insert({sz, p});
     ctx->pool_cached += sz;
@@ -125,6 +132,8 @@ extern "C" void s3d_destroy(s3d_ctx *ctx)
     cudaFree(ctx->d_partials); cudaFree(ctx->d_nn_idx); cudaFree(ctx->d_nn_d2); cudaFree(ctx->d_nn_pos); cudaFree(ctx->d_last_nn);
     cudaFree(ctx->d_cq); cudaFree(ctx->d_cn); cudaFree(ctx->d_lb); cudaFree(ctx->d_cq2); cudaFree(ctx->d_barriers);
     cudaFree(ctx->d_seg);
+    cudaFree(ctx->d_gather_send); cudaFree(ctx->d_gather_recv);
+    if (ctx->h_gather) cudaFreeHost(ctx->h_gather);
     s3d_dev_pool_release(ctx);
     for (auto &kv : ctx->pool_live) cudaFree(kv.first);     // handles the caller never freed
     ctx->pool_live.clear();
@@ -186,7 +195,9 @@ extern "C" int s3d_cloud_upload(s3d_ctx *ctx, const float *xyz, int stride_float
     s3d_cloud *c = nullptr;
     int rc = cloud_alloc(ctx, n, &c);
     if (rc) return rc;
-    if (n > 0) {
+    float *tmp = nullptr;
+    rc = [&]() -> int {       // every early return below leaves through the clean-up after the lambda
+        if (n == 0) return S3D_OK;
         size_t bytes = sizeof(float) * (size_t)n * stride_floats;
         if (stride_floats == 4) {
             // PCD rows "x y z rgba" are already float4-shaped: copy straight, then normalise w on device
@@ -194,16 +205,16 @@ extern "C" int s3d_cloud_upload(s3d_ctx *ctx, const float *xyz, int stride_float
             pack_xyz_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>((const float *)c->d_pts, 4, n, c->d_pts);
             S3D_LAUNCHED(ctx);
         } else {
-            float *tmp = nullptr;
             S3D_CUDA(ctx, s3d_dev_alloc_t(ctx, &tmp, bytes));
             S3D_CUDA(ctx, cudaMemcpyAsync(tmp, xyz, bytes, cudaMemcpyHostToDevice, ctx->stream));
             pack_xyz_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(tmp, stride_floats, n, c->d_pts);
             S3D_LAUNCHED(ctx);
-            S3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-            s3d_dev_free(ctx, tmp);
         }
         S3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    }
+        return S3D_OK;
+    }();
+    if (tmp) { cudaStreamSynchronize(ctx->stream); s3d_dev_free(ctx, tmp); }
+    if (rc) { s3d_cloud_free(ctx, c); return rc; }
     *out = c;
     return S3D_OK;
 }
@@ -439,7 +450,19 @@ extern "C" int s3d_cloud_download(s3d_ctx *ctx, const s3d_cloud *cloud, float *x
 extern "C" int s3d_cloud_drop_index(s3d_ctx *ctx, s3d_cloud *cloud)
 {
     if (!ctx || !cloud) return S3D_E_ARG;
-    cloud->grid.valid = false;
+    // the buffers go back to the ctx pool (stream ordered: whatever still reads them was enqueued before)
+    s3d_grid_free(ctx, cloud->grid);
+    s3d_grid_free(ctx, cloud->coarse);
+    s3d_dev_free(ctx, cloud->d_coarse_pts); cloud->d_coarse_pts = nullptr; cloud->cap_coarse_pts = 0;
+    return S3D_OK;
+}
+
+extern "C" int s3d_memory_stats(const s3d_ctx *ctx, size_t *live_bytes, size_t *peak_live_bytes, size_t *cached_bytes)
+{
+    if (!ctx) return S3D_E_ARG;
+    if (live_bytes) *live_bytes = ctx->pool_live_bytes;
+    if (peak_live_bytes) *peak_live_bytes = ctx->pool_peak_bytes;
+    if (cached_bytes) *cached_bytes = ctx->pool_cached;
     return S3D_OK;
 }
 

@@ -101,6 +101,10 @@ struct s3d_ctx {
     float4 *d_cq = nullptr; float4 *d_cn = nullptr; float4 *d_lb = nullptr; float4 *d_cq2 = nullptr;
     unsigned *d_barriers = nullptr; int cap_barriers = 0;
     int persist_resident[2] = {0, 0};   // co-resident CTAs of icp_persist_kernel<EST> on this device
+    bool brute_attr_done = false;       // dynamic shared-memory opt-in of nn_brute_tma_kernel done on this ctx's device
+    // pose gather (gather.cu): persistent send / receive buffers on the device and a page-locked landing buffer
+    s3d_result *d_gather_send = nullptr, *d_gather_recv = nullptr, *h_gather = nullptr;
+    size_t cap_gather_send = 0, cap_gather_recv = 0, cap_gather_host = 0;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     s3d_timing timing = {0, 0, 0, 0};
     // plane segmentation scratch
@@ -114,6 +118,7 @@ struct s3d_ctx {
     std::map<void *, size_t> pool_live;
     std::multimap<size_t, void *> pool_free;
     size_t pool_cached = 0;
+    size_t pool_live_bytes = 0, pool_peak_bytes = 0;   // handed out right now / high-water mark (s3d_memory_stats)
 };
 
 int s3d_fail(s3d_ctx *ctx, int code, const char *what, cudaError_t e = cudaSuccess);
@@ -127,6 +132,13 @@ void s3d_dev_pool_release(s3d_ctx *ctx);
 template <typename T> static inline cudaError_t s3d_dev_alloc_t(s3d_ctx *ctx, T **out, size_t bytes) { return s3d_dev_alloc(ctx, reinterpret_cast<void **>(out), bytes); }
 // cloud.cu: orders the ctx stream behind a cloud's asynchronous upload and packs its rows (no-op for every other cloud)
 int s3d_cloud_ready(s3d_ctx *ctx, const s3d_cloud *cloud);
+// icp.cu: the two halves of s3d_register_batch (enqueue everything / read the event times after a synchronisation),
+// the host-side completion of a record (norm, failure convention) and the device-side packing of the records
+int s3d_register_issue(s3d_ctx *ctx, const s3d_cloud *const *src, const s3d_cloud *const *tgt, const double *guess, int n_pairs,
+                       const s3d_icp_params *prm, bool *built_out, int *iter_launches_out);
+void s3d_register_timing(s3d_ctx *ctx, bool built, int iter_launches);
+void s3d_result_finish(s3d_result *r);
+int s3d_result_pack(s3d_ctx *ctx, int n_pairs, s3d_result *d_out, int n_slots);
 // grid.cu
 int s3d_grid_build(s3d_ctx *ctx, s3d_cloud *cloud, float cell);
 void s3d_grid_free(s3d_ctx *ctx, GridIndex &g);

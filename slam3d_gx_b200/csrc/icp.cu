@@ -1051,10 +1051,12 @@ static void launch_iter(s3d_ctx *ctx, dim3 grid, int nn_stride, int use_seed, fl
                                                                       ctx->d_nn_pos, ctx->d_nn_d2, nn_stride, use_seed, max_d2, min_corr, pivot_eps, nn_out);
 }
 
-extern "C" int s3d_register_batch(s3d_ctx *ctx, const s3d_cloud *const *src, const s3d_cloud *const *tgt,
-                                  const double *guess, int n_pairs, const s3d_icp_params *prm, s3d_result *out)
+// Enqueues one batch on the ctx stream (index builds where needed, pair descriptors, every iteration launch) and records
+// ev[0..2] around the two stages; the final per-pair state is left in ctx->d_state.  No host synchronisation.
+int s3d_register_issue(s3d_ctx *ctx, const s3d_cloud *const *src, const s3d_cloud *const *tgt,
+                       const double *guess, int n_pairs, const s3d_icp_params *prm, bool *built_out, int *iter_launches_out)
 {
-    if (!ctx || !src || !tgt || !prm || !out || n_pairs <= 0) return s3d_fail(ctx, S3D_E_ARG, "s3d_register_batch: bad argument");
+    if (!ctx || !src || !tgt || !prm || n_pairs <= 0) return s3d_fail(ctx, S3D_E_ARG, "s3d_register_batch: bad argument");
     if (prm->estimator != S3D_ESTIMATOR_POINT_TO_PLANE && prm->estimator != S3D_ESTIMATOR_SVD) return s3d_fail(ctx, S3D_E_ARG, "unknown estimator");
     if (prm->search != S3D_SEARCH_GRID && prm->search != S3D_SEARCH_BRUTE && prm->search != S3D_SEARCH_GRID_LANE)
         return s3d_fail(ctx, S3D_E_ARG, "unknown search mode");
@@ -1201,8 +1203,10 @@ extern "C" int s3d_register_batch(s3d_ctx *ctx, const s3d_cloud *const *src, con
         if (!use_grid) {
             dim3 g2((n_max + ICP_BLOCK * BF_SRC_PER_THREAD - 1) / (ICP_BLOCK * BF_SRC_PER_THREAD), n_pairs);
             size_t smem = sizeof(float4) * BF_TILE * BF_STAGES;
-            static bool attr_done = false;
-            if (!attr_done) { cudaFuncSetAttribute(nn_brute_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_done = true; }
+            if (!ctx->brute_attr_done) {      // the attribute is per device, hence per ctx
+                S3D_CUDA(ctx, cudaFuncSetAttribute(nn_brute_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                ctx->brute_attr_done = true;
+            }
             nn_brute_tma_kernel<<<g2, ICP_BLOCK, smem, ctx->stream>>>(ctx->d_desc, ctx->d_state, ctx->d_nn_idx, ctx->d_nn_d2, n_max);
             S3D_LAUNCHED(ctx); ++iter_launches;
             if (plane) launch_iter<S3D_ESTIMATOR_POINT_TO_PLANE, S3D_SEARCH_BRUTE>(ctx, grid, n_max, 0, max_d2, min_corr, pivot_eps, no);
@@ -1214,29 +1218,79 @@ extern "C" int s3d_register_batch(s3d_ctx *ctx, const s3d_cloud *const *src, con
         S3D_LAUNCHED(ctx); ++iter_launches;
     }
     cudaEventRecord(ctx->ev[2], ctx->stream);
-    S3D_CUDA(ctx, cudaMemcpyAsync(ctx->h_state, ctx->d_state, sizeof(PairState) * n_pairs, cudaMemcpyDeviceToHost, ctx->stream));
-    S3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *built_out = built; *iter_launches_out = iter_launches;
+    ctx->timing.total_launches = (int)(ctx->launches - launches0);
+    return S3D_OK;
+}
 
-    for (int i = 0; i < n_pairs; ++i) {
-        const PairState &s = ctx->h_state[i];
-        s3d_result &r = out[i];
-        memset(&r, 0, sizeof(r));
-        r.inliers = s.inliers; r.iterations = s.iterations; r.status = s.status; r.fitness = s.fitness;
-        if (s.status == S3D_PAIR_OK) {
-            memcpy(r.T, s.T, sizeof(double) * 12);
-            r.T[15] = 1.0;
-            r.norm = pose_norm(r.T);
-        } else {
-            r.T[0] = r.T[5] = r.T[10] = r.T[15] = 1.0; // the reference's failure convention: T == Identity
-        }
-    }
+// after the stream has been synchronised: event times of the two stages of the last s3d_register_issue
+void s3d_register_timing(s3d_ctx *ctx, bool built, int iter_launches)
+{
     float ms_index = 0.f, ms_iter = 0.f;
     cudaEventElapsedTime(&ms_index, ctx->ev[0], ctx->ev[1]);
     cudaEventElapsedTime(&ms_iter, ctx->ev[1], ctx->ev[2]);
     ctx->timing.index_ms = built ? ms_index : 0.f;
     ctx->timing.iterate_ms = ms_iter;
     ctx->timing.iter_launches = iter_launches;
-    ctx->timing.total_launches = (int)(ctx->launches - launches0);
+}
+
+// A record as it leaves the device (T, fitness, inliers, iterations, status) gets, on the host, the reference's `norm`
+// (src/GraphicEnd.cpp:618) and the reference's failure convention T == Identity (:585-600,621-624).
+void s3d_result_finish(s3d_result *r)
+{
+    if (r->status == S3D_PAIR_OK) {
+        r->T[12] = r->T[13] = r->T[14] = 0.0; r->T[15] = 1.0;
+        r->norm = pose_norm(r->T);
+    } else {
+        memset(r->T, 0, sizeof(r->T));
+        r->T[0] = r->T[5] = r->T[10] = r->T[15] = 1.0;
+        r->norm = 0.0;
+    }
+}
+
+// PairState -> s3d_result on the device: the records are formed where the solve left them, directly in the buffer the pose
+// gather sends (gather.cu), so nothing but the gathered records ever crosses PCIe.  Slots >= n_pairs are marked absent.
+__global__ void result_pack_kernel(const PairState *__restrict__ states, int n_pairs, s3d_result *__restrict__ out, int n_slots)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_slots) return;
+    s3d_result r;
+    memset(&r, 0, sizeof(r));
+    if (i < n_pairs) {
+        const PairState &s = states[i];
+        #pragma unroll
+        for (int k = 0; k < 12; ++k) r.T[k] = s.T[k];
+        r.T[15] = 1.0;
+        r.fitness = s.fitness; r.inliers = s.inliers; r.iterations = s.iterations; r.status = s.status;
+    } else r.status = S3D_PAIR_ABSENT;
+    out[i] = r;
+}
+
+int s3d_result_pack(s3d_ctx *ctx, int n_pairs, s3d_result *d_out, int n_slots)
+{
+    result_pack_kernel<<<(n_slots + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_state, n_pairs, d_out, n_slots);
+    S3D_LAUNCHED(ctx);
+    return S3D_OK;
+}
+
+extern "C" int s3d_register_batch(s3d_ctx *ctx, const s3d_cloud *const *src, const s3d_cloud *const *tgt,
+                                  const double *guess, int n_pairs, const s3d_icp_params *prm, s3d_result *out)
+{
+    if (!out) return s3d_fail(ctx, S3D_E_ARG, "s3d_register_batch: bad argument");
+    bool built = false; int iter_launches = 0;
+    int rc = s3d_register_issue(ctx, src, tgt, guess, n_pairs, prm, &built, &iter_launches);
+    if (rc) return rc;
+    S3D_CUDA(ctx, cudaMemcpyAsync(ctx->h_state, ctx->d_state, sizeof(PairState) * n_pairs, cudaMemcpyDeviceToHost, ctx->stream));
+    S3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < n_pairs; ++i) {
+        const PairState &s = ctx->h_state[i];
+        s3d_result &r = out[i];
+        memset(&r, 0, sizeof(r));
+        r.inliers = s.inliers; r.iterations = s.iterations; r.status = s.status; r.fitness = s.fitness;
+        memcpy(r.T, s.T, sizeof(double) * 12);
+        s3d_result_finish(&r);
+    }
+    s3d_register_timing(ctx, built, iter_launches);
     return S3D_OK;
 }
 

@@ -15,8 +15,8 @@ using namespace std;
 #define S3D_CHECK(call) do { int rc__ = (call); if (rc__ != S3D_OK) { cerr << BOLDRED << "slam3d_b200: " #call " failed (" << rc__ << "): " \
     << s3d_last_error(_ctx) << RESET << endl; exit(1); } } while (0)
 
-GraphicEnd::GraphicEnd() : _pSLAMEnd(0), _currCloud(0), _lost(0), _index(0), _moreLoops(0), _ctx(0), _nextRaw(0), _nextIndex(-1), _pinned(0), _pinnedFloats(0),
-                           _have_guess(false), _use_guess(false)
+GraphicEnd::GraphicEnd() : _pSLAMEnd(0), _currCloud(0), _lost(0), _index(0), _moreLoops(0), _ctx(0), _peakClouds(0), _nextRaw(0), _nextIndex(-1), _pinned(0),
+                           _pinnedFloats(0), _readerState(0), _readN(0), _readIndex(-1), _have_guess(false), _use_guess(false)
 {
     g_pParaReader = new ParameterReader(parameter_file_addr);                       // :62
     int seed = atoi(g_pParaReader->GetPara("random_seed").c_str());
@@ -30,6 +30,7 @@ GraphicEnd::GraphicEnd() : _pSLAMEnd(0), _currCloud(0), _lost(0), _index(0), _mo
 
 GraphicEnd::~GraphicEnd()
 {
+    if (_reader.joinable()) _reader.join();
     for (size_t i = 0; i < _clouds.size(); ++i) s3d_cloud_free(_ctx, _clouds[i]);
     if (_nextRaw) s3d_cloud_free(_ctx, _nextRaw);
     s3d_host_free(_ctx, _pinned);
@@ -95,7 +96,9 @@ int GraphicEnd::run()
     cout << "********************" << endl;
     _present.planes.clear();
     readimage();
+    issuePrefetched(false);
     _present.planes = extractPlanesAndGenerateImage(_currCloud);                                    // :158
+    issuePrefetched(false);
 
     // the reference registers from scratch every frame (features); an ICP tracks, so the previous frame's result
     // (same key frame) is the initial guess
@@ -150,6 +153,7 @@ int GraphicEnd::run()
     }
     _index++;
     _present.frame_index = _index;
+    releaseUnused();
     return 1;
 }
 
@@ -159,10 +163,13 @@ int GraphicEnd::readimage()
     ss.str(""); ss.clear();
     ss << _pclPath << _index << ".pcd";                                                             // :279
     s3d_cloud *raw = 0, *c = 0;
+    if (_readIndex == _index) issuePrefetched(true);       // the reader thread was given this frame: take its rows
     if (_nextRaw && _nextIndex == _index) {
         raw = _nextRaw;                  // uploaded while the previous frame was being registered
         _nextRaw = 0;
     } else {
+        if (_reader.joinable()) _reader.join();
+        _readerState = 0; _readIndex = -1;
         if (_nextRaw) { s3d_cloud_free(_ctx, _nextRaw); _nextRaw = 0; }      // the run jumped: the prefetched frame is not the one wanted
         vector<float> pts;
         int n = 0;
@@ -182,36 +189,73 @@ int GraphicEnd::readimage()
         c = v;
     }
     _clouds.push_back(c);
+    if (_clouds.size() > _peakClouds) _peakClouds = _clouds.size();
     _currCloud = c;
     cout << "load ok." << endl;
     prefetch(_index + 1);
     return 0;
 }
 
-// Starts the upload of frame `index` on the context's copy stream: the transfer crosses PCIe while the SMs extract planes and
-// register the frame just loaded.  (The reference loads frame k+1 only when run() is called for it, src/GraphicEnd.cpp:266-281.)
-// A missing file is not an error here: the caller decides where the sequence ends.
+// Frame `index` is read and parsed on a worker thread while the frame just loaded is processed (the reference loads frame
+// k+1 only when run() is called for it, src/GraphicEnd.cpp:266-281).  A missing file is not an error here: the caller
+// decides where the sequence ends.  The worker touches neither the ctx nor the page-locked rows.
 void GraphicEnd::prefetch(int index)
 {
+    if (_reader.joinable()) _reader.join();
     stringstream path;
     path << _pclPath << index << ".pcd";
-    ifstream probe(path.str().c_str(), ios::binary);
-    if (!probe.good()) return;
-    probe.close();
-    vector<float> pts;
-    int n = 0;
-    if (!loadPCDFile(path.str(), pts, n) || n <= 0) return;
-    if (pts.size() > _pinnedFloats) {
+    _readIndex = index;
+    _readerState = 1;
+    const string file = path.str();
+    _reader = std::thread([this, file]() {
+        int n = 0;
+        const bool ok = loadPCDFile(file, _readRows, n) && n > 0;
+        _readN = n;
+        _readerState.store(ok ? 2 : 3, std::memory_order_release);
+    });
+}
+
+// Main thread, between the stages of run(): when the reader has delivered the rows, copy them into the page-locked staging
+// buffer and start the upload on the ctx copy stream; it crosses PCIe while the SMs extract planes / register.
+void GraphicEnd::issuePrefetched(bool wait)
+{
+    if (wait && _reader.joinable()) _reader.join();
+    if (_readerState.load(std::memory_order_acquire) < 2) return;
+    if (_reader.joinable()) _reader.join();
+    const bool ok = _readerState == 2;
+    _readerState = 0;
+    const int index = _readIndex;
+    _readIndex = -1;
+    if (!ok) return;
+    if (_readRows.size() > _pinnedFloats) {
         // the staging rows of the frame before were consumed by readimage() (its pass-through returned with the stream drained)
         s3d_host_free(_ctx, _pinned);
         _pinned = 0; _pinnedFloats = 0;
         void *h = 0;
-        if (s3d_host_alloc(_ctx, pts.size() * sizeof(float), &h) != S3D_OK) return;
-        _pinned = (float *)h; _pinnedFloats = pts.size();
+        if (s3d_host_alloc(_ctx, _readRows.size() * sizeof(float), &h) != S3D_OK) return;
+        _pinned = (float *)h; _pinnedFloats = _readRows.size();
     }
-    memcpy(_pinned, pts.data(), pts.size() * sizeof(float));
-    if (s3d_cloud_upload_async(_ctx, _pinned, 4, n, &_nextRaw) != S3D_OK) { _nextRaw = 0; return; }
+    memcpy(_pinned, _readRows.data(), _readRows.size() * sizeof(float));
+    if (_nextRaw) { s3d_cloud_free(_ctx, _nextRaw); _nextRaw = 0; }
+    if (s3d_cloud_upload_async(_ctx, _pinned, 4, _readN, &_nextRaw) != S3D_OK) { _nextRaw = 0; return; }
     _nextIndex = index;
+}
+
+// Only key frames (and the three frame structures in flight) keep their clouds: everything else goes back to the device
+// pool.  Without this every frame of a long run stayed resident with its search index (~56 MB each).
+void GraphicEnd::releaseUnused()
+{
+    vector<const s3d_cloud *> used;
+    used.push_back(_currCloud);
+    const vector<PLANE> *live[3] = {&_currKF.planes, &_present.planes, &_last.planes};
+    for (int k = 0; k < 3; ++k) for (size_t i = 0; i < live[k]->size(); ++i) used.push_back((*live[k])[i].cloud);
+    for (size_t k = 0; k < _keyframes.size(); ++k) for (size_t i = 0; i < _keyframes[k].planes.size(); ++i) used.push_back(_keyframes[k].planes[i].cloud);
+    size_t w = 0;
+    for (size_t i = 0; i < _clouds.size(); ++i) {
+        if (find(used.begin(), used.end(), (const s3d_cloud *)_clouds[i]) != used.end()) _clouds[w++] = _clouds[i];
+        else s3d_cloud_free(_ctx, _clouds[i]);
+    }
+    _clouds.resize(w);
 }
 
 void GraphicEnd::addEdge(int from, int to, const Isometry3d &T, double info, bool robust)
@@ -227,6 +271,9 @@ void GraphicEnd::addEdge(int from, int to, const Isometry3d &T, double info, boo
 void GraphicEnd::generateKeyFrame(Isometry3d T)
 {
     cout << BOLDGREEN << "GraphicEnd::generateKeyFrame" << RESET << endl;
+    // the outgoing key frame stops being a registration target: only its points, normals and labels stay resident
+    // (11 MB at 640x480); its search index (rebuilt on demand by check()) goes back to the pool
+    if (!_currKF.planes.empty() && _currKF.planes[0].cloud) s3d_cloud_drop_index(_ctx, const_cast<s3d_cloud *>(_currKF.planes[0].cloud));
     _currKF.id++;                                                                                   // :308
     _currKF.planes = _present.planes;
     _currKF.frame_index = _index;

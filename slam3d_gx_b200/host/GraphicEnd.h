@@ -7,9 +7,11 @@
 // Frame loop, keyframe policy, gates and output files follow the reference line by line; what is not on the
 // path (feature detection, GUI, image painting, g2o optimisation) is left out.
 #pragma once
+#include <atomic>
 #include <fstream>
 #include <sstream>
 #include <string>
+#include <thread>
 #include <vector>
 #include "../../include/slam3d_b200.h"
 #include "ParameterReader.h"
@@ -95,19 +97,31 @@ class GraphicEnd
     s3d_icp_params _icp;
     s3d_plane_params _seg;
     double _icp_max_rmse, _icp_min_inlier_ratio;
-    std::vector<s3d_cloud *> _clouds;   // every cloud uploaded so far (keyframes keep theirs resident in HBM)
-    // the NEXT frame's cloud, uploaded on the copy stream while this frame is registered (s3d_cloud_upload_async)
+    // Device clouds that are still referenced: key frames keep theirs resident in HBM (they are loop-closure sources and
+    // targets for the rest of the run), a frame that did not become a key frame is freed -- cloud, normals, labels and the
+    // search index it got as a registration target -- as soon as _present/_last/_currKF have moved on (releaseUnused()).
+    std::vector<s3d_cloud *> _clouds;
+    size_t _peakClouds;                 // high-water mark of _clouds.size(): bounded by #key frames + 3
+    // The NEXT frame: its PCD file is read and parsed by a worker thread while this frame is processed; as soon as the rows
+    // are there the main thread (the only one that calls into the ctx) starts their upload on the copy stream
+    // (s3d_cloud_upload_async), so disk read, PCIe copy and this frame's kernels overlap.
     s3d_cloud *_nextRaw;
     int _nextIndex;
     float *_pinned;                     // page-locked staging rows of the prefetched frame
     size_t _pinnedFloats;
+    std::thread _reader;
+    std::atomic<int> _readerState;      // 0 idle, 1 reading, 2 rows ready, 3 failed / no such file
+    std::vector<float> _readRows;
+    int _readN, _readIndex;
     std::stringstream ss;
     bool _have_guess, _use_guess;       // tracking: last successful key-frame -> frame pose as the next initial guess
     Isometry3d _guess;
 
  protected:
     RESULT_OF_MULTIPNP toResult(const s3d_result &r, int n_src, int minimum_inliers);
-    void prefetch(int index);
+    void prefetch(int index);           // start the reader thread for frame `index`
+    void issuePrefetched(bool wait);    // rows ready -> s3d_cloud_upload_async (wait: join the reader first)
+    void releaseUnused();               // free every cloud no frame structure refers to any more
     void addEdge(int from, int to, const Isometry3d &T, double info, bool robust);
 };
 

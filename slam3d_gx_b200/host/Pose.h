@@ -32,6 +32,18 @@ struct Isometry3d {
         for (int i = 0; i < 3; ++i) r.m[4 * i + 3] = -(r.m[4 * i] * m[3] + r.m[4 * i + 1] * m[7] + r.m[4 * i + 2] * m[11]);
         return r;
     }
+    // from a (not necessarily normalised) quaternion (qx,qy,qz,qw) and a translation
+    static Isometry3d fromQuaternion(const double q[4], const double t[3])
+    {
+        double n = std::sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+        Isometry3d r;
+        if (!(n > 0)) { r.m[3] = t[0]; r.m[7] = t[1]; r.m[11] = t[2]; return r; }
+        const double x = q[0] / n, y = q[1] / n, z = q[2] / n, w = q[3] / n;
+        r.m[0] = 1 - 2 * (y * y + z * z); r.m[1] = 2 * (x * y - z * w);     r.m[2] = 2 * (x * z + y * w);      r.m[3] = t[0];
+        r.m[4] = 2 * (x * y + z * w);     r.m[5] = 1 - 2 * (x * x + z * z); r.m[6] = 2 * (y * z - x * w);      r.m[7] = t[1];
+        r.m[8] = 2 * (x * z - y * w);     r.m[9] = 2 * (y * z + x * w);     r.m[10] = 1 - 2 * (x * x + y * y); r.m[11] = t[2];
+        return r;
+    }
     // unit quaternion (qx,qy,qz,qw), qw >= 0
     void quaternion(double q[4]) const
     {

@@ -12,6 +12,15 @@
 
 int main(int argc, char **argv)
 {
+    // test_host pcd <in.pcd> <out.bin>: dump what loadPCDFile reads (int32 n, then n rows of 4 floats) for the fixture tests
+    if (argc == 4 && std::string(argv[1]) == "pcd") {
+        std::vector<float> rows; int n = 0;
+        if (!loadPCDFile(argv[2], rows, n)) { std::fprintf(stderr, "loadPCDFile failed\n"); return 2; }
+        FILE *f = std::fopen(argv[3], "wb");
+        REQUIRE(f);
+        std::fwrite(&n, 4, 1, f); std::fwrite(rows.data(), 16, (size_t)n, f); std::fclose(f);
+        return 0;
+    }
     REQUIRE(argc == 3);
     // --- ParameterReader on a reference-style parameters.yaml
     ParameterReader pr(argv[1]);
@@ -49,6 +58,30 @@ int main(int argc, char **argv)
     std::string g2o = std::string(argv[2]) + "/t.g2o";
     REQUIRE(opt.save(g2o.c_str()));
     REQUIRE(opt.vertex(1) && opt.vertex(1)->id == 1 && !opt.vertex(7));
+    // --- g2o text reader: what save() wrote comes back (reference src/saveOutput.cpp:30, src/generateTrajectory.cpp:29 call opt.load)
+    {
+        Isometry3d T2 = T * T;
+        VertexSE3 v2; v2.setId(2); opt.addVertex(v2);                      // created at Identity like reference GraphicEnd.cpp:324
+        EdgeSE3 e2; e2.setVertices(1, 2); e2.setMeasurement(T); e2.setInformationDiagonal(100.0); e2.setRobustKernel(true); opt.addEdge(e2);
+        EdgeSE3 e3; e3.setVertices(2, 0); e3.setMeasurement(T2.inverse()); e3.setInformationDiagonal(25.0); opt.addEdge(e3);
+        std::string g2 = std::string(argv[2]) + "/t2.g2o";
+        REQUIRE(opt.save(g2.c_str()));
+        SparseOptimizer back;
+        REQUIRE(back.load(g2.c_str()));
+        REQUIRE(back.vertices().size() == 3 && back.edges().size() == 3);
+        REQUIRE(back.vertex(0) && back.vertex(0)->fixed && !back.vertex(1)->fixed);
+        for (int i = 0; i < 16; ++i) REQUIRE(std::fabs(back.vertex(1)->estimate.m[i] - T.m[i]) < 1e-8);    // %.9g on disk
+        REQUIRE(back.edges()[1].from == 1 && back.edges()[1].to == 2 && back.edges()[2].information[3][3] == 25.0 && back.edges()[2].information[0][1] == 0.0);
+        for (int i = 0; i < 16; ++i) REQUIRE(std::fabs(back.edges()[2].measurement.m[i] - T2.inverse().m[i]) < 1e-8);
+        // estimate data round trip (x y z qx qy qz qw)
+        double d[7]; back.vertex(1)->getEstimateData(d);
+        VertexSE3 w; w.setEstimateData(d);
+        for (int i = 0; i < 16; ++i) REQUIRE(std::fabs(w.estimate.m[i] - T.m[i]) < 1e-8);
+        // spanning-tree propagation from the fixed vertex: vertex 2 (Identity on disk) becomes T * T
+        REQUIRE(back.optimize(10) == 2);
+        for (int i = 0; i < 16; ++i) REQUIRE(std::fabs(back.vertex(2)->estimate.m[i] - T2.m[i]) < 1e-7);
+        REQUIRE(!back.load((std::string(argv[2]) + "/does_not_exist.g2o").c_str()));
+    }
     // --- PCD round trip
     std::vector<float> pts;
     for (int i = 0; i < 5; ++i) { pts.push_back(0.1f * i); pts.push_back(-1.f * i); pts.push_back(2.f + i); pts.push_back(0.f); }
