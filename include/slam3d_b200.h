@@ -118,6 +118,17 @@ typedef struct s3d_timing {
     int32_t total_launches;/* every kernel this library launched during the call */
 } s3d_timing;
 
+/* timing of the last s3d_segment_planes (CUDA events on the ctx stream) and what its evaluation passes read:
+ * points_scanned * 16 bytes is the algorithmic traffic of the RANSAC scan (16 N bytes per pass) */
+typedef struct s3d_plane_timing {
+    float   total_ms;               /* every kernel of the call */
+    float   eval_ms;                /* the candidate-evaluation passes only (plane_eval_kernel) */
+    int32_t rounds;                 /* RANSAC rounds that ran (planes found, + 1 when the last round found none) */
+    int32_t eval_passes_per_round;  /* passes over the remaining points per round: 1 for <= 64 candidates */
+    int64_t points_scanned;         /* sum over the rounds of the points one evaluation pass read */
+    int64_t reserved;
+} s3d_plane_timing;
+
 /* ---- context ------------------------------------------------------------------------------- */
 
 int  s3d_abi_version(void);
@@ -215,6 +226,7 @@ int  s3d_last_correspondences(s3d_ctx *ctx, int32_t *idx_out, int n);
 int  s3d_last_timing(const s3d_ctx *ctx, s3d_timing *out);
 void s3d_icp_params_default(s3d_icp_params *p);
 void s3d_plane_params_default(s3d_plane_params *p);
+int  s3d_last_plane_timing(const s3d_ctx *ctx, s3d_plane_timing *out);
 
 /* ---- keypoint planarity (replaces isPlanar, src/planarFeatures.cpp:88-136) ------------------- */
 /* depth: HOST uint16 image; uv: n pairs (u,v) already truncated to int like :90-91;

@@ -180,32 +180,38 @@ void oracle_nn_brute(const float *src_xyzw, int n, const float *tgt_xyzw, int m,
 
 /* --------------------------------------------------------------- small dense solvers -------- */
 
-/* Cholesky solve of the symmetric 6x6 A x = g (A given as full matrix). Returns 0 on success,
- * 1 when a pivot falls below pivot_eps * A[k][k] (rank deficient: planar sliding). */
+/* Solve of the symmetric 6x6 A x = g by the square-root-free Cholesky factorisation A = L D L^T (A given as full matrix).
+ * Returns 0 on success, 1 when a pivot falls below pivot_eps * A[k][k] (rank deficient: planar sliding).  Part of the
+ * arithmetic contract: the CUDA solve (csrc/icp.cu) performs the same IEEE operations in the same order (no contraction
+ * on either side), so poses are bit-identical. */
 static int chol6_solve(const double A[6][6], const double g[6], double pivot_eps, double x[6])
 {
-    double L[6][6]; memset(L, 0, sizeof(L));
+    double L[6][6], D[6], iD[6];
+    int bad = 0;
+    memset(L, 0, sizeof(L));
     for (int j = 0; j < 6; ++j) {
         double s = A[j][j];
-        for (int k = 0; k < j; ++k) s -= L[j][k] * L[j][k];
-        if (!(s > pivot_eps * A[j][j]) || !(A[j][j] > 0.0)) return 1;
-        L[j][j] = sqrt(s);
+        for (int k = 0; k < j; ++k) s = s - (L[j][k] * L[j][k]) * D[k];
+        if (!(s > pivot_eps * A[j][j]) || !(A[j][j] > 0.0)) bad = 1;
+        D[j] = s; iD[j] = 1.0 / s;
         for (int i = j + 1; i < 6; ++i) {
             double v = A[i][j];
-            for (int k = 0; k < j; ++k) v -= L[i][k] * L[j][k];
-            L[i][j] = v / L[j][j];
+            for (int k = 0; k < j; ++k) v = v - (L[i][k] * L[j][k]) * D[k];
+            L[i][j] = v * iD[j];
         }
     }
+    if (bad) return 1;
     double y[6];
-    for (int i = 0; i < 6; ++i) { double v = g[i]; for (int k = 0; k < i; ++k) v -= L[i][k] * y[k]; y[i] = v / L[i][i]; }
-    for (int i = 5; i >= 0; --i) { double v = y[i]; for (int k = i + 1; k < 6; ++k) v -= L[k][i] * x[k]; x[i] = v / L[i][i]; }
+    for (int i = 0; i < 6; ++i) { double v = g[i]; for (int k = 0; k < i; ++k) v = v - L[i][k] * y[k]; y[i] = v; }
+    for (int i = 5; i >= 0; --i) { double v = y[i] * iD[i]; for (int k = i + 1; k < 6; ++k) v = v - L[k][i] * x[k]; x[i] = v; }
     return 0;
 }
 
 /* R = Rz(gamma) Ry(beta) Rx(alpha) with the full sin/cos matrix (PCL constructTransformationMatrix) */
 static void euler_to_T(const double x[6], double D[12])
 {
-    double sa = sin(x[0]), ca = cos(x[0]), sb = sin(x[1]), cb = cos(x[1]), sg = sin(x[2]), cg = cos(x[2]);
+    double sa, ca, sb, cb, sg, cg;      /* orc_sincos: fixed operation order, bit-identical to the CUDA path */
+    orc_sincos(x[0], &sa, &ca); orc_sincos(x[1], &sb, &cb); orc_sincos(x[2], &sg, &cg);
     D[0] = cg * cb; D[1] = -sg * ca + cg * sb * sa; D[2] = sg * sa + cg * sb * ca;  D[3] = x[3];
     D[4] = sg * cb; D[5] = cg * ca + sg * sb * sa;  D[6] = -cg * sa + sg * sb * ca; D[7] = x[4];
     D[8] = -sb;     D[9] = cb * sa;                 D[10] = cb * ca;                D[11] = x[5];
@@ -311,6 +317,7 @@ int oracle_icp(const float *src, int n, const float *tgt, const float *tgt_nrm, 
 #ifdef _OPENMP
     if (nthreads > 0) omp_set_num_threads(nthreads);
 #endif
+    const float absP = orc_absmax3(src, n, 0), absQ = orc_absmax3(tgt, m, 0), absN = tgt_nrm ? orc_absmax3(tgt_nrm, m, 1) : 1.0f;
     kdtree *tree = kd_build(tgt, m);
     int *nn = (int *)malloc(sizeof(int) * (n > 0 ? n : 1));
     float *nd = (float *)malloc(sizeof(float) * (n > 0 ? n : 1));
@@ -324,17 +331,18 @@ int oracle_icp(const float *src, int n, const float *tgt, const float *tgt_nrm, 
             orc_xform(Tf, src[4 * i], src[4 * i + 1], src[4 * i + 2], xp + 3 * i);
             kd_query(tree, xp + 3 * i, &nn[i], &nd[i]);
         }
-        /* accumulate sequentially in double (order independent of thread count) */
-        double A[6][6]; double g[6]; memset(A, 0, sizeof(A)); memset(g, 0, sizeof(g));
-        double sp[3] = {0, 0, 0}, sq[3] = {0, 0, 0}, spq[3][3]; memset(spq, 0, sizeof(spq));
-        double sum_d2 = 0; int cnt = 0;
+        /* order-independent fixed-point sums (oracle_common.h): every product rounded once to 2^-g, integers added exactly */
+        const orc_fx fx = orc_fx_make(orc_icp_bound(absP, absQ, est == S3D_ESTIMATOR_POINT_TO_PLANE ? absN : 1.0f, T));
+        __int128 SA[6][6], Sg[6], Sp[3], Sq[3], Spq[3][3], Sd2 = 0;
+        memset(SA, 0, sizeof(SA)); memset(Sg, 0, sizeof(Sg)); memset(Sp, 0, sizeof(Sp)); memset(Sq, 0, sizeof(Sq)); memset(Spq, 0, sizeof(Spq));
+        int cnt = 0;
         for (int i = 0; i < n; ++i) {
             int j = nn[i];
             int ok = (j >= 0) && (nd[i] <= max_d2);
             if (ok && est == S3D_ESTIMATOR_POINT_TO_PLANE) ok = tgt_nrm[4 * j + 3] != 0.0f;
             if (!ok) { nn[i] = -1; continue; }
             const float *p = xp + 3 * i, *q = tgt + 4 * j;
-            ++cnt; sum_d2 += (double)nd[i];
+            ++cnt; Sd2 += orc_fx_term(&fx, nd[i], 1.0f);
             if (est == S3D_ESTIMATOR_POINT_TO_PLANE) {
                 const float *nv = tgt_nrm + 4 * j;
                 float J[6];
@@ -345,18 +353,22 @@ int oracle_icp(const float *src, int n, const float *tgt, const float *tgt_nrm, 
                 float ex = q[0] - p[0], ey = q[1] - p[1], ez = q[2] - p[2];
                 float r = fmaf(nv[2], ez, fmaf(nv[1], ey, nv[0] * ex));
                 for (int a = 0; a < 6; ++a) {
-                    for (int b = a; b < 6; ++b) A[a][b] += (double)J[a] * (double)J[b];
-                    g[a] += (double)J[a] * (double)r;
+                    for (int b = a; b < 6; ++b) SA[a][b] += orc_fx_term(&fx, J[a], J[b]);
+                    Sg[a] += orc_fx_term(&fx, J[a], r);
                 }
             } else {
                 for (int a = 0; a < 3; ++a) {
-                    sp[a] += p[a]; sq[a] += q[a];
-                    for (int b = 0; b < 3; ++b) spq[a][b] += (double)p[a] * (double)q[b];
+                    Sp[a] += orc_fx_term(&fx, p[a], 1.0f); Sq[a] += orc_fx_term(&fx, q[a], 1.0f);
+                    for (int b = 0; b < 3; ++b) Spq[a][b] += orc_fx_term(&fx, p[a], q[b]);
                 }
             }
         }
+        double A[6][6]; double g[6]; double sp[3], sq[3], spq[3][3];
+        for (int a = 0; a < 6; ++a) { for (int b = 0; b < 6; ++b) A[a][b] = orc_fx_value(&fx, SA[a][b]); g[a] = orc_fx_value(&fx, Sg[a]); }
+        for (int a = 0; a < 3; ++a) { sp[a] = orc_fx_value(&fx, Sp[a]); sq[a] = orc_fx_value(&fx, Sq[a]); for (int b = 0; b < 3; ++b) spq[a][b] = orc_fx_value(&fx, Spq[a][b]); }
+        const double sum_d2 = orc_fx_value(&fx, Sd2);
         res->inliers = cnt;
-        res->fitness = cnt ? sum_d2 / cnt : 0.0;
+        res->fitness = cnt ? sum_d2 / (double)cnt : 0.0;
         if (cnt < min_corr) { status = S3D_PAIR_FEW_CORRESPONDENCES; break; }
         double D[12];
         if (est == S3D_ESTIMATOR_POINT_TO_PLANE) {
@@ -366,8 +378,9 @@ int oracle_icp(const float *src, int n, const float *tgt, const float *tgt_nrm, 
             euler_to_T(x, D);
         } else {
             double H[3][3], R[3][3], pb[3], qb[3];
-            for (int a = 0; a < 3; ++a) { pb[a] = sp[a] / cnt; qb[a] = sq[a] / cnt; }
-            for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) H[a][b] = spq[a][b] - cnt * pb[a] * qb[b];
+            const double cnt_d = (double)cnt;
+            for (int a = 0; a < 3; ++a) { pb[a] = sp[a] / cnt_d; qb[a] = sq[a] / cnt_d; }
+            for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) H[a][b] = spq[a][b] - (cnt_d * pb[a]) * qb[b];
             /* H here is sum p q^T (rows p, cols q); kabsch_rotation expects H = U S V^T with
              * R = V U^T mapping p to q */
             kabsch_rotation(H, R);

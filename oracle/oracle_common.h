@@ -22,6 +22,7 @@
 
 #include <math.h>
 #include <stdint.h>
+#include <string.h>
 
 /* p' = R p + t with T = row-major 3x4 float */
 static inline void orc_xform(const float *T, float x, float y, float z, float *o)
@@ -116,6 +117,116 @@ static inline void orc_jacobi3(double A[3][3], double V[3][3], double w[3])
         }
     }
     for (int i = 0; i < 3; ++i) w[i] = A[i][i];
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * Order-independent sums ("fixed-point accumulation") -- part of the arithmetic contract.
+ *
+ * Every sum of the path (the 27 normal-equation sums + sum d^2 of point-to-plane ICP, the 15 Kabsch sums, the 9 PCA
+ * sums of the plane refit) is a sum of products a*b of two float32 values (b = 1 for plain sums).  a*b is exact in
+ * double.  Each product is rounded ONCE to a multiple of 2^-g (round to nearest even) and the resulting integers are
+ * added exactly, so the sum does not depend on the order of the additions: a sequential CPU loop, a GPU reduction tree
+ * of any shape and a batched launch give the same bits.
+ *   rounding:  s = fma(a, b, M) with M = 1.5 * 2^(52-g)  =>  bits(s) - bits(M) = rint(a*b * 2^g)   (|a*b| * 2^g < 2^49)
+ *   g:         49 - E with 2^E > B, B a bound on every |a*b| computed from data bounds (below); g is data dependent but
+ *              order independent (maxima of absolute values).
+ *   value:     the exact integer sum S is converted once: ((double)(S >> 32) * 2^32 + (double)(S & 0xffffffff)) * 2^-g
+ * Absolute resolution 2^-g: about 1e-11 for a room-sized scene in metres, i.e. at least as fine as plain double
+ * accumulation of 3e5 terms.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct { int g; uint64_t mbits; double scale; } orc_fx;
+
+static inline uint64_t orc_dbits(double d) { uint64_t u; memcpy(&u, &d, 8); return u; }
+static inline double orc_bitsd(uint64_t u) { double d; memcpy(&d, &u, 8); return d; }
+
+/* B: finite, > 0.  E = exponent with 2^(E-1) <= B < 2^E (from the bits of B), g = 49 - E. */
+static inline orc_fx orc_fx_make(double B)
+{
+    orc_fx f;
+    const int E = (int)((orc_dbits(B) >> 52) & 0x7ff) - 1022;
+    f.g = 49 - E;
+    f.mbits = ((uint64_t)(1075 - f.g) << 52) | ((uint64_t)1 << 51);
+    f.scale = orc_bitsd((uint64_t)(1023 - f.g) << 52);
+    return f;
+}
+static inline int64_t orc_fx_term(const orc_fx *f, float a, float b)
+{
+    return (int64_t)(orc_dbits(fma((double)a, (double)b, orc_bitsd(f->mbits))) - f->mbits);
+}
+static inline double orc_fx_value(const orc_fx *f, __int128 S)
+{
+    const int64_t H = (int64_t)(S >> 32), L = (int64_t)(S & (__int128)0xffffffff);
+    return ((double)H * 4294967296.0 + (double)L) * f->scale;
+}
+/* largest finite |component| of n rows of 4 floats (first 3 used); rows with row[3] == 0 skipped when need_w */
+static inline float orc_absmax3(const float *rows, int n, int need_w)
+{
+    float m = 0.f;
+    for (int i = 0; i < n; ++i) {
+        if (need_w && rows[4 * i + 3] == 0.0f) continue;
+        for (int k = 0; k < 3; ++k) { float a = fabsf(rows[4 * i + k]); if (a <= 3.4028234663852886e38f && a > m) m = a; }
+    }
+    return m;
+}
+/* bound on every product of one ICP iteration: source coordinates <= P, target coordinates <= Q, normal components <= Nn
+ * (1 for the SVD estimator), pose T (row-major 3x4, double).  |x| <= 3 Rm P + tm =: X; A = max(X, Q, 1), N = max(Nn, 1);
+ * |J| <= 2 N A, |r| <= 6 N A, d^2 <= 12 A^2  =>  every product <= 12 N^2 A^2 < B = 16 N^2 A^2. */
+static inline double orc_icp_bound(float P, float Q, float Nn, const double *T12)
+{
+    double Rm = 0.0, tm = 0.0;
+    for (int r = 0; r < 3; ++r) {
+        for (int c = 0; c < 3; ++c) { double a = fabs(T12[4 * r + c]); if (a > Rm) Rm = a; }
+        double a = fabs(T12[4 * r + 3]); if (a > tm) tm = a;
+    }
+    double A = 3.0 * Rm * (double)P + tm;
+    if ((double)Q > A) A = (double)Q;
+    if (!(A > 1.0)) A = 1.0;                 /* also catches NaN */
+    double N = (double)Nn > 1.0 ? (double)Nn : 1.0;
+    double B = 16.0 * (N * N) * (A * A);
+    if (!(B < 1e300)) B = 1e300;
+    return B;
+}
+/* plane refit: sums of x, y, z and their products over points with |coordinate| <= A */
+static inline double orc_pca_bound(float A)
+{
+    double a = (double)A > 1.0 ? (double)A : 1.0;
+    double B = 2.0 * (a * a);
+    if (!(B < 1e300)) B = 1e300;
+    return B;
+}
+
+/* sin and cos with a fixed operation order (Cody-Waite reduction by pi/2 in two parts, Taylor-Horner in r^2, fma):
+ * bit-identical on the CPU and on the GPU, unlike the two math libraries' sin/cos.  |x| < 2^20. */
+static inline void orc_sincos(double x, double *sn, double *cs)
+{
+    const double k = rint(x * 0.63661977236758138);                 /* 2/pi */
+    double r = fma(-k, 1.5707963267948966, x);                     /* pi/2 high */
+    r = fma(-k, 6.123233995736766e-17, r);                         /* pi/2 low  */
+    const double z = r * r;
+    double ps = -8.2206352466243295e-18;                           /* -1/19! */
+    ps = fma(ps, z, 2.8114572543455206e-15);                       /*  1/17! */
+    ps = fma(ps, z, -7.6471637318198164e-13);                      /* -1/15! */
+    ps = fma(ps, z, 1.6059043836821613e-10);                       /*  1/13! */
+    ps = fma(ps, z, -2.5052108385441720e-08);                      /* -1/11! */
+    ps = fma(ps, z, 2.7557319223985893e-06);                       /*  1/9!  */
+    ps = fma(ps, z, -1.9841269841269841e-04);                      /* -1/7!  */
+    ps = fma(ps, z, 8.3333333333333332e-03);                       /*  1/5!  */
+    ps = fma(ps, z, -1.6666666666666666e-01);                      /* -1/3!  */
+    const double s0 = fma(ps * z, r, r);
+    double pc = 4.1103176233121648e-19;                            /*  1/20! */
+    pc = fma(pc, z, -1.5619206968586226e-16);                      /* -1/18! */
+    pc = fma(pc, z, 4.7794773323873853e-14);                       /*  1/16! */
+    pc = fma(pc, z, -1.1470745597729725e-11);                      /* -1/14! */
+    pc = fma(pc, z, 2.0876756987868099e-09);                       /*  1/12! */
+    pc = fma(pc, z, -2.7557319223985888e-07);                      /* -1/10! */
+    pc = fma(pc, z, 2.4801587301587302e-05);                       /*  1/8!  */
+    pc = fma(pc, z, -1.3888888888888889e-03);                      /* -1/6!  */
+    pc = fma(pc, z, 4.1666666666666664e-02);                       /*  1/4!  */
+    pc = fma(pc, z, -0.5);
+    const double c0 = fma(pc, z, 1.0);
+    const long long q = (long long)k & 3;
+    *sn = q == 0 ? s0 : q == 1 ? c0 : q == 2 ? -s0 : -c0;
+    *cs = q == 0 ? c0 : q == 1 ? -s0 : q == 2 ? -c0 : s0;
 }
 
 #endif

@@ -69,6 +69,7 @@ int oracle_segment_planes(const float *xyzw, int n, const s3d_plane_params *prm,
     const float tau = prm->distance_threshold;
     int *rem = (int *)malloc(sizeof(int) * (n > 0 ? n : 1)); /* original indices of remaining points, in order */
     int n_rem = n, n_planes = 0;
+    const orc_fx fx = orc_fx_make(orc_pca_bound(orc_absmax3(xyzw, n, 0)));
     for (int i = 0; i < n; ++i) { rem[i] = i; labels_out[i] = -1; }
     if (normals_out) memset(normals_out, 0, sizeof(float) * 4 * n);
     int *valid = (int *)malloc(sizeof(int) * n_cand), *count = (int *)malloc(sizeof(int) * n_cand);
@@ -94,22 +95,27 @@ int oracle_segment_planes(const float *xyzw, int n, const s3d_plane_params *prm,
         if (best < 0 || count[best] == 0) break; /* :376-379 */
         /* optimizeModelCoefficients: PCA over the inliers of the best model */
         const float *bc = coefs + 4 * best;
-        double s1[3] = {0, 0, 0}, s2[6] = {0, 0, 0, 0, 0, 0}; int ni = 0;
+        /* order-independent fixed-point sums (oracle_common.h), resolution from the largest coordinate of the cloud */
+        __int128 S1[3] = {0, 0, 0}, S2[6] = {0, 0, 0, 0, 0, 0}; int ni = 0;
         for (int i = 0; i < n_rem; ++i) {
             const float *p = xyzw + 4 * rem[i];
             if (fabsf(orc_plane_eval(bc, p[0], p[1], p[2])) < tau) {
-                double x = p[0], y = p[1], z = p[2];
-                s1[0] += x; s1[1] += y; s1[2] += z;
-                s2[0] += x * x; s2[1] += x * y; s2[2] += x * z; s2[3] += y * y; s2[4] += y * z; s2[5] += z * z;
+                S1[0] += orc_fx_term(&fx, p[0], 1.0f); S1[1] += orc_fx_term(&fx, p[1], 1.0f); S1[2] += orc_fx_term(&fx, p[2], 1.0f);
+                S2[0] += orc_fx_term(&fx, p[0], p[0]); S2[1] += orc_fx_term(&fx, p[0], p[1]); S2[2] += orc_fx_term(&fx, p[0], p[2]);
+                S2[3] += orc_fx_term(&fx, p[1], p[1]); S2[4] += orc_fx_term(&fx, p[1], p[2]); S2[5] += orc_fx_term(&fx, p[2], p[2]);
                 ++ni;
             }
         }
+        double s1[3], s2[6];
+        for (int k = 0; k < 3; ++k) s1[k] = orc_fx_value(&fx, S1[k]);
+        for (int k = 0; k < 6; ++k) s2[k] = orc_fx_value(&fx, S2[k]);
         float rc[4] = {bc[0], bc[1], bc[2], bc[3]};
         if (ni >= 3) { /* PCL needs > 3 inliers to refit; with fewer the RANSAC model is kept */
-            double cx = s1[0] / ni, cy = s1[1] / ni, cz = s1[2] / ni;
+            const double nd = (double)ni;
+            double cx = s1[0] / nd, cy = s1[1] / nd, cz = s1[2] / nd;
             double C[3][3], V[3][3], w[3];
-            C[0][0] = s2[0] / ni - cx * cx; C[0][1] = C[1][0] = s2[1] / ni - cx * cy; C[0][2] = C[2][0] = s2[2] / ni - cx * cz;
-            C[1][1] = s2[3] / ni - cy * cy; C[1][2] = C[2][1] = s2[4] / ni - cy * cz; C[2][2] = s2[5] / ni - cz * cz;
+            C[0][0] = s2[0] / nd - cx * cx; C[0][1] = C[1][0] = s2[1] / nd - cx * cy; C[0][2] = C[2][0] = s2[2] / nd - cx * cz;
+            C[1][1] = s2[3] / nd - cy * cy; C[1][2] = C[2][1] = s2[4] / nd - cy * cz; C[2][2] = s2[5] / nd - cz * cz;
             orc_jacobi3(C, V, w);
             int k = 0; if (w[1] < w[k]) k = 1; if (w[2] < w[k]) k = 2;
             double nx = V[0][k], ny = V[1][k], nz = V[2][k];

@@ -34,6 +34,11 @@ class Timing(C.Structure):
                 ("total_launches", C.c_int32)]
 
 
+class PlaneTiming(C.Structure):
+    _fields_ = [("total_ms", C.c_float), ("eval_ms", C.c_float), ("rounds", C.c_int32), ("eval_passes_per_round", C.c_int32),
+                ("points_scanned", C.c_int64), ("reserved", C.c_int64)]
+
+
 ESTIMATOR_POINT_TO_PLANE, ESTIMATOR_SVD = 0, 1
 SEARCH_GRID, SEARCH_BRUTE, SEARCH_GRID_LANE = 0, 1, 2
 PAIR_OK, PAIR_FEW, PAIR_DEGENERATE, PAIR_NONFINITE = 0, 1, 2, 3

@@ -34,7 +34,7 @@ EXPORTS = [
     "s3d_last_correspondences", "s3d_last_timing", "s3d_icp_params_default", "s3d_plane_params_default",
     "s3d_planar_keypoints", "s3d_gather_results", "s3d_cloud_passthrough_z", "s3d_cloud_voxel_grid", "s3d_cloud_transform",
     "s3d_cloud_concat", "s3d_map_fuse", "s3d_cloud_from_depth_normals", "s3d_cloud_upload_async", "s3d_cloud_wait", "s3d_host_alloc", "s3d_host_free",
-    "s3d_memory_stats", "s3d_comm_unique_id", "s3d_comm_create", "s3d_comm_destroy", "s3d_register_batch_gather",
+    "s3d_memory_stats", "s3d_last_plane_timing", "s3d_comm_unique_id", "s3d_comm_create", "s3d_comm_destroy", "s3d_register_batch_gather",
 ]
 COMM_ID_BYTES = 128
 
@@ -88,6 +88,7 @@ def load_library():
     lib.s3d_plane_params_default.restype = None
     lib.s3d_planar_keypoints.argtypes = [vp, vp, ci, ci, C.POINTER(_abi.CameraC), vp, ci, C.c_float, ci, C.c_uint64, vp]
     lib.s3d_gather_results.argtypes = [vp, vp, C.POINTER(_abi.Result), ci, ci, C.POINTER(_abi.Result)]
+    lib.s3d_last_plane_timing.argtypes = [vp, C.POINTER(_abi.PlaneTiming)]
     lib.s3d_memory_stats.argtypes = [vp, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
     lib.s3d_comm_unique_id.argtypes = [vp]
     lib.s3d_comm_create.argtypes = [vp, vp, ci, ci, C.POINTER(vp)]
@@ -363,6 +364,12 @@ class Context:
         self.lib.s3d_last_timing(self.h, C.byref(t))
         return dict(index_ms=t.index_ms, iterate_ms=t.iterate_ms, iter_launches=t.iter_launches,
                     total_launches=t.total_launches)
+
+    def last_plane_timing(self) -> dict:
+        t = _abi.PlaneTiming()
+        self.lib.s3d_last_plane_timing(self.h, C.byref(t))
+        return dict(total_ms=t.total_ms, eval_ms=t.eval_ms, rounds=t.rounds, eval_passes_per_round=t.eval_passes_per_round,
+                    points_scanned=t.points_scanned)
 
     def planar_keypoints(self, depth: np.ndarray, cam, uv: np.ndarray, threshold=0.01, min_inliers=40, seed=12345):
         """isPlanar (reference src/planarFeatures.cpp:88-136) for a batch of keypoints."""

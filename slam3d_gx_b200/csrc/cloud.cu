@@ -7,6 +7,7 @@
 #include <cstring>
 #include <cmath>
 #include <iterator>
+#include <algorithm>
 #include "context.h"
 #include "compact.cuh"
 
@@ -139,6 +140,8 @@ extern "C" void s3d_destroy(s3d_ctx *ctx)
     ctx->pool_live.clear();
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     for (int i = 0; i < 4; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    for (int i = 0; i < 2; ++i) if (ctx->ev_plane[i]) cudaEventDestroy(ctx->ev_plane[i]);
+    for (int i = 0; i < 2 * S3D_MAX_PLANES; ++i) if (ctx->ev_eval[i]) cudaEventDestroy(ctx->ev_eval[i]);
     if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); cudaEventDestroy(ctx->copy_fence); }
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
@@ -216,6 +219,44 @@ extern "C" int s3d_cloud_upload(s3d_ctx *ctx, const float *xyz, int stride_float
     if (tmp) { cudaStreamSynchronize(ctx->stream); s3d_dev_free(ctx, tmp); }
     if (rc) { s3d_cloud_free(ctx, c); return rc; }
     *out = c;
+    return S3D_OK;
+}
+
+// largest finite |x|, |y|, |z| over the rows (rows with w == 0 skipped when need_w): a maximum, hence independent of the
+// order in which threads see the rows.  Non-negative floats order like their bit patterns.
+__global__ void __launch_bounds__(256) absmax_kernel(const float4 *__restrict__ rows, int n, int need_w, float *__restrict__ out)
+{
+    float m = 0.f;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float4 p = rows[i];
+        if (need_w && p.w == 0.f) continue;
+        const float a = fabsf(p.x), b = fabsf(p.y), c = fabsf(p.z);
+        if (a <= 3.4028234663852886e38f && a > m) m = a;
+        if (b <= 3.4028234663852886e38f && b > m) m = b;
+        if (c <= 3.4028234663852886e38f && c > m) m = c;
+    }
+    #pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(reinterpret_cast<unsigned int *>(out), __float_as_uint(m));
+}
+
+int s3d_cloud_absmax(s3d_ctx *ctx, const s3d_cloud *cloud, bool want_normals)
+{
+    if (!cloud->d_absmax) {
+        S3D_CUDA(ctx, s3d_dev_alloc_t(ctx, &cloud->d_absmax, 2 * sizeof(float)));
+        cloud->absmax_pts_valid = cloud->absmax_nrm_valid = false;
+    }
+    const int blocks = std::max(1, std::min(ctx->sm_count * 4, (cloud->n + 255) / 256));
+    if (!cloud->absmax_pts_valid) {
+        S3D_CUDA(ctx, cudaMemsetAsync(cloud->d_absmax, 0, sizeof(float), ctx->stream));
+        if (cloud->n > 0) { absmax_kernel<<<blocks, 256, 0, ctx->stream>>>(cloud->d_pts, cloud->n, 0, cloud->d_absmax); S3D_LAUNCHED(ctx); }
+        cloud->absmax_pts_valid = true;
+    }
+    if (want_normals && !cloud->absmax_nrm_valid) {
+        S3D_CUDA(ctx, cudaMemsetAsync(cloud->d_absmax + 1, 0, sizeof(float), ctx->stream));
+        if (cloud->n > 0 && cloud->d_nrm) { absmax_kernel<<<blocks, 256, 0, ctx->stream>>>(cloud->d_nrm, cloud->n, 1, cloud->d_absmax + 1); S3D_LAUNCHED(ctx); }
+        cloud->absmax_nrm_valid = true;
+    }
     return S3D_OK;
 }
 
@@ -398,6 +439,7 @@ extern "C" int s3d_cloud_set_normals(s3d_ctx *ctx, s3d_cloud *cloud, const float
         s3d_dev_free(ctx, tmp);
     }
     cloud->grid.valid = false; // sorted normals are stale
+    cloud->absmax_nrm_valid = false;
     return S3D_OK;
 }
 
@@ -414,6 +456,7 @@ extern "C" int s3d_cloud_set_normals_device(s3d_ctx *ctx, s3d_cloud *cloud, cons
         S3D_LAUNCHED(ctx);
     }
     cloud->grid.valid = false;
+    cloud->absmax_nrm_valid = false;
     return S3D_OK;
 }
 
@@ -477,5 +520,6 @@ extern "C" void s3d_cloud_free(s3d_ctx *ctx, s3d_cloud *cloud)
     s3d_grid_free(ctx, cloud->coarse);
     s3d_dev_free(ctx, cloud->d_coarse_pts);
     s3d_dev_free(ctx, cloud->d_pts); s3d_dev_free(ctx, cloud->d_nrm); s3d_dev_free(ctx, cloud->d_labels);
+    s3d_dev_free(ctx, cloud->d_absmax);
     delete cloud;
 }

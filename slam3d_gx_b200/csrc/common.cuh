@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <math.h>
+#include <string.h>
 
 #define S3D_NACC 32          // accumulator slots per pair (29 used)
 #define S3D_ACC_SUMD2 27
@@ -78,32 +79,149 @@ __device__ __forceinline__ bool s3d_plane_from3(float3 p0, float3 p1, float3 p2,
     return true;
 }
 
-// cyclic Jacobi on a symmetric 3x3 in double, fixed 12 sweeps (same control flow as orc_jacobi3)
-__device__ inline void s3d_jacobi3(double A[3][3], double V[3][3], double w[3])
+// ------------------------------------------------------------------------------------------------
+// Strict double: every operation is one correctly rounded IEEE operation, never contracted into an FMA and never
+// reassociated, so the small dense solvers below perform exactly the operations of their restatement in
+// oracle/icp_oracle.c / oracle/plane_oracle.c (compiled with -ffp-contract=off): poses and plane coefficients are
+// bit-identical between the CUDA path and the oracle.
+// ------------------------------------------------------------------------------------------------
+struct sd {
+    double v;
+    __host__ __device__ sd() {}
+    __host__ __device__ sd(double x) : v(x) {}
+};
+__device__ __forceinline__ sd operator+(sd a, sd b) { return sd(__dadd_rn(a.v, b.v)); }
+__device__ __forceinline__ sd operator-(sd a, sd b) { return sd(__dsub_rn(a.v, b.v)); }
+__device__ __forceinline__ sd operator*(sd a, sd b) { return sd(__dmul_rn(a.v, b.v)); }
+__device__ __forceinline__ sd operator/(sd a, sd b) { return sd(__ddiv_rn(a.v, b.v)); }
+__device__ __forceinline__ sd operator-(sd a) { return sd(-a.v); }
+__device__ __forceinline__ bool operator<(sd a, sd b) { return a.v < b.v; }
+__device__ __forceinline__ bool operator>(sd a, sd b) { return a.v > b.v; }
+__device__ __forceinline__ bool operator>=(sd a, sd b) { return a.v >= b.v; }
+__device__ __forceinline__ sd sd_sqrt(sd a) { return sd(__dsqrt_rn(a.v)); }
+__device__ __forceinline__ sd sd_fabs(sd a) { return sd(fabs(a.v)); }
+
+// cyclic Jacobi on a symmetric 3x3 in strict double, fixed 12 sweeps (same operations as orc_jacobi3)
+__device__ inline void s3d_jacobi3(sd A[3][3], sd V[3][3], sd w[3])
 {
-    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) V[i][j] = (i == j);
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) V[i][j] = sd(i == j ? 1.0 : 0.0);
     for (int sweep = 0; sweep < 12; ++sweep) {
         for (int p = 0; p < 2; ++p) for (int q = p + 1; q < 3; ++q) {
-            double apq = A[p][q];
-            if (fabs(apq) < 1e-300) continue;
-            double theta = (A[q][q] - A[p][p]) / (2.0 * apq);
-            double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
-            double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+            sd apq = A[p][q];
+            if (fabs(apq.v) < 1e-300) continue;
+            sd theta = (A[q][q] - A[p][p]) / (sd(2.0) * apq);
+            sd t = sd(theta.v >= 0 ? 1.0 : -1.0) / (sd_fabs(theta) + sd_sqrt(theta * theta + sd(1.0)));
+            sd c = sd(1.0) / sd_sqrt(t * t + sd(1.0)), s = t * c;
             for (int k = 0; k < 3; ++k) {
-                double akp = A[k][p], akq = A[k][q];
+                sd akp = A[k][p], akq = A[k][q];
                 A[k][p] = c * akp - s * akq; A[k][q] = s * akp + c * akq;
             }
             for (int k = 0; k < 3; ++k) {
-                double apk = A[p][k], aqk = A[q][k];
+                sd apk = A[p][k], aqk = A[q][k];
                 A[p][k] = c * apk - s * aqk; A[q][k] = s * apk + c * aqk;
             }
             for (int k = 0; k < 3; ++k) {
-                double vkp = V[k][p], vkq = V[k][q];
+                sd vkp = V[k][p], vkq = V[k][q];
                 V[k][p] = c * vkp - s * vkq; V[k][q] = s * vkp + c * vkq;
             }
         }
     }
     for (int i = 0; i < 3; ++i) w[i] = A[i][i];
+}
+
+// sin and cos with the fixed operation order of orc_sincos (oracle/oracle_common.h): bit-identical to the oracle
+__device__ inline void s3d_sincos(double x, double *sn, double *cs)
+{
+    const double k = rint(__dmul_rn(x, 0.63661977236758138));
+    double r = __fma_rn(-k, 1.5707963267948966, x);
+    r = __fma_rn(-k, 6.123233995736766e-17, r);
+    const double z = __dmul_rn(r, r);
+    double ps = -8.2206352466243295e-18;
+    ps = __fma_rn(ps, z, 2.8114572543455206e-15);
+    ps = __fma_rn(ps, z, -7.6471637318198164e-13);
+    ps = __fma_rn(ps, z, 1.6059043836821613e-10);
+    ps = __fma_rn(ps, z, -2.5052108385441720e-08);
+    ps = __fma_rn(ps, z, 2.7557319223985893e-06);
+    ps = __fma_rn(ps, z, -1.9841269841269841e-04);
+    ps = __fma_rn(ps, z, 8.3333333333333332e-03);
+    ps = __fma_rn(ps, z, -1.6666666666666666e-01);
+    const double s0 = __fma_rn(__dmul_rn(ps, z), r, r);
+    double pc = 4.1103176233121648e-19;
+    pc = __fma_rn(pc, z, -1.5619206968586226e-16);
+    pc = __fma_rn(pc, z, 4.7794773323873853e-14);
+    pc = __fma_rn(pc, z, -1.1470745597729725e-11);
+    pc = __fma_rn(pc, z, 2.0876756987868099e-09);
+    pc = __fma_rn(pc, z, -2.7557319223985888e-07);
+    pc = __fma_rn(pc, z, 2.4801587301587302e-05);
+    pc = __fma_rn(pc, z, -1.3888888888888889e-03);
+    pc = __fma_rn(pc, z, 4.1666666666666664e-02);
+    pc = __fma_rn(pc, z, -0.5);
+    const double c0 = __fma_rn(pc, z, 1.0);
+    const long long q = (long long)k & 3;
+    *sn = q == 0 ? s0 : q == 1 ? c0 : q == 2 ? -s0 : -c0;
+    *cs = q == 0 ? c0 : q == 1 ? -s0 : q == 2 ? -c0 : s0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Order-independent sums (the contract is written down in oracle/oracle_common.h): every product a*b of two float32
+// values is rounded once to a multiple of 2^-g by s = fma(a, b, M), M = 1.5 * 2^(52-g); bits(s) - bits(M) is the integer
+// rint(a*b*2^g) and integers add exactly.  A thread adds the raw bits of s (wrapping int64) and removes count * bits(M)
+// when it hands its partial sums on; partial sums travel as (hi, lo) pairs of int64 with value hi * 2^32 + lo, which any
+// number of adds in any order cannot overflow; the total becomes a double once, (double)hi * 2^32 + (double)lo, scaled by 2^-g.
+// ------------------------------------------------------------------------------------------------
+struct FxScale { unsigned long long mbits; double scale; int g; };
+
+__host__ __device__ __forceinline__ FxScale s3d_fx_make(double B)      // 2^(E-1) <= B < 2^E, g = 49 - E
+{
+    FxScale f;
+#ifdef __CUDA_ARCH__
+    const unsigned long long bb = (unsigned long long)__double_as_longlong(B);
+#else
+    unsigned long long bb; memcpy(&bb, &B, 8);
+#endif
+    const int E = (int)((bb >> 52) & 0x7ff) - 1022;
+    f.g = 49 - E;
+    f.mbits = ((unsigned long long)(1075 - f.g) << 52) | (1ull << 51);
+    const unsigned long long sb = (unsigned long long)(1023 - f.g) << 52;
+#ifdef __CUDA_ARCH__
+    f.scale = __longlong_as_double((long long)sb);
+#else
+    memcpy(&f.scale, &sb, 8);
+#endif
+    return f;
+}
+// raw bits of fma(a, b, M): what a thread accumulates (wrapping)
+__device__ __forceinline__ long long s3d_fx_bits(double a, double b, double M) { return __double_as_longlong(__fma_rn(a, b, M)); }
+// a partial sum v (true value fits int64) -> its (hi, lo) contribution
+__device__ __forceinline__ void s3d_fx_split(long long v, long long &hi, long long &lo) { hi = v >> 32; lo = v & 0xffffffffll; }
+__device__ __forceinline__ double s3d_fx_value(long long hi, long long lo, double scale)
+{
+    return __dmul_rn(__dadd_rn(__dmul_rn(__ll2double_rn(hi), 4294967296.0), __ll2double_rn(lo)), scale);
+}
+// bound on every product of one ICP iteration (orc_icp_bound): strict operations, identical bits on both sides
+__device__ __forceinline__ double s3d_icp_bound(float P, float Q, float Nn, const double *T12)
+{
+    double Rm = 0.0, tm = 0.0;
+    #pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        #pragma unroll
+        for (int c = 0; c < 3; ++c) { const double a = fabs(T12[4 * r + c]); if (a > Rm) Rm = a; }
+        const double a = fabs(T12[4 * r + 3]); if (a > tm) tm = a;
+    }
+    double A = __dadd_rn(__dmul_rn(__dmul_rn(3.0, Rm), (double)P), tm);
+    if ((double)Q > A) A = (double)Q;
+    if (!(A > 1.0)) A = 1.0;
+    const double N = (double)Nn > 1.0 ? (double)Nn : 1.0;
+    double B = __dmul_rn(__dmul_rn(16.0, __dmul_rn(N, N)), __dmul_rn(A, A));
+    if (!(B < 1e300)) B = 1e300;
+    return B;
+}
+__device__ __forceinline__ double s3d_pca_bound(float A)
+{
+    const double a = (double)A > 1.0 ? (double)A : 1.0;
+    double B = __dmul_rn(2.0, __dmul_rn(a, a));
+    if (!(B < 1e300)) B = 1e300;
+    return B;
 }
 
 __device__ __forceinline__ float warp_sum(float v)

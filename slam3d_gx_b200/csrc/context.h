@@ -56,6 +56,10 @@ struct s3d_cloud {
     cudaEvent_t ready = nullptr;
     float *d_stage = nullptr;     // rows as the host holds them (stride != 4), until the cloud is freed
     mutable int unpacked_stride = 0;   // != 0: the rows still have to be packed into float4 (x,y,z,1), on the ctx stream, at first use
+    // largest finite |coordinate| of the points [0] and largest finite |component| of the valid normals [1]: the data
+    // bounds behind the resolution of the order-independent sums (common.cuh); computed on the device at first use
+    mutable float *d_absmax = nullptr;
+    mutable bool absmax_pts_valid = false, absmax_nrm_valid = false;
 };
 
 // one registration unit as the kernels see it
@@ -65,6 +69,7 @@ struct PairDesc {
     const float4 *sorted_pts; const float4 *sorted_nrm;             // grid order
     const uint32_t *cell_start; const GridParams *grid; const uint32_t *rowmask;
     const float4 *coarse_pts; const uint32_t *coarse_cell_start; const uint32_t *coarse_rowmask; const GridParams *coarse_grid;  // null when absent
+    const float *src_absmax; const float *tgt_absmax;               // s3d_cloud::d_absmax of the two clouds
 };
 
 struct PairState {
@@ -91,7 +96,7 @@ struct s3d_ctx {
     int cap_pairs = 0, cap_ctas = 0;
     PairDesc *d_desc = nullptr; PairDesc *h_desc = nullptr;
     PairState *d_state = nullptr; PairState *h_state = nullptr;
-    double *d_partials = nullptr;     // [pairs][ctas][S3D_NACC]
+    long long *d_partials = nullptr;  // [pairs][ctas][S3D_ROW]: (hi, lo) partial sums of the order-independent accumulation
     // brute-force scratch + last-correspondence buffer
     int cap_nn = 0;
     int32_t *d_nn_idx = nullptr; float *d_nn_d2 = nullptr; int32_t *d_nn_pos = nullptr;
@@ -107,6 +112,9 @@ struct s3d_ctx {
     size_t cap_gather_send = 0, cap_gather_recv = 0, cap_gather_host = 0;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     s3d_timing timing = {0, 0, 0, 0};
+    cudaEvent_t ev_plane[2] = {nullptr, nullptr};
+    cudaEvent_t ev_eval[2 * S3D_MAX_PLANES] = {};       // around the evaluation pass of each RANSAC round
+    s3d_plane_timing plane_timing = {0, 0, 0, 0, 0, 0};
     // plane segmentation scratch
     size_t cap_seg = 0;
     void *d_seg = nullptr;
@@ -132,6 +140,8 @@ void s3d_dev_pool_release(s3d_ctx *ctx);
 template <typename T> static inline cudaError_t s3d_dev_alloc_t(s3d_ctx *ctx, T **out, size_t bytes) { return s3d_dev_alloc(ctx, reinterpret_cast<void **>(out), bytes); }
 // cloud.cu: orders the ctx stream behind a cloud's asynchronous upload and packs its rows (no-op for every other cloud)
 int s3d_cloud_ready(s3d_ctx *ctx, const s3d_cloud *cloud);
+// cloud.cu: makes cloud->d_absmax valid on the ctx stream (a small reduction kernel the first time, nothing afterwards)
+int s3d_cloud_absmax(s3d_ctx *ctx, const s3d_cloud *cloud, bool want_normals);
 // icp.cu: the two halves of s3d_register_batch (enqueue everything / read the event times after a synchronisation),
 // the host-side completion of a record (norm, failure convention) and the device-side packing of the records
 int s3d_register_issue(s3d_ctx *ctx, const s3d_cloud *const *src, const s3d_cloud *const *tgt, const double *guess, int n_pairs,

@@ -141,82 +141,83 @@ __global__ void __launch_bounds__(ICP_BLOCK) nn_brute_tma_kernel(const PairDesc 
 // ------------------------------------------------------------------------------------------------
 // small dense solvers (double, one thread) -- same algorithms as oracle/icp_oracle.c
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ int chol6_solve(const double A[6][6], const double g[6], double pivot_eps, double x[6])
+__device__ __forceinline__ int chol6_solve(const sd A[6][6], const sd g[6], double pivot_eps, sd x[6])
 {
     // Square-root-free Cholesky (A = L D L^T), fully unrolled: every index is a compile-time constant, so L, D, y live
-    // in registers, and the dependent chain is 6 reciprocals instead of 6 square roots + 21 divisions.  The pivots D[j]
-    // are exactly the quantities chol6_solve of oracle/icp_oracle.c tests (its s = L[j][j]^2), so the rank-deficiency
-    // verdict is the same; the solution agrees to rounding.
-    double L[6][6], D[6], iD[6];
+    // in registers, and the dependent chain is 6 reciprocals instead of 6 square roots + 21 divisions.  Strict double
+    // (common.cuh): the same IEEE operations in the same order as chol6_solve of oracle/icp_oracle.c -- identical bits,
+    // including the rank-deficiency verdict.
+    sd L[6][6], D[6], iD[6];
     int bad = 0;
     #pragma unroll
     for (int j = 0; j < 6; ++j) {
-        double s = A[j][j];
+        sd s = A[j][j];
         #pragma unroll
-        for (int k = 0; k < j; ++k) s -= L[j][k] * L[j][k] * D[k];
-        if (!(s > pivot_eps * A[j][j]) || !(A[j][j] > 0.0)) bad = 1;
-        D[j] = s; iD[j] = 1.0 / s;
+        for (int k = 0; k < j; ++k) s = s - (L[j][k] * L[j][k]) * D[k];
+        if (!(s.v > __dmul_rn(pivot_eps, A[j][j].v)) || !(A[j][j].v > 0.0)) bad = 1;
+        D[j] = s; iD[j] = sd(1.0) / s;
         #pragma unroll
         for (int i = j + 1; i < 6; ++i) {
-            double v = A[i][j];
+            sd v = A[i][j];
             #pragma unroll
-            for (int k = 0; k < j; ++k) v -= L[i][k] * L[j][k] * D[k];
+            for (int k = 0; k < j; ++k) v = v - (L[i][k] * L[j][k]) * D[k];
             L[i][j] = v * iD[j];
         }
     }
     if (bad) return 1;
-    double y[6];
+    sd y[6];
     #pragma unroll
     for (int i = 0; i < 6; ++i) {
-        double v = g[i];
+        sd v = g[i];
         #pragma unroll
-        for (int k = 0; k < i; ++k) v -= L[i][k] * y[k];
+        for (int k = 0; k < i; ++k) v = v - L[i][k] * y[k];
         y[i] = v;
     }
     #pragma unroll
     for (int i = 5; i >= 0; --i) {
-        double v = y[i] * iD[i];
+        sd v = y[i] * iD[i];
         #pragma unroll
-        for (int k = i + 1; k < 6; ++k) v -= L[k][i] * x[k];
+        for (int k = i + 1; k < 6; ++k) v = v - L[k][i] * x[k];
         x[i] = v;
     }
     return 0;
 }
 
-__device__ void euler_to_T(const double x[6], double D[12])
+__device__ void euler_to_T(const sd x[6], sd D[12])
 {
-    double sa, ca, sb, cb, sg, cg;
-    sincos(x[0], &sa, &ca); sincos(x[1], &sb, &cb); sincos(x[2], &sg, &cg);
+    double sa_, ca_, sb_, cb_, sg_, cg_;
+    s3d_sincos(x[0].v, &sa_, &ca_); s3d_sincos(x[1].v, &sb_, &cb_); s3d_sincos(x[2].v, &sg_, &cg_);
+    const sd sa(sa_), ca(ca_), sb(sb_), cb(cb_), sg(sg_), cg(cg_);
     D[0] = cg * cb; D[1] = -sg * ca + cg * sb * sa; D[2] = sg * sa + cg * sb * ca;  D[3] = x[3];
     D[4] = sg * cb; D[5] = cg * ca + sg * sb * sa;  D[6] = -cg * sa + sg * sb * ca; D[7] = x[4];
     D[8] = -sb;     D[9] = cb * sa;                 D[10] = cb * ca;                D[11] = x[5];
 }
 
-__device__ void kabsch_rotation(double H[3][3], double R[3][3])
+__device__ void kabsch_rotation(sd H[3][3], sd R[3][3])
 {
-    double HtH[3][3], V[3][3], w[3];
+    sd HtH[3][3], V[3][3], w[3];
     for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) {
-        double s = 0; for (int k = 0; k < 3; ++k) s += H[k][i] * H[k][j];
+        sd s(0.0); for (int k = 0; k < 3; ++k) s = s + H[k][i] * H[k][j];
         HtH[i][j] = s;
     }
     s3d_jacobi3(HtH, V, w);
     int ord[3] = {0, 1, 2};
     for (int a = 0; a < 2; ++a) for (int b = a + 1; b < 3; ++b) if (w[ord[b]] > w[ord[a]]) { int t = ord[a]; ord[a] = ord[b]; ord[b] = t; }
-    double Vs[3][3], U[3][3];
+    sd Vs[3][3], U[3][3];
     for (int c = 0; c < 3; ++c) for (int r = 0; r < 3; ++r) Vs[r][c] = V[r][ord[c]];
     for (int c = 0; c < 2; ++c) {
-        double u[3] = {0, 0, 0};
-        for (int r = 0; r < 3; ++r) for (int k = 0; k < 3; ++k) u[r] += H[r][k] * Vs[k][c];
-        double n = sqrt(u[0] * u[0] + u[1] * u[1] + u[2] * u[2]);
-        if (n < 1e-300) n = 1;
+        sd u[3] = {sd(0.0), sd(0.0), sd(0.0)};
+        for (int r = 0; r < 3; ++r) for (int k = 0; k < 3; ++k) u[r] = u[r] + H[r][k] * Vs[k][c];
+        sd n = sd_sqrt(u[0] * u[0] + u[1] * u[1] + u[2] * u[2]);
+        if (n.v < 1e-300) n = sd(1.0);
         for (int r = 0; r < 3; ++r) U[r][c] = u[r] / n;
     }
     {
-        double d = U[0][0] * U[0][1] + U[1][0] * U[1][1] + U[2][0] * U[2][1];
-        for (int r = 0; r < 3; ++r) U[r][1] -= d * U[r][0];
-        double n = sqrt(U[0][1] * U[0][1] + U[1][1] * U[1][1] + U[2][1] * U[2][1]);
-        if (n < 1e-300) n = 1;
-        for (int r = 0; r < 3; ++r) U[r][1] /= n;
+        sd d = U[0][0] * U[0][1] + U[1][0] * U[1][1] + U[2][0] * U[2][1];
+        for (int r = 0; r < 3; ++r) U[r][1] = U[r][1] - d * U[r][0];
+        sd n = sd_sqrt(U[0][1] * U[0][1] + U[1][1] * U[1][1] + U[2][1] * U[2][1]);
+        if (n.v < 1e-300) n = sd(1.0);
+        for (int r = 0; r < 3; ++r) U[r][1] = U[r][1] / n;
     }
     U[0][2] = U[1][0] * U[2][1] - U[2][0] * U[1][1];
     U[1][2] = U[2][0] * U[0][1] - U[0][0] * U[2][1];
@@ -225,36 +226,38 @@ __device__ void kabsch_rotation(double H[3][3], double R[3][3])
     Vs[1][2] = Vs[2][0] * Vs[0][1] - Vs[0][0] * Vs[2][1];
     Vs[2][2] = Vs[0][0] * Vs[1][1] - Vs[1][0] * Vs[0][1];
     for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) {
-        double s = 0; for (int k = 0; k < 3; ++k) s += Vs[i][k] * U[j][k];
+        sd s(0.0); for (int k = 0; k < 3; ++k) s = s + Vs[i][k] * U[j][k];
         R[i][j] = s;
     }
 }
 
-// consumes the summed accumulators of one pair, updates its state (runs in one thread)
+// consumes the summed accumulators of one pair (already converted to double by s3d_fx_value), updates its state
+// (runs in one thread).  Strict double throughout: bit-identical to the tail of oracle_icp's iteration.
 template <int EST>
 __device__ __noinline__ void solve_and_update(const double *acc, PairState *st, int min_corr, double pivot_eps)
 {
     const double cnt_d = acc[S3D_ACC_COUNT];
     const int cnt = (int)(cnt_d + 0.5);
     st->inliers = cnt;
-    st->fitness = cnt > 0 ? acc[S3D_ACC_SUMD2] / cnt_d : 0.0;
+    st->fitness = cnt > 0 ? __ddiv_rn(acc[S3D_ACC_SUMD2], cnt_d) : 0.0;
     if (cnt < min_corr) { st->status = S3D_PAIR_FEW_CORRESPONDENCES; return; }
-    double D[12];
+    sd D[12];
     if (EST == S3D_ESTIMATOR_POINT_TO_PLANE) {
-        double A[6][6], g[6], x[6];
+        sd A[6][6], g[6], x[6];
         #pragma unroll
         for (int a = 0; a < 6; ++a) {
             #pragma unroll
-            for (int b = a; b < 6; ++b) { const int k = a * 6 - (a * (a - 1)) / 2 + (b - a); A[a][b] = acc[k]; A[b][a] = acc[k]; }
+            for (int b = a; b < 6; ++b) { const int k = a * 6 - (a * (a - 1)) / 2 + (b - a); A[a][b] = sd(acc[k]); A[b][a] = sd(acc[k]); }
         }
         #pragma unroll
-        for (int a = 0; a < 6; ++a) g[a] = acc[21 + a];
+        for (int a = 0; a < 6; ++a) g[a] = sd(acc[21 + a]);
         if (chol6_solve(A, g, pivot_eps, x)) { st->status = S3D_PAIR_DEGENERATE; return; }
         euler_to_T(x, D);
     } else {
-        double H[3][3], R[3][3], pb[3], qb[3];
-        for (int a = 0; a < 3; ++a) { pb[a] = acc[a] / cnt_d; qb[a] = acc[3 + a] / cnt_d; }
-        for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) H[a][b] = acc[6 + 3 * a + b] - cnt_d * pb[a] * qb[b];
+        sd H[3][3], R[3][3], pb[3], qb[3];
+        const sd cn(cnt_d);
+        for (int a = 0; a < 3; ++a) { pb[a] = sd(acc[a]) / cn; qb[a] = sd(acc[3 + a]) / cn; }
+        for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) H[a][b] = sd(acc[6 + 3 * a + b]) - (cn * pb[a]) * qb[b];
         kabsch_rotation(H, R);
         for (int a = 0; a < 3; ++a) {
             for (int b = 0; b < 3; ++b) D[4 * a + b] = R[a][b];
@@ -262,59 +265,28 @@ __device__ __noinline__ void solve_and_update(const double *acc, PairState *st, 
         }
     }
     bool finite = true;
-    for (int k = 0; k < 12; ++k) finite = finite && isfinite(D[k]);
+    for (int k = 0; k < 12; ++k) finite = finite && isfinite(D[k].v);
     if (!finite) { st->status = S3D_PAIR_NONFINITE; return; }
-    double T[12], O[12];
-    for (int k = 0; k < 12; ++k) T[k] = st->T[k];
+    sd T[12], O[12];
+    for (int k = 0; k < 12; ++k) T[k] = sd(st->T[k]);
     for (int r = 0; r < 3; ++r) {
         for (int c = 0; c < 3; ++c) O[4 * r + c] = D[4 * r] * T[c] + D[4 * r + 1] * T[4 + c] + D[4 * r + 2] * T[8 + c];
         O[4 * r + 3] = D[4 * r] * T[3] + D[4 * r + 1] * T[7] + D[4 * r + 2] * T[11] + D[4 * r + 3];
     }
-    for (int k = 0; k < 12; ++k) { st->T[k] = O[k]; st->Tf_prev[k] = st->Tf[k]; st->Tf[k] = (float)O[k]; }
+    for (int k = 0; k < 12; ++k) { st->T[k] = O[k].v; st->Tf_prev[k] = st->Tf[k]; st->Tf[k] = (float)O[k].v; }
     st->iterations += 1;
 }
 
 // ------------------------------------------------------------------------------------------------
 // the fused iteration kernel
 // ------------------------------------------------------------------------------------------------
+// One accepted correspondence into the order-independent sums (common.cuh; contract in oracle/oracle_common.h): J and r
+// in float32 with the oracle's expressions (identical bits), every product exact in double, rounded once to 2^-g by
+// fma(a, b, M), the raw bits added into wrapping int64 accumulators.  The caller counts the terms (S3D_ACC_COUNT is not
+// touched here) and removes count * bits(M) when it hands the partial sums on (fx_unbias).
+#define S3D_FX_SEGMENT 240     // queries per thread between hand-overs: 240 * 32 lanes * 2^49 < 2^63
 template <int EST>
-__device__ __forceinline__ void accumulate(float *acc, float px, float py, float pz, float4 q, float4 nv, float d2)
-{
-    if (EST == S3D_ESTIMATOR_POINT_TO_PLANE) {
-        float J[6];
-        J[0] = __fmaf_rn(nv.z, py, -__fmul_rn(nv.y, pz));
-        J[1] = __fmaf_rn(nv.x, pz, -__fmul_rn(nv.z, px));
-        J[2] = __fmaf_rn(nv.y, px, -__fmul_rn(nv.x, py));
-        J[3] = nv.x; J[4] = nv.y; J[5] = nv.z;
-        float ex = __fsub_rn(q.x, px), ey = __fsub_rn(q.y, py), ez = __fsub_rn(q.z, pz);
-        float r = __fmaf_rn(nv.z, ez, __fmaf_rn(nv.y, ey, __fmul_rn(nv.x, ex)));
-        int k = 0;
-        #pragma unroll
-        for (int a = 0; a < 6; ++a) {
-            #pragma unroll
-            for (int b = a; b < 6; ++b) { acc[k] = fmaf(J[a], J[b], acc[k]); ++k; }
-        }
-        #pragma unroll
-        for (int a = 0; a < 6; ++a) acc[21 + a] = fmaf(J[a], r, acc[21 + a]);
-    } else {
-        float p[3] = {px, py, pz}, qq[3] = {q.x, q.y, q.z};
-        #pragma unroll
-        for (int a = 0; a < 3; ++a) {
-            acc[a] += p[a]; acc[3 + a] += qq[a];
-            #pragma unroll
-            for (int b = 0; b < 3; ++b) acc[6 + 3 * a + b] = fmaf(p[a], qq[b], acc[6 + 3 * a + b]);
-        }
-    }
-    acc[S3D_ACC_SUMD2] += d2;
-    acc[S3D_ACC_COUNT] += 1.0f;
-}
-
-
-// Same sums with the oracle's arithmetic: J and r in float32 (bit-identical expressions), products exact in
-// double, double accumulation -- GPU and oracle then differ only by the order of double additions, which keeps
-// even the rank-deficiency verdict (a pivot compared with 1e-9 * diagonal) in agreement.
-template <int EST>
-__device__ __forceinline__ void accumulate_d(double *acc, float px, float py, float pz, float4 q, float4 nv, float d2)
+__device__ __forceinline__ void accumulate_fx(long long *acc, double M, float px, float py, float pz, float4 q, float4 nv, float d2)
 {
     if (EST == S3D_ESTIMATOR_POINT_TO_PLANE) {
         float J[6];
@@ -332,34 +304,44 @@ __device__ __forceinline__ void accumulate_d(double *acc, float px, float py, fl
         #pragma unroll
         for (int a = 0; a < 6; ++a) {
             #pragma unroll
-            for (int b = a; b < 6; ++b) { acc[k] = fma(Jd[a], Jd[b], acc[k]); ++k; }
+            for (int b = a; b < 6; ++b) { acc[k] += s3d_fx_bits(Jd[a], Jd[b], M); ++k; }
         }
         #pragma unroll
-        for (int a = 0; a < 6; ++a) acc[21 + a] = fma(Jd[a], rd, acc[21 + a]);
+        for (int a = 0; a < 6; ++a) acc[21 + a] += s3d_fx_bits(Jd[a], rd, M);
     } else {
         const double p[3] = {(double)px, (double)py, (double)pz}, qq[3] = {(double)q.x, (double)q.y, (double)q.z};
         #pragma unroll
         for (int a = 0; a < 3; ++a) {
-            acc[a] += p[a]; acc[3 + a] += qq[a];
+            acc[a] += s3d_fx_bits(p[a], 1.0, M); acc[3 + a] += s3d_fx_bits(qq[a], 1.0, M);
             #pragma unroll
-            for (int b = 0; b < 3; ++b) acc[6 + 3 * a + b] = fma(p[a], qq[b], acc[6 + 3 * a + b]);
+            for (int b = 0; b < 3; ++b) acc[6 + 3 * a + b] += s3d_fx_bits(p[a], qq[b], M);
         }
     }
-    acc[S3D_ACC_SUMD2] += (double)d2;
-    acc[S3D_ACC_COUNT] += 1.0;
+    acc[S3D_ACC_SUMD2] += s3d_fx_bits((double)d2, 1.0, M);
+}
+// slots that carry fixed-point sums for this estimator (the others stay 0)
+template <int EST> __device__ __forceinline__ bool fx_slot_used(int k)
+{
+    return k == S3D_ACC_SUMD2 || k < (EST == S3D_ESTIMATOR_POINT_TO_PLANE ? 27 : 15);
+}
+// raw accumulator of `cnt` terms -> the true partial sum (an integer number of 2^-g units)
+template <int EST> __device__ __forceinline__ long long fx_unbias(long long raw, int k, int cnt, unsigned long long mbits)
+{
+    return fx_slot_used<EST>(k) ? raw - (long long)((unsigned long long)cnt * mbits) : 0ll;
+}
+// the 29 totals (hi, lo) of a pair -> doubles for the solve (slot 28 is the plain count)
+template <int EST> __device__ __forceinline__ double fx_total(long long hi, long long lo, int k, double scale)
+{
+    if (k == S3D_ACC_COUNT) return __dadd_rn(__dmul_rn(__ll2double_rn(hi), 4294967296.0), __ll2double_rn(lo));
+    return fx_slot_used<EST>(k) ? s3d_fx_value(hi, lo, scale) : 0.0;
 }
 
 template <int EST, int SEARCH>
 __global__ void __launch_bounds__(ICP_BLOCK, ICP_MIN_BLOCKS) icp_iter_kernel(const PairDesc *__restrict__ descs, PairState *__restrict__ states,
-                                                                             double *__restrict__ partials, const int32_t *__restrict__ nn_idx,
                                                                              int32_t *__restrict__ nn_pos, float *__restrict__ nn_lb, int nn_stride, int use_seed,
-                                                                             float max_d2, int min_corr, double pivot_eps,
-                                                                             int32_t *__restrict__ nn_out)
+                                                                             float max_d2)
 {
-    __shared__ double wsum[ICP_BLOCK / 32][S3D_NACC];
-    __shared__ double tail[8][S3D_NACC];
     __shared__ uint2 rq[RANGE_QCAP * ICP_BLOCK];   // per-thread queues of candidate ranges (search.cuh)
-    __shared__ bool is_last;
     const int pair = blockIdx.y;
     PairState *st = states + pair;
     if (st->status != 0) return;   // failed pairs stay failed; every CTA of the pair takes this exit together
@@ -492,48 +474,88 @@ __global__ void __launch_bounds__(ICP_BLOCK, ICP_MIN_BLOCKS) icp_iter_kernel(con
         }
     }
 
-    // ---- phase 2: residuals and normal-equation sums of the accepted correspondences --------------
-    float acc[29];
-    #pragma unroll
-    for (int k = 0; k < 29; ++k) acc[k] = 0.f;
-    for (int i = tid0; i < d.n_src; i += tstride) {
-        const float4 p = d.src[i];
-        const float3 x = s3d_xform(T, p.x, p.y, p.z);
-        int j = -1; float4 q = make_float4(0.f, 0.f, 0.f, 0.f), nv = make_float4(0.f, 0.f, 0.f, 1.f);
-        if (SEARCH == S3D_SEARCH_GRID) {
-            const int bpos = my_pos[i];     // written by this same thread in phase 1
-            if (bpos >= 0) {
-                q = __ldg(&d.sorted_pts[bpos]);
-                j = __float_as_int(q.w);
-                if (EST == S3D_ESTIMATOR_POINT_TO_PLANE) nv = __ldg(&d.sorted_nrm[bpos]);
-            }
-        } else {
-            j = nn_idx[(size_t)pair * nn_stride + i];
-            if (j >= 0) {
-                q = __ldg(&d.tgt[j]);
-                if (EST == S3D_ESTIMATOR_POINT_TO_PLANE) nv = __ldg(&d.tgt_nrm[j]);
-            }
-        }
-        const float bd = s3d_dist2(x.x, x.y, x.z, q.x, q.y, q.z);   // same expression as in the search: identical bits
-        const bool ok = (j >= 0) && (bd <= max_d2) && (nv.w != 0.f);
-        if (ok) accumulate<EST>(acc, x.x, x.y, x.z, q, nv, bd);
-        if (nn_out) nn_out[i] = ok ? j : -1;
-    }
+}
 
-    // CTA reduction: shuffles inside the warp (float), double across warps
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+// Phase 2 of an iteration of the per-iteration-launch modes: residuals and normal-equation sums of the accepted
+// correspondences (order-independent fixed-point sums), one (hi, lo) row per CTA, the last CTA of the pair (atomic ticket)
+// adds the rows and solves.  A kernel of its own: 29 int64 accumulators do not fit the 64 registers of the search kernel.
+#define S3D_ROW 64            // int64 per partial row: hi sums at [k], lo sums at [32 + k]
+template <int EST, int SEARCH>
+__global__ void __launch_bounds__(ICP_BLOCK, 2) icp_accum_kernel(const PairDesc *__restrict__ descs, PairState *__restrict__ states,
+                                                                 long long *__restrict__ partials, const int32_t *__restrict__ nn_idx,
+                                                                 const int32_t *__restrict__ nn_pos, int nn_stride,
+                                                                 float max_d2, int min_corr, double pivot_eps, int32_t *__restrict__ nn_out)
+{
+    __shared__ long long whi[ICP_BLOCK / 32][S3D_NACC], wlo[ICP_BLOCK / 32][S3D_NACC];
+    __shared__ long long thi[8][S3D_NACC], tlo[8][S3D_NACC];
+    __shared__ double total[S3D_NACC];
+    __shared__ FxScale fxs;
+    __shared__ bool is_last;
+    const int pair = blockIdx.y;
+    PairState *st = states + pair;
+    if (st->status != 0) return;   // failed pairs stay failed; every CTA of the pair takes this exit together
+    const PairDesc d = descs[pair];
+    if (threadIdx.x == 0) fxs = s3d_fx_make(s3d_icp_bound(*d.src_absmax, *d.tgt_absmax, EST == S3D_ESTIMATOR_POINT_TO_PLANE ? d.tgt_absmax[1] : 1.0f, st->T));
+    float T[12];
     #pragma unroll
-    for (int k = 0; k < 29; ++k) {
-        float v = warp_sum(acc[k]);
-        if (lane == 0) wsum[warp][k] = (double)v;
-    }
+    for (int k = 0; k < 12; ++k) T[k] = st->Tf[k];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane < 29) { whi[warp][lane] = 0; wlo[warp][lane] = 0; }
     __syncthreads();
-    double *row = partials + ((size_t)pair * gridDim.x + blockIdx.x) * S3D_NACC;
-    if (threadIdx.x < 29) {
-        double s = 0.0;
+    const unsigned long long mbits = fxs.mbits;
+    const double M = __longlong_as_double((long long)mbits);
+    const int tid0 = blockIdx.x * ICP_BLOCK + threadIdx.x, tstride = gridDim.x * ICP_BLOCK;
+    const int32_t *my_pos = nn_pos + (size_t)pair * nn_stride;
+    int total_cnt = 0;
+    for (int i0 = tid0 - lane; i0 < d.n_src; i0 += tstride * S3D_FX_SEGMENT) {       // warp-uniform segments
+        long long acc[29];
         #pragma unroll
-        for (int w = 0; w < ICP_BLOCK / 32; ++w) s += wsum[w][threadIdx.x];
-        __stcg(&row[threadIdx.x], s);
+        for (int k = 0; k < 29; ++k) acc[k] = 0;
+        int cnt = 0;
+        for (int s = 0; s < S3D_FX_SEGMENT; ++s) {
+            const int i = i0 + lane + s * tstride;
+            if (i >= d.n_src) break;
+            const float4 p = d.src[i];
+            const float3 x = s3d_xform(T, p.x, p.y, p.z);
+            int j = -1; float4 q = make_float4(0.f, 0.f, 0.f, 0.f), nv = make_float4(0.f, 0.f, 0.f, 1.f);
+            if (SEARCH == S3D_SEARCH_GRID) {
+                const int bpos = my_pos[i];
+                if (bpos >= 0) {
+                    q = __ldg(&d.sorted_pts[bpos]);
+                    j = __float_as_int(q.w);
+                    if (EST == S3D_ESTIMATOR_POINT_TO_PLANE) nv = __ldg(&d.sorted_nrm[bpos]);
+                }
+            } else {
+                j = nn_idx[(size_t)pair * nn_stride + i];
+                if (j >= 0) {
+                    q = __ldg(&d.tgt[j]);
+                    if (EST == S3D_ESTIMATOR_POINT_TO_PLANE) nv = __ldg(&d.tgt_nrm[j]);
+                }
+            }
+            const float bd = s3d_dist2(x.x, x.y, x.z, q.x, q.y, q.z);   // same expression as in the search: identical bits
+            const bool ok = (j >= 0) && (bd <= max_d2) && (nv.w != 0.f);
+            if (ok) { accumulate_fx<EST>(acc, M, x.x, x.y, x.z, q, nv, bd); ++cnt; }
+            if (nn_out) nn_out[i] = ok ? j : -1;
+        }
+        total_cnt += cnt;
+        // hand the segment over: true partial sums, added across the warp (< 2^63), split into (hi, lo)
+        #pragma unroll
+        for (int k = 0; k < 28; ++k) {
+            long long v = fx_unbias<EST>(acc[k], k, cnt, mbits);
+            #pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0) { long long hi, lo; s3d_fx_split(v, hi, lo); whi[warp][k] += hi; wlo[warp][k] += lo; }
+        }
+    }
+    total_cnt = warp_sum_i(total_cnt);
+    if (lane == 0) wlo[warp][S3D_ACC_COUNT] = total_cnt;
+    __syncthreads();
+    long long *row = partials + ((size_t)pair * gridDim.x + blockIdx.x) * S3D_ROW;
+    if (threadIdx.x < 29) {
+        long long hi = 0, lo = 0;
+        #pragma unroll
+        for (int w = 0; w < ICP_BLOCK / 32; ++w) { hi += whi[w][threadIdx.x]; lo += wlo[w][threadIdx.x]; }
+        __stcg(&row[threadIdx.x], hi); __stcg(&row[32 + threadIdx.x], lo);
     }
     __threadfence();
     __syncthreads();
@@ -544,26 +566,26 @@ __global__ void __launch_bounds__(ICP_BLOCK, ICP_MIN_BLOCKS) icp_iter_kernel(con
     __syncthreads();
     if (!is_last) return;
     __threadfence();
-    // last CTA of the pair: fixed-order sum of all partial rows, then solve
+    // last CTA of the pair: sum of all partial rows (integers: any order gives the same bits), then solve
     {
         const int slot = threadIdx.x & 31, part = threadIdx.x >> 5; // 8 parts
-        double s = 0.0;
+        long long hi = 0, lo = 0;
         if (slot < 29) {
-            const double *base = partials + (size_t)pair * gridDim.x * S3D_NACC;
-            for (int c = part; c < (int)gridDim.x; c += 8) s += __ldcg(&base[(size_t)c * S3D_NACC + slot]);
+            const long long *base = partials + (size_t)pair * gridDim.x * S3D_ROW;
+            for (int c = part; c < (int)gridDim.x; c += 8) { hi += __ldcg(&base[(size_t)c * S3D_ROW + slot]); lo += __ldcg(&base[(size_t)c * S3D_ROW + 32 + slot]); }
         }
-        tail[part][slot] = s;
+        thi[part][slot] = hi; tlo[part][slot] = lo;
     }
     __syncthreads();
     if (threadIdx.x < 32) {
-        double s = 0.0;
+        long long hi = 0, lo = 0;
         #pragma unroll
-        for (int p8 = 0; p8 < 8; ++p8) s += tail[p8][threadIdx.x];
-        tail[0][threadIdx.x] = s;
+        for (int p8 = 0; p8 < 8; ++p8) { hi += thi[p8][threadIdx.x]; lo += tlo[p8][threadIdx.x]; }
+        total[threadIdx.x] = threadIdx.x < 29 ? fx_total<EST>(hi, lo, threadIdx.x, fxs.scale) : 0.0;
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        solve_and_update<EST>(tail[0], st, min_corr, pivot_eps);
+        solve_and_update<EST>(total, st, min_corr, pivot_eps);
         st->ticket = 0u;
     }
 }
@@ -575,7 +597,7 @@ __global__ void __launch_bounds__(ICP_BLOCK, ICP_MIN_BLOCKS) icp_iter_kernel(con
 #ifndef TS_BLOCK
 #define TS_BLOCK 512
 #endif
-static_assert(TS_CAP * 16 >= 29 * 33 * 8, "the warp tile also carries the transposed 29 x 33 double reduction");
+static_assert(TS_CAP * 16 >= 29 * 33 * 8, "the warp tile also carries the transposed 29 x 33 int64 reduction");
 #define TS_WARPS (TS_BLOCK / 32)
 #define TS_STAGE (TS_CAP / 128)     // chunks of per-query state (32 lanes x 4 float4) a warp's tile holds
 
@@ -589,7 +611,7 @@ static_assert(TS_CAP * 16 >= 29 * 33 * 8, "the warp tile also carries the transp
 
 struct PersistArgs {
     const PairDesc *descs; PairState *states;
-    double *partials;            // [2][groups][group_ctas][S3D_NACC]
+    long long *partials;         // [2][groups][group_ctas][S3D_ROW]: (hi, lo) partial sums, double buffered by barrier parity
     unsigned *barriers;          // [groups], zero at launch, monotonic
     float4 *cq;                  // per query: its correspondence (x,y,z, original target index; -1: none)
     float4 *cn;                  // per query: the correspondence's normal (nx,ny,nz,valid)   (point-to-plane)
@@ -644,8 +666,10 @@ __global__ void __launch_bounds__(TS_BLOCK, 1) icp_persist_kernel(const PersistA
     extern __shared__ __align__(16) unsigned char ts_smem[];
     float4 *tiles = reinterpret_cast<float4 *>(ts_smem);          // TS_WARPS tiles of TS_CAP candidates
     __shared__ PairState st;                                      // this CTA's copy of the pair state (all CTAs of a group agree bit for bit)
-    __shared__ double wsum[TS_WARPS][S3D_NACC];
-    __shared__ double tail[TS_WARPS][S3D_NACC];
+    __shared__ long long whi[TS_WARPS][S3D_NACC], wlo[TS_WARPS][S3D_NACC];     // per-warp (hi, lo) sums of the iteration
+    __shared__ long long thi[TS_WARPS][S3D_NACC], tlo[TS_WARPS][S3D_NACC];     // group totals, one part per warp
+    __shared__ double total[S3D_NACC];                            // the pair's 29 sums as doubles, input of the solve
+    __shared__ FxScale fxs;                                       // resolution of this iteration's sums (from the pose and the data bounds)
     __shared__ TileCfg cfg[2];                                    // search levels of the current pair: [0] decimated grid, [1] full grid
     __shared__ int dyn_next;                                      // dynamic decide pass: next octet of this CTA to hand out
     __shared__ float4 dyn_pre[TS_WARPS][96];                      // ... and the state of each warp's NEXT item (32 x point, correspondence, search state)
@@ -676,6 +700,7 @@ __global__ void __launch_bounds__(TS_BLOCK, 1) icp_persist_kernel(const PersistA
         __syncthreads();
         if (threadIdx.x == 0) {
             st = a.states[pair];
+            fxs = s3d_fx_make(s3d_icp_bound(*d.src_absmax, *d.tgt_absmax, EST == S3D_ESTIMATOR_POINT_TO_PLANE ? d.tgt_absmax[1] : 1.0f, st.T));
             dyn_next = 0; n_pending = 0; n_pending_prev = 0;
             cfg[1].gp = *d.grid; cfg[1].cell_start = d.cell_start; cfg[1].pts = d.sorted_pts;
             cfg[1].slack = a.slack_cells * cfg[1].gp.cell; cfg[1].gate_r = gate_r;
@@ -879,9 +904,35 @@ __global__ void __launch_bounds__(TS_BLOCK, 1) icp_persist_kernel(const PersistA
             if (dyn) __syncthreads();
 
             // ---- accumulate pass ----
-            double acc[29];
+            // Order-independent fixed-point sums (common.cuh): 29 wrapping int64 accumulators per thread.  Every
+            // S3D_FX_SEGMENT queries per thread (and at the end) the warp hands its partial sums over: unbias, add the 32
+            // lanes through the warp's tile (transposed: lane k adds slot k of the 32 lanes, ~100 instructions instead of
+            // 29 five-step shuffle trees), split into (hi, lo) and add to the warp's running sums in shared memory.
+            const unsigned long long mbits = fxs.mbits;
+            const double M = __longlong_as_double((long long)mbits);
+            long long acc[29];
             #pragma unroll
-            for (int k = 0; k < 29; ++k) acc[k] = 0.0;
+            for (int k = 0; k < 29; ++k) acc[k] = 0;
+            int cnt = 0, cnt_total = 0, since = 0;
+            if (lane < 29) { whi[warp][lane] = 0; wlo[warp][lane] = 0; }
+            auto hand_over = [&]() {
+                long long *tr = reinterpret_cast<long long *>(buf);          // 29 x 33 int64 <= TS_CAP float4
+                __syncwarp();
+                #pragma unroll
+                for (int k = 0; k < 28; ++k) tr[k * 33 + lane] = fx_unbias<EST>(acc[k], k, cnt, mbits);
+                __syncwarp();
+                if (lane < 28) {
+                    long long v = 0;
+                    #pragma unroll 8
+                    for (int l = 0; l < 32; ++l) v += tr[lane * 33 + l];
+                    long long hi, lo; s3d_fx_split(v, hi, lo);
+                    whi[warp][lane] += hi; wlo[warp][lane] += lo;
+                }
+                __syncwarp();
+                #pragma unroll
+                for (int k = 0; k < 29; ++k) acc[k] = 0;
+                cnt_total += cnt; cnt = 0; since = 0;
+            };
             for (int kc0 = 0; wslot + W * 4 * kc0 < nunits; kc0 += TS_STAGE) {
                 #pragma unroll
                 for (int c = 0; c < TS_STAGE; ++c) {
@@ -906,11 +957,16 @@ __global__ void __launch_bounds__(TS_BLOCK, 1) icp_persist_kernel(const PersistA
                         const int j = __float_as_int(q.w);
                         const float d2q = s3d_dist2(x.x, x.y, x.z, q.x, q.y, q.z);    // same expression as in the search: identical bits
                         const bool ok = (j >= 0) && (d2q <= a.max_d2) && (nv.w != 0.f);
-                        if (ok) accumulate_d<EST>(acc, x.x, x.y, x.z, q, nv, d2q);
+                        if (ok) { accumulate_fx<EST>(acc, M, x.x, x.y, x.z, q, nv, d2q); ++cnt; }
                         if (last && a.nn_out) a.nn_out[i] = ok ? j : -1;
                     }
                 }
+                since += TS_STAGE;
+                if (since >= S3D_FX_SEGMENT - TS_STAGE) hand_over();      // warp-uniform
             }
+            hand_over();
+            cnt_total = warp_sum_i(cnt_total);
+            if (lane == 0) wlo[warp][S3D_ACC_COUNT] = cnt_total;
 
 #if defined(S3D_STATS) || defined(S3D_PHASES)
             if (blockIdx.x == 0 && lane == 0) {
@@ -924,30 +980,15 @@ __global__ void __launch_bounds__(TS_BLOCK, 1) icp_persist_kernel(const PersistA
             }
 #endif
             PHASE(8);
-            // CTA reduction in double: shuffles inside the warp, shared memory across warps, one row per CTA
-            // (through the warp's tile, transposed: lane k sums slot k of the 32 lanes in lane order -- ~100 instructions
-            //  instead of 29 five-step double shuffle trees)
-            {
-                double *tr = reinterpret_cast<double *>(buf);          // 29 x 33 doubles <= TS_CAP float4
-                __syncwarp();
-                #pragma unroll
-                for (int k = 0; k < 29; ++k) tr[k * 33 + lane] = acc[k];
-                __syncwarp();
-                if (lane < 29) {
-                    double s = 0.0;
-                    #pragma unroll 8
-                    for (int l = 0; l < 32; ++l) s += tr[lane * 33 + l];
-                    wsum[warp][lane] = s;
-                }
-                __syncwarp();
-            }
+            // CTA reduction: the warps' (hi, lo) sums are integers, any order of addition gives the same bits
             __syncthreads();
-            double *rows = a.partials + ((size_t)(epoch & 1u) * a.groups + group) * a.group_ctas * S3D_NACC;
+            long long *rows = a.partials + ((size_t)(epoch & 1u) * a.groups + group) * a.group_ctas * S3D_ROW;
             if (threadIdx.x < 29) {
-                double s = 0.0;
+                long long hi = 0, lo = 0;
                 #pragma unroll
-                for (int w = 0; w < TS_WARPS; ++w) s += wsum[w][threadIdx.x];
-                __stcg(&rows[(size_t)rank * S3D_NACC + threadIdx.x], s);
+                for (int w = 0; w < TS_WARPS; ++w) { hi += whi[w][threadIdx.x]; lo += wlo[w][threadIdx.x]; }
+                __stcg(&rows[(size_t)rank * S3D_ROW + threadIdx.x], hi);
+                __stcg(&rows[(size_t)rank * S3D_ROW + 32 + threadIdx.x], lo);
             }
             if (threadIdx.x == 32) { n_pending_prev = n_pending; n_pending = 0; dyn_next = 0; }     // every warp is past its decide pass
             // group barrier (all CTAs are co-resident: cooperative launch)
@@ -965,34 +1006,38 @@ __global__ void __launch_bounds__(TS_BLOCK, 1) icp_persist_kernel(const PersistA
             }
             __syncthreads();
             PHASE(10);
-            // every CTA: the same fixed-order sum of the group's rows, then the same solve
+            // every CTA: the sum of the group's rows (integers), converted to doubles once, then the same solve
             {
-                // (loads of up to 10 rows in flight per thread, added in row order)
-                double s = 0.0;
+                // (loads of up to 10 rows in flight per thread)
+                long long hi = 0, lo = 0;
                 if (lane < 29) {
                     for (int c0 = warp; c0 < a.group_ctas; c0 += 10 * TS_WARPS) {
-                        double v[10];
+                        long long vh[10], vl[10];
                         #pragma unroll
                         for (int j = 0; j < 10; ++j) {
                             const int c = c0 + j * TS_WARPS;
-                            v[j] = c < a.group_ctas ? __ldcg(&rows[(size_t)c * S3D_NACC + lane]) : 0.0;
+                            vh[j] = c < a.group_ctas ? __ldcg(&rows[(size_t)c * S3D_ROW + lane]) : 0ll;
+                            vl[j] = c < a.group_ctas ? __ldcg(&rows[(size_t)c * S3D_ROW + 32 + lane]) : 0ll;
                         }
                         #pragma unroll
-                        for (int j = 0; j < 10; ++j) s += v[j];
+                        for (int j = 0; j < 10; ++j) { hi += vh[j]; lo += vl[j]; }
                     }
                 }
-                tail[warp][lane] = s;
+                thi[warp][lane] = hi; tlo[warp][lane] = lo;
             }
             __syncthreads();
             if (threadIdx.x < 32) {
-                double s = 0.0;
+                long long hi = 0, lo = 0;
                 #pragma unroll
-                for (int w = 0; w < TS_WARPS; ++w) s += tail[w][threadIdx.x];
-                tail[0][threadIdx.x] = s;
+                for (int w = 0; w < TS_WARPS; ++w) { hi += thi[w][threadIdx.x]; lo += tlo[w][threadIdx.x]; }
+                total[threadIdx.x] = threadIdx.x < 29 ? fx_total<EST>(hi, lo, threadIdx.x, fxs.scale) : 0.0;
             }
             __syncthreads();
             PHASE(11);
-            if (threadIdx.x == 0) solve_and_update<EST>(tail[0], &st, a.min_corr, a.pivot_eps);
+            if (threadIdx.x == 0) {
+                solve_and_update<EST>(total, &st, a.min_corr, a.pivot_eps);
+                fxs = s3d_fx_make(s3d_icp_bound(*d.src_absmax, *d.tgt_absmax, EST == S3D_ESTIMATOR_POINT_TO_PLANE ? d.tgt_absmax[1] : 1.0f, st.T));
+            }
             __syncthreads();
             PHASE(12);
         }
@@ -1038,17 +1083,24 @@ static int ensure_batch(s3d_ctx *ctx, int n_pairs, int ctas)
     if ((size_t)ctx->cap_pairs * ctas > (size_t)ctx->cap_ctas) {
         cudaFree(ctx->d_partials); ctx->d_partials = nullptr;
         size_t rows = (size_t)ctx->cap_pairs * ctas;
-        S3D_CUDA(ctx, cudaMalloc(&ctx->d_partials, sizeof(double) * S3D_NACC * rows));
+        S3D_CUDA(ctx, cudaMalloc(&ctx->d_partials, sizeof(long long) * S3D_ROW * rows));
         ctx->cap_ctas = (int)std::min<size_t>(rows, 0x7fffffff);
     }
     return S3D_OK;
 }
 
+// one iteration of the per-iteration-launch modes: [grid search kernel] + accumulate/solve kernel
 template <int EST, int SEARCH>
-static void launch_iter(s3d_ctx *ctx, dim3 grid, int nn_stride, int use_seed, float max_d2, int min_corr, double pivot_eps, int32_t *nn_out)
+static int launch_iter(s3d_ctx *ctx, dim3 grid, int nn_stride, int use_seed, float max_d2, int min_corr, double pivot_eps, int32_t *nn_out)
 {
-    icp_iter_kernel<EST, SEARCH><<<grid, ICP_BLOCK, 0, ctx->stream>>>(ctx->d_desc, ctx->d_state, ctx->d_partials, ctx->d_nn_idx,
-                                                                      ctx->d_nn_pos, ctx->d_nn_d2, nn_stride, use_seed, max_d2, min_corr, pivot_eps, nn_out);
+    if (SEARCH == S3D_SEARCH_GRID) {
+        icp_iter_kernel<EST, SEARCH><<<grid, ICP_BLOCK, 0, ctx->stream>>>(ctx->d_desc, ctx->d_state, ctx->d_nn_pos, ctx->d_nn_d2, nn_stride, use_seed, max_d2);
+        S3D_LAUNCHED(ctx);
+    }
+    icp_accum_kernel<EST, SEARCH><<<grid, ICP_BLOCK, 0, ctx->stream>>>(ctx->d_desc, ctx->d_state, ctx->d_partials, ctx->d_nn_idx, ctx->d_nn_pos,
+                                                                       nn_stride, max_d2, min_corr, pivot_eps, nn_out);
+    S3D_LAUNCHED(ctx);
+    return S3D_OK;
 }
 
 // Enqueues one batch on the ctx stream (index builds where needed, pair descriptors, every iteration launch) and records
@@ -1166,6 +1218,10 @@ int s3d_register_issue(s3d_ctx *ctx, const s3d_cloud *const *src, const s3d_clou
         d.coarse_cell_start = coarse ? tgt[i]->coarse.d_cell_start : nullptr;
         d.coarse_rowmask = coarse ? tgt[i]->coarse.d_rowmask : nullptr;
         d.coarse_grid = coarse ? tgt[i]->coarse.d_params : nullptr;
+        rc = s3d_cloud_absmax(ctx, src[i], false);
+        if (rc == S3D_OK) rc = s3d_cloud_absmax(ctx, tgt[i], plane);
+        if (rc) return rc;
+        d.src_absmax = src[i]->d_absmax; d.tgt_absmax = tgt[i]->d_absmax;
         PairState &s = ctx->h_state[i];
         memset(&s, 0, sizeof(s));
         static const double I12[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
@@ -1209,13 +1265,15 @@ int s3d_register_issue(s3d_ctx *ctx, const s3d_cloud *const *src, const s3d_clou
             }
             nn_brute_tma_kernel<<<g2, ICP_BLOCK, smem, ctx->stream>>>(ctx->d_desc, ctx->d_state, ctx->d_nn_idx, ctx->d_nn_d2, n_max);
             S3D_LAUNCHED(ctx); ++iter_launches;
-            if (plane) launch_iter<S3D_ESTIMATOR_POINT_TO_PLANE, S3D_SEARCH_BRUTE>(ctx, grid, n_max, 0, max_d2, min_corr, pivot_eps, no);
-            else launch_iter<S3D_ESTIMATOR_SVD, S3D_SEARCH_BRUTE>(ctx, grid, n_max, 0, max_d2, min_corr, pivot_eps, no);
+            rc = plane ? launch_iter<S3D_ESTIMATOR_POINT_TO_PLANE, S3D_SEARCH_BRUTE>(ctx, grid, n_max, 0, max_d2, min_corr, pivot_eps, no)
+                       : launch_iter<S3D_ESTIMATOR_SVD, S3D_SEARCH_BRUTE>(ctx, grid, n_max, 0, max_d2, min_corr, pivot_eps, no);
+            ++iter_launches;
         } else {
-            if (plane) launch_iter<S3D_ESTIMATOR_POINT_TO_PLANE, S3D_SEARCH_GRID>(ctx, grid, n_max, it > 0, max_d2, min_corr, pivot_eps, no);
-            else launch_iter<S3D_ESTIMATOR_SVD, S3D_SEARCH_GRID>(ctx, grid, n_max, it > 0, max_d2, min_corr, pivot_eps, no);
+            rc = plane ? launch_iter<S3D_ESTIMATOR_POINT_TO_PLANE, S3D_SEARCH_GRID>(ctx, grid, n_max, it > 0, max_d2, min_corr, pivot_eps, no)
+                       : launch_iter<S3D_ESTIMATOR_SVD, S3D_SEARCH_GRID>(ctx, grid, n_max, it > 0, max_d2, min_corr, pivot_eps, no);
+            iter_launches += 2;
         }
-        S3D_LAUNCHED(ctx); ++iter_launches;
+        if (rc) return rc;
     }
     cudaEventRecord(ctx->ev[2], ctx->stream);
     *built_out = built; *iter_launches_out = iter_launches;

@@ -3,34 +3,51 @@
 // Replaces GraphicEnd::extractPlanesAndGenerateImage (reference src/GraphicEnd.cpp:353-430), i.e. the
 // loop  { pcl::SACSegmentation::segment ; flip sign so d >= 0 ; ExtractIndices positive/negative }
 // with the PCL-1.7 semantics restated in oracle/plane_oracle.c.  All candidate planes of a round are
-// evaluated in ONE streaming pass over the remaining points (16 B per point per 32 candidates); the
+// evaluated in ONE streaming pass over the remaining points (16 B per point for up to 64 candidates); the
 // sequential adaptive-stop logic of pcl::RandomSampleConsensus::computeModel is then replayed over
 // the counts by a single thread, so the chosen model is exactly the one the sequential loop picks.
 // The per-point result (plane label + plane normal) is what the ICP uses as target normals.
+//
+// The whole extraction is driven from the device: the host enqueues max_planes rounds of five kernels
+// (hypotheses / evaluate + replay / PCA refit / count / compact) with worst-case grids; every kernel reads the
+// loop state (points left, planes found, stopped) from device memory and returns at once when the
+// reference's `while (remaining > percent * n)` loop (src/GraphicEnd.cpp:372) would have ended.  One
+// read-back at the end returns the planes.  The PCA sums are order-independent fixed-point sums and the
+// refit runs in strict double (common.cuh), so coefficients and labels equal the oracle's bit for bit.
 #include <cstring>
+#include <algorithm>
 #include "context.h"
 #include "common.cuh"
 #include "compact.cuh"
 
+#define S3D_FX_SEGMENT_P 240   // points per thread between hand-overs of the fixed-point sums (see icp.cu)
+
 #define PLANE_CANDIDATES_EXTRA 14
 #define PLANE_MAX_CAND 1024
-#define PLANE_CHUNK 32
+#define PLANE_CHUNK 64
 #define PLANE_BLOCK 256
 
-struct PlaneSel {
-    float4 ransac;     // model picked by the RANSAC replay
-    float4 refined;    // after PCA refit + sign flip
-    int best;          // candidate index or -1
-    int best_count;
-    int iterations;
-    int stop;          // 1: no plane found in this round
-    unsigned ticket;
-    int pad[3];
+struct PlaneState {
+    int n_rem;          // points not yet assigned to a plane (compacted, order kept)
+    int n_planes;
+    int stopped;        // the reference's loop has ended (condition false or one of its `break`s taken)
+    int active;         // this round runs (decided by the hypothesis kernel from the three fields above)
+    float4 ransac;      // model picked by the RANSAC replay
+    float4 refined;     // after PCA refit + sign flip
+    int best_count, iterations;
+    unsigned ticket_eval, ticket_refit, ticket_write, pad;
+    int rem_at_round[S3D_MAX_PLANES];     // points scanned by the evaluation pass of each round (roofline bookkeeping)
+    s3d_plane planes[S3D_MAX_PLANES];
 };
 
 __global__ void plane_init_kernel(const float4 *__restrict__ pts, int n, float4 *__restrict__ rem, int32_t *__restrict__ labels,
-                                  float4 *__restrict__ nrm)
+                                  float4 *__restrict__ nrm, PlaneState *st)
 {
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        st->n_rem = n; st->n_planes = 0; st->stopped = 0; st->active = 0;
+        st->ticket_eval = st->ticket_refit = st->ticket_write = 0u;
+        for (int k = 0; k < S3D_MAX_PLANES; ++k) st->rem_at_round[k] = 0;
+    }
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         float4 p = pts[i];
         rem[i] = make_float4(p.x, p.y, p.z, __int_as_float(i));
@@ -39,31 +56,75 @@ __global__ void plane_init_kernel(const float4 *__restrict__ pts, int n, float4 
     }
 }
 
-__global__ void plane_hyp_kernel(const float4 *__restrict__ rem, int n_rem, uint64_t seed, int round, int n_cand,
-                                 float4 *__restrict__ coefs, int *__restrict__ valid, uint32_t *__restrict__ counts, PlaneSel *sel)
+// Loop test of the reference (src/GraphicEnd.cpp:372,424) + candidate planes of this round.  One CTA.
+__global__ void __launch_bounds__(PLANE_MAX_CAND) plane_hyp_kernel(const float4 *__restrict__ rem, int n, float percent, int max_planes,
+                                                                   uint64_t seed, int round, int n_cand, float4 *__restrict__ coefs,
+                                                                   int *__restrict__ valid, uint32_t *__restrict__ counts, PlaneState *st)
 {
-    int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c == 0) { sel->ticket = 0u; sel->stop = 0; sel->best = -1; }
-    if (c >= n_cand) return;
+    const int n_rem = st->n_rem, n_planes = st->n_planes;
+    const bool go = !st->stopped && (double)n_rem > (double)percent * (double)n && n_planes < max_planes && n_rem >= 3;
+    __syncthreads();                 // everybody has read the state before thread 0 changes it
+    const int c = threadIdx.x;
+    if (c == 0) {
+        st->active = go ? 1 : 0;
+        if (!go) st->stopped = 1;
+        else st->rem_at_round[round] = n_rem;
+    }
+    if (!go || c >= n_cand) return;
     uint32_t s[3];
-    s3d_sample3(seed, (uint64_t)round, (uint64_t)c, (uint32_t)n_rem, s);
+    s3d_sample3(seed, (uint64_t)n_planes, (uint64_t)c, (uint32_t)n_rem, s);
     float4 a = rem[s[0]], b = rem[s[1]], d = rem[s[2]];
     float4 coef = make_float4(0.f, 0.f, 0.f, 0.f);
     bool ok = s3d_plane_from3(make_float3(a.x, a.y, a.z), make_float3(b.x, b.y, b.z), make_float3(d.x, d.y, d.z), coef);
     coefs[c] = coef; valid[c] = ok ? 1 : 0; counts[c] = 0u;
 }
 
-// one pass over the remaining points evaluates PLANE_CHUNK candidates (chunk index = blockIdx.y)
-__global__ void __launch_bounds__(PLANE_BLOCK) plane_eval_kernel(const float4 *__restrict__ rem, int n_rem, const float4 *__restrict__ coefs,
-                                                                 const int *__restrict__ valid, int n_cand, float tau,
-                                                                 uint32_t *__restrict__ counts)
+// replay of pcl::RandomSampleConsensus::computeModel over the pre-evaluated candidates (one thread)
+__device__ void plane_select(const float4 *__restrict__ coefs, const int *__restrict__ valid, const uint32_t *__restrict__ counts,
+                             int n_cand, int n_points, int max_iterations, double probability, PlaneState *st)
 {
+    int iterations = 0, best = -1, best_count = -2147483647;
+    double k = 1.0;
+    const double log_prob = log(1.0 - probability);
+    const double one_over = n_points > 0 ? 1.0 / (double)n_points : 0.0;
+    const double eps = 2.220446049250313e-16;
+    for (int c = 0; c < n_cand && iterations < k; ++c) {
+        if (!valid[c]) continue;
+        int cc = (int)__ldcg(&counts[c]);
+        if (cc > best_count) {
+            best_count = cc; best = c;
+            double w = best_count * one_over;
+            double p_no = 1.0 - w * w * w;
+            if (p_no < eps) p_no = eps;
+            if (p_no > 1.0 - eps) p_no = 1.0 - eps;
+            k = log_prob / log(p_no);
+        }
+        ++iterations;
+        if (iterations > max_iterations) break;
+    }
+    st->best_count = best >= 0 ? best_count : 0; st->iterations = iterations;
+    if (best < 0 || best_count == 0) { st->stopped = 1; st->active = 0; }          // reference :376-379
+    else { st->ransac = coefs[best]; st->refined = coefs[best]; }
+}
+
+// ONE pass over the remaining points evaluates up to PLANE_CHUNK (64) candidates (chunk index = blockIdx.y; the stock
+// 50 + 14 candidates are one chunk): 16 bytes per point and pass.  The last CTA to finish replays the RANSAC loop.
+__global__ void __launch_bounds__(PLANE_BLOCK) plane_eval_kernel(const float4 *__restrict__ rem, const float4 *__restrict__ coefs,
+                                                                 const int *__restrict__ valid, int n_cand, float tau,
+                                                                 uint32_t *__restrict__ counts, int max_iterations, double probability,
+                                                                 PlaneState *st)
+{
+    if (!st->active) return;
+    const int n_rem = st->n_rem;
     __shared__ float4 sc[PLANE_CHUNK];
+    __shared__ uint32_t s_cnt[PLANE_CHUNK];
+    __shared__ bool is_last;
     const int c0 = blockIdx.y * PLANE_CHUNK;
     if (threadIdx.x < PLANE_CHUNK) {
         int c = c0 + threadIdx.x;
         // invalid candidates get a plane no point can satisfy (NaN compares false)
         sc[threadIdx.x] = (c < n_cand && valid[c]) ? coefs[c] : make_float4(0.f, 0.f, 0.f, __int_as_float(0x7fc00000));
+        s_cnt[threadIdx.x] = 0u;
     }
     __syncthreads();
     int cnt[PLANE_CHUNK];
@@ -77,11 +138,7 @@ __global__ void __launch_bounds__(PLANE_BLOCK) plane_eval_kernel(const float4 *_
             cnt[k] += (fabsf(s3d_plane_eval(c.x, c.y, c.z, c.w, p.x, p.y, p.z)) < tau) ? 1 : 0;
         }
     }
-    // counts: warp shuffle -> shared-memory atomics -> ONE global atomic per candidate and CTA (every warp going to the 64
-    // global counters serialised at ~27 cycles per same-address atomic: 65 us of a 88 us kernel)
-    __shared__ uint32_t s_cnt[PLANE_CHUNK];
-    if (threadIdx.x < PLANE_CHUNK) s_cnt[threadIdx.x] = 0u;
-    __syncthreads();
+    // counts: warp shuffle -> shared-memory atomics -> ONE global atomic per candidate and CTA (integers: deterministic)
     #pragma unroll
     for (int k = 0; k < PLANE_CHUNK; ++k) {
         int v = warp_sum_i(cnt[k]);
@@ -89,135 +146,209 @@ __global__ void __launch_bounds__(PLANE_BLOCK) plane_eval_kernel(const float4 *_
     }
     __syncthreads();
     if (threadIdx.x < PLANE_CHUNK && s_cnt[threadIdx.x] && c0 + threadIdx.x < n_cand) atomicAdd(&counts[c0 + threadIdx.x], s_cnt[threadIdx.x]);
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = (atomicAdd(&st->ticket_eval, 1u) == gridDim.x * gridDim.y - 1);
+    __syncthreads();
+    if (!is_last || threadIdx.x != 0) return;
+    __threadfence();
+    st->ticket_eval = 0u;
+    plane_select(coefs, valid, counts, n_cand, n_rem, max_iterations, probability, st);
 }
 
-// replay of pcl::RandomSampleConsensus::computeModel over the pre-evaluated candidates
-__global__ void plane_select_kernel(const float4 *__restrict__ coefs, const int *__restrict__ valid, const uint32_t *__restrict__ counts,
-                                    int n_cand, int n_points, int max_iterations, double probability, PlaneSel *sel)
+// PCA refit over the inliers of the RANSAC model (SampleConsensusModelPlane::optimizeModelCoefficients): nine
+// order-independent fixed-point sums + the count; the last CTA converts the totals and refits in strict double.
+__global__ void __launch_bounds__(PLANE_BLOCK) plane_refit_kernel(const float4 *__restrict__ rem, float tau, const float *__restrict__ absmax,
+                                                                  PlaneState *st, long long *__restrict__ partials)
 {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    int iterations = 0, best = -1, best_count = -2147483647;
-    double k = 1.0;
-    const double log_prob = log(1.0 - probability);
-    const double one_over = n_points > 0 ? 1.0 / (double)n_points : 0.0;
-    const double eps = 2.220446049250313e-16;
-    for (int c = 0; c < n_cand && iterations < k; ++c) {
-        if (!valid[c]) continue;
-        int cc = (int)counts[c];
-        if (cc > best_count) {
-            best_count = cc; best = c;
-            double w = best_count * one_over;
-            double p_no = 1.0 - w * w * w;
-            if (p_no < eps) p_no = eps;
-            if (p_no > 1.0 - eps) p_no = 1.0 - eps;
-            k = log_prob / log(p_no);
-        }
-        ++iterations;
-        if (iterations > max_iterations) break;
-    }
-    sel->best = best; sel->best_count = best >= 0 ? best_count : 0; sel->iterations = iterations;
-    sel->stop = (best < 0 || best_count == 0) ? 1 : 0;
-    if (best >= 0) { sel->ransac = coefs[best]; sel->refined = coefs[best]; }
-}
-
-// PCA refit over the inliers of the RANSAC model (SampleConsensusModelPlane::optimizeModelCoefficients)
-__global__ void __launch_bounds__(PLANE_BLOCK) plane_refit_kernel(const float4 *__restrict__ rem, int n_rem, float tau, PlaneSel *sel,
-                                                                  double *__restrict__ partials)
-{
-    __shared__ double ws[PLANE_BLOCK / 32][10];
+    if (!st->active) return;
+    const int n_rem = st->n_rem;
+    __shared__ long long whi[PLANE_BLOCK / 32][10], wlo[PLANE_BLOCK / 32][10];
     __shared__ bool is_last;
-    if (sel->stop) return;
-    const float4 m = sel->ransac;
-    double s[10];
-    #pragma unroll
-    for (int k = 0; k < 10; ++k) s[k] = 0.0;
-    for (int i = blockIdx.x * PLANE_BLOCK + threadIdx.x; i < n_rem; i += gridDim.x * PLANE_BLOCK) {
-        const float4 p = rem[i];
-        if (fabsf(s3d_plane_eval(m.x, m.y, m.z, m.w, p.x, p.y, p.z)) < tau) {
-            double x = p.x, y = p.y, z = p.z;
-            s[0] += x; s[1] += y; s[2] += z;
-            s[3] += x * x; s[4] += x * y; s[5] += x * z; s[6] += y * y; s[7] += y * z; s[8] += z * z;
-            s[9] += 1.0;
+    const float4 m = st->ransac;
+    const FxScale fx = s3d_fx_make(s3d_pca_bound(*absmax));
+    const double M = __longlong_as_double((long long)fx.mbits);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane < 10) { whi[warp][lane] = 0; wlo[warp][lane] = 0; }
+    __syncwarp();
+    const int tstride = gridDim.x * PLANE_BLOCK;
+    int total_cnt = 0;
+    for (int i0 = blockIdx.x * PLANE_BLOCK + threadIdx.x - lane; i0 < n_rem; i0 += tstride * S3D_FX_SEGMENT_P) {     // warp-uniform segments
+        long long s[9];
+        #pragma unroll
+        for (int k = 0; k < 9; ++k) s[k] = 0;
+        int cnt = 0;
+        for (int q = 0; q < S3D_FX_SEGMENT_P; ++q) {
+            const int i = i0 + lane + q * tstride;
+            if (i >= n_rem) break;
+            const float4 p = rem[i];
+            if (fabsf(s3d_plane_eval(m.x, m.y, m.z, m.w, p.x, p.y, p.z)) < tau) {
+                const double x = p.x, y = p.y, z = p.z;
+                s[0] += s3d_fx_bits(x, 1.0, M); s[1] += s3d_fx_bits(y, 1.0, M); s[2] += s3d_fx_bits(z, 1.0, M);
+                s[3] += s3d_fx_bits(x, x, M); s[4] += s3d_fx_bits(x, y, M); s[5] += s3d_fx_bits(x, z, M);
+                s[6] += s3d_fx_bits(y, y, M); s[7] += s3d_fx_bits(y, z, M); s[8] += s3d_fx_bits(z, z, M);
+                ++cnt;
+            }
+        }
+        total_cnt += cnt;
+        #pragma unroll
+        for (int k = 0; k < 9; ++k) {
+            long long v = s[k] - (long long)((unsigned long long)cnt * fx.mbits);
+            #pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0) { long long hi, lo; s3d_fx_split(v, hi, lo); whi[warp][k] += hi; wlo[warp][k] += lo; }
         }
     }
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    #pragma unroll
-    for (int k = 0; k < 10; ++k) { double v = warp_sum_d(s[k]); if (lane == 0) ws[warp][k] = v; }
+    total_cnt = warp_sum_i(total_cnt);
+    if (lane == 0) wlo[warp][9] = total_cnt;
     __syncthreads();
     if (threadIdx.x < 10) {
-        double v = 0.0;
-        for (int w = 0; w < PLANE_BLOCK / 32; ++w) v += ws[w][threadIdx.x];
-        __stcg(&partials[(size_t)blockIdx.x * 10 + threadIdx.x], v);
+        long long hi = 0, lo = 0;
+        for (int w = 0; w < PLANE_BLOCK / 32; ++w) { hi += whi[w][threadIdx.x]; lo += wlo[w][threadIdx.x]; }
+        __stcg(&partials[(size_t)blockIdx.x * 20 + threadIdx.x], hi);
+        __stcg(&partials[(size_t)blockIdx.x * 20 + 10 + threadIdx.x], lo);
     }
     __threadfence();
     __syncthreads();
-    if (threadIdx.x == 0) is_last = (atomicAdd(&sel->ticket, 1u) == gridDim.x - 1);
+    if (threadIdx.x == 0) is_last = (atomicAdd(&st->ticket_refit, 1u) == gridDim.x - 1);
     __syncthreads();
     if (!is_last) return;
     __threadfence();
-    // final sum over the CTAs' rows in a fixed two-level order: 25 strided parts (250 threads, loads in flight together), then the parts
-    {
-        __shared__ double parts[25][10];
-        if (threadIdx.x < 250) {
-            const int slot = threadIdx.x % 10, part = threadIdx.x / 10;
-            double v = 0.0;
-            for (int b = part; b < (int)gridDim.x; b += 25) v += __ldcg(&partials[(size_t)b * 10 + slot]);
-            parts[part][slot] = v;
-        }
-        __syncthreads();
-        if (threadIdx.x < 10) {
-            double v = 0.0;
-            for (int q = 0; q < 25; ++q) v += parts[q][threadIdx.x];
-            ws[0][threadIdx.x] = v;
-        }
+    // total over the CTAs' rows: integers, any order (25 strided parts with their loads in flight together, then the parts)
+    __shared__ long long phi[25][10], plo[25][10];
+    __shared__ double tot[10];
+    if (threadIdx.x < 250) {
+        const int slot = threadIdx.x % 10, part = threadIdx.x / 10;
+        long long hi = 0, lo = 0;
+        for (int b = part; b < (int)gridDim.x; b += 25) { hi += __ldcg(&partials[(size_t)b * 20 + slot]); lo += __ldcg(&partials[(size_t)b * 20 + 10 + slot]); }
+        phi[part][slot] = hi; plo[part][slot] = lo;
+    }
+    __syncthreads();
+    if (threadIdx.x < 10) {
+        long long hi = 0, lo = 0;
+        for (int q = 0; q < 25; ++q) { hi += phi[q][threadIdx.x]; lo += plo[q][threadIdx.x]; }
+        tot[threadIdx.x] = threadIdx.x < 9 ? s3d_fx_value(hi, lo, fx.scale) : __ll2double_rn(lo);
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        const double *t = ws[0];
-        double ni = t[9];
+        const double ni = tot[9];
         float4 rc = m;
         if (ni >= 3.0) {
-            double cx = t[0] / ni, cy = t[1] / ni, cz = t[2] / ni;
-            double C[3][3], V[3][3], w[3];
-            C[0][0] = t[3] / ni - cx * cx; C[0][1] = C[1][0] = t[4] / ni - cx * cy; C[0][2] = C[2][0] = t[5] / ni - cx * cz;
-            C[1][1] = t[6] / ni - cy * cy; C[1][2] = C[2][1] = t[7] / ni - cy * cz; C[2][2] = t[8] / ni - cz * cz;
+            // strict double: the operations of oracle/plane_oracle.c, in its order
+            const sd nd(ni);
+            const sd cx = sd(tot[0]) / nd, cy = sd(tot[1]) / nd, cz = sd(tot[2]) / nd;
+            sd C[3][3], V[3][3], w[3];
+            C[0][0] = sd(tot[3]) / nd - cx * cx; C[0][1] = C[1][0] = sd(tot[4]) / nd - cx * cy; C[0][2] = C[2][0] = sd(tot[5]) / nd - cx * cz;
+            C[1][1] = sd(tot[6]) / nd - cy * cy; C[1][2] = C[2][1] = sd(tot[7]) / nd - cy * cz; C[2][2] = sd(tot[8]) / nd - cz * cz;
             s3d_jacobi3(C, V, w);
             int k = 0; if (w[1] < w[k]) k = 1; if (w[2] < w[k]) k = 2;
-            double nx = V[0][k], ny = V[1][k], nz = V[2][k];
-            double nn = sqrt(nx * nx + ny * ny + nz * nz);
-            nx /= nn; ny /= nn; nz /= nn;
-            double d = -(nx * cx + ny * cy + nz * cz);
-            if (d < 0) { nx = -nx; ny = -ny; nz = -nz; d = -d; }   // reference src/GraphicEnd.cpp:383-387
-            rc = make_float4((float)nx, (float)ny, (float)nz, (float)d);
+            sd nx = V[0][k], ny = V[1][k], nz = V[2][k];
+            const sd nn = sd_sqrt(nx * nx + ny * ny + nz * nz);
+            nx = nx / nn; ny = ny / nn; nz = nz / nn;
+            sd d = -(nx * cx + ny * cy + nz * cz);
+            if (d.v < 0) { nx = -nx; ny = -ny; nz = -nz; d = -d; }   // reference src/GraphicEnd.cpp:383-387
+            rc = make_float4((float)nx.v, (float)ny.v, (float)nz.v, (float)d.v);
         } else if (rc.w < 0.f) rc = make_float4(-rc.x, -rc.y, -rc.z, -rc.w);
-        sel->refined = rc;
-        sel->ticket = 0u;
+        st->refined = rc;
+        st->ticket_refit = 0u;
     }
 }
 
-struct KeepPred {   // keep = NOT an inlier of the refined model (ExtractIndices negative)
-    const float4 *rem; const PlaneSel *sel; float tau;
-    __device__ bool operator()(int i) const
-    {
-        if (sel->stop) return true;
-        const float4 m = sel->refined, p = rem[i];
-        return !(fabsf(s3d_plane_eval(m.x, m.y, m.z, m.w, p.x, p.y, p.z)) < tau);
+// ---- order-preserving removal of the inliers of the refined model (ExtractIndices negative, reference :419-420) ----
+__device__ __forceinline__ bool plane_keep(const float4 m, const float4 p, float tau)
+{
+    return !(fabsf(s3d_plane_eval(m.x, m.y, m.z, m.w, p.x, p.y, p.z)) < tau);
+}
+
+__global__ void __launch_bounds__(S3D_COMPACT_BLOCK) plane_count_kernel(const float4 *__restrict__ rem, float tau, const PlaneState *st,
+                                                                        uint32_t *__restrict__ block_counts)
+{
+    if (!st->active) return;
+    const int n_rem = st->n_rem;
+    if ((int)(blockIdx.x * S3D_COMPACT_BLOCK) >= n_rem) return;
+    __shared__ int warp_cnt[32];
+    const float4 m = st->refined;
+    const int i = blockIdx.x * S3D_COMPACT_BLOCK + threadIdx.x;
+    const bool keep = (i < n_rem) && plane_keep(m, rem[i], tau);
+    const unsigned b = __ballot_sync(0xffffffffu, keep);
+    if ((threadIdx.x & 31) == 0) warp_cnt[threadIdx.x >> 5] = __popc(b);
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        int v = warp_sum_i(warp_cnt[threadIdx.x]);
+        if (threadIdx.x == 0) block_counts[blockIdx.x] = (uint32_t)v;
     }
-};
-struct KeepEmit {
-    const float4 *rem; float4 *out;
-    __device__ void operator()(int i, uint32_t pos) const { out[pos] = rem[i]; }
-};
-struct InlierDrop {   // inliers leave the cloud: record their plane id and the plane normal
-    const float4 *rem; const PlaneSel *sel; int32_t *labels; float4 *nrm; int plane_id;
-    __device__ void operator()(int i) const
+}
+
+// Every block adds up the counts of the blocks before it (a few hundred values) instead of waiting for a scan kernel; kept
+// points go to rem_out in order, inliers get their label and the plane normal; the last block to finish closes the round.
+__global__ void __launch_bounds__(S3D_COMPACT_BLOCK) plane_write_kernel(const float4 *__restrict__ rem, float4 *__restrict__ rem_out, float tau,
+                                                                        const uint32_t *__restrict__ block_counts, int32_t *__restrict__ labels,
+                                                                        float4 *__restrict__ nrm, PlaneState *st)
+{
+    if (!st->active) return;
+    const int n_rem = st->n_rem, plane_id = st->n_planes;
+    if ((int)(blockIdx.x * S3D_COMPACT_BLOCK) >= n_rem) return;
+    const int nb = (n_rem + S3D_COMPACT_BLOCK - 1) / S3D_COMPACT_BLOCK;
+    __shared__ int warp_cnt[32];
+    __shared__ uint32_t warp_pre[32];
+    __shared__ uint32_t block_off, total_kept;
+    __shared__ bool is_last;
+    const float4 m = st->refined;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    // offset of this block = sum of the counts of blocks [0, blockIdx.x); total = sum over all nb blocks
     {
-        const float4 m = sel->refined;
-        int oi = __float_as_int(rem[i].w);
+        uint32_t before = 0u, all = 0u;
+        for (int k = threadIdx.x; k < nb; k += S3D_COMPACT_BLOCK) { const uint32_t v = block_counts[k]; all += v; if (k < (int)blockIdx.x) before += v; }
+        #pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { before += __shfl_xor_sync(0xffffffffu, before, o); all += __shfl_xor_sync(0xffffffffu, all, o); }
+        if (lane == 0) { warp_pre[w] = before; warp_cnt[w] = (int)all; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t b = 0u, a = 0u;
+            for (int k = 0; k < 32; ++k) { b += warp_pre[k]; a += (uint32_t)warp_cnt[k]; }
+            block_off = b; total_kept = a;
+        }
+        __syncthreads();
+    }
+    const int i = blockIdx.x * S3D_COMPACT_BLOCK + threadIdx.x;
+    const bool in = i < n_rem;
+    float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (in) p = rem[i];
+    const bool keep = in && plane_keep(m, p, tau);
+    const unsigned b = __ballot_sync(0xffffffffu, keep);
+    if (lane == 0) warp_cnt[w] = __popc(b);
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        int v = warp_cnt[threadIdx.x], incl = v;
+        #pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (threadIdx.x >= o) incl += t;
+        }
+        warp_cnt[threadIdx.x] = incl - v;
+    }
+    __syncthreads();
+    if (keep) rem_out[block_off + (uint32_t)warp_cnt[w] + (uint32_t)__popc(b & ((1u << lane) - 1u))] = p;
+    else if (in) {
+        const int oi = __float_as_int(p.w);
         labels[oi] = plane_id;
         nrm[oi] = make_float4(m.x, m.y, m.z, 1.0f);
     }
-};
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = (atomicAdd(&st->ticket_write, 1u) == (unsigned)nb - 1u);
+    __syncthreads();
+    if (!is_last || threadIdx.x != 0) return;
+    // close the round (reference :376-429): nothing removed -> the loop ends without a new plane
+    st->ticket_write = 0u;
+    const int nin = n_rem - (int)total_kept;
+    if (nin == 0) { st->stopped = 1; return; }
+    s3d_plane &pl = st->planes[plane_id];
+    pl.coef[0] = m.x; pl.coef[1] = m.y; pl.coef[2] = m.z; pl.coef[3] = m.w;
+    pl.inliers = nin; pl.hypotheses = st->iterations;
+    st->n_rem = (int)total_kept;
+    st->n_planes = plane_id + 1;
+}
 
 extern "C" void s3d_plane_params_default(s3d_plane_params *p)
 {
@@ -241,6 +372,8 @@ extern "C" int s3d_segment_planes(s3d_ctx *ctx, s3d_cloud *cloud, const s3d_plan
     if (!cloud->d_nrm) S3D_CUDA(ctx, s3d_dev_alloc_t(ctx, &cloud->d_nrm, sizeof(float4) * np));
     if (!cloud->d_labels) S3D_CUDA(ctx, s3d_dev_alloc_t(ctx, &cloud->d_labels, sizeof(int32_t) * np));
     cloud->grid.valid = false;
+    cloud->absmax_nrm_valid = false;
+    { int rc = s3d_cloud_absmax(ctx, cloud, false); if (rc) return rc; }
 
     const int n_cand = prm->max_iterations + PLANE_CANDIDATES_EXTRA;
     const int nblk_c = (int)((np + S3D_COMPACT_BLOCK - 1) / S3D_COMPACT_BLOCK);
@@ -250,8 +383,8 @@ extern "C" int s3d_segment_planes(s3d_ctx *ctx, s3d_cloud *cloud, const s3d_plan
     auto carve = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
     size_t o_remA = carve(sizeof(float4) * np), o_remB = carve(sizeof(float4) * np);
     size_t o_coef = carve(sizeof(float4) * PLANE_MAX_CAND), o_valid = carve(sizeof(int) * PLANE_MAX_CAND);
-    size_t o_cnt = carve(sizeof(uint32_t) * PLANE_MAX_CAND), o_sel = carve(sizeof(PlaneSel));
-    size_t o_part = carve(sizeof(double) * 10 * (size_t)g_wide), o_blk = carve(sizeof(uint32_t) * (size_t)(nblk_c + 2));
+    size_t o_cnt = carve(sizeof(uint32_t) * PLANE_MAX_CAND), o_state = carve(sizeof(PlaneState));
+    size_t o_part = carve(sizeof(long long) * 20 * (size_t)g_wide), o_blk = carve(sizeof(uint32_t) * (size_t)(nblk_c + 2));
     if (off > ctx->cap_seg) {
         cudaFree(ctx->d_seg); ctx->d_seg = nullptr; ctx->cap_seg = 0;
         S3D_CUDA(ctx, cudaMalloc(&ctx->d_seg, off));
@@ -260,47 +393,63 @@ extern "C" int s3d_segment_planes(s3d_ctx *ctx, s3d_cloud *cloud, const s3d_plan
     char *base = (char *)ctx->d_seg;
     float4 *rem = (float4 *)(base + o_remA), *rem2 = (float4 *)(base + o_remB);
     float4 *coefs = (float4 *)(base + o_coef); int *valid = (int *)(base + o_valid);
-    uint32_t *counts = (uint32_t *)(base + o_cnt); PlaneSel *sel = (PlaneSel *)(base + o_sel);
-    double *partials = (double *)(base + o_part); uint32_t *blk = (uint32_t *)(base + o_blk);
-    struct HostBack { PlaneSel sel; uint32_t kept; } *hb = (HostBack *)s3d_pinned(ctx, sizeof(HostBack));
+    uint32_t *counts = (uint32_t *)(base + o_cnt); PlaneState *state = (PlaneState *)(base + o_state);
+    long long *partials = (long long *)(base + o_part); uint32_t *blk = (uint32_t *)(base + o_blk);
+    PlaneState *hb = (PlaneState *)s3d_pinned(ctx, sizeof(PlaneState));
     if (!hb) return s3d_fail(ctx, S3D_E_CUDA, "pinned alloc");
     cudaStream_t st = ctx->stream;
+    const float tau = prm->distance_threshold;
 
-    plane_init_kernel<<<g_wide, 256, 0, st>>>(cloud->d_pts, n, rem, cloud->d_labels, cloud->d_nrm);
-    S3D_LAUNCHED(ctx);
-    int n_rem = n, n_planes = 0;
-    while ((double)n_rem > (double)prm->plane_percent * (double)n && n_planes < prm->max_planes) {   // :372, :424
-        if (n_rem < 3) break;
-        plane_hyp_kernel<<<(n_cand + 127) / 128, 128, 0, st>>>(rem, n_rem, prm->seed, n_planes, n_cand, coefs, valid, counts, sel);
-        S3D_LAUNCHED(ctx);
-        dim3 ge(std::max(1, std::min(ctx->sm_count * 2, (n_rem + PLANE_BLOCK - 1) / PLANE_BLOCK)), (n_cand + PLANE_CHUNK - 1) / PLANE_CHUNK);
-        plane_eval_kernel<<<ge, PLANE_BLOCK, 0, st>>>(rem, n_rem, coefs, valid, n_cand, prm->distance_threshold, counts);
-        S3D_LAUNCHED(ctx);
-        plane_select_kernel<<<1, 32, 0, st>>>(coefs, valid, counts, n_cand, n_rem, prm->max_iterations, (double)prm->probability, sel);
-        S3D_LAUNCHED(ctx);
-        plane_refit_kernel<<<ctx->sm_count, PLANE_BLOCK, 0, st>>>(rem, n_rem, prm->distance_threshold, sel, partials);   // one CTA per SM: the kernel is mostly its reduction
-        S3D_LAUNCHED(ctx);
-        const int nb = (n_rem + S3D_COMPACT_BLOCK - 1) / S3D_COMPACT_BLOCK;
-        KeepPred pred{rem, sel, prm->distance_threshold};
-        compact_count_kernel<<<nb, S3D_COMPACT_BLOCK, 0, st>>>(n_rem, pred, blk);
-        S3D_LAUNCHED(ctx);
-        compact_scan_kernel<<<1, 1024, 0, st>>>(blk, nb, blk + nb);
-        S3D_LAUNCHED(ctx);
-        compact_write_kernel<<<nb, S3D_COMPACT_BLOCK, 0, st>>>(n_rem, pred, KeepEmit{rem, rem2},
-                                                                InlierDrop{rem, sel, cloud->d_labels, cloud->d_nrm, n_planes}, blk);
-        S3D_LAUNCHED(ctx);
-        S3D_CUDA(ctx, cudaMemcpyAsync(&hb->sel, sel, sizeof(PlaneSel), cudaMemcpyDeviceToHost, st));
-        S3D_CUDA(ctx, cudaMemcpyAsync(&hb->kept, blk + nb, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-        S3D_CUDA(ctx, cudaStreamSynchronize(st));
-        if (hb->sel.stop) break;                                   // :376-379
-        const int nin = n_rem - (int)hb->kept;
-        if (nin == 0) break;
-        s3d_plane &pl = planes_out[n_planes];
-        pl.coef[0] = hb->sel.refined.x; pl.coef[1] = hb->sel.refined.y; pl.coef[2] = hb->sel.refined.z; pl.coef[3] = hb->sel.refined.w;
-        pl.inliers = nin; pl.hypotheses = hb->sel.iterations;
-        std::swap(rem, rem2);
-        n_rem = (int)hb->kept; ++n_planes;
+    if (!ctx->ev_plane[0]) {
+        for (int k = 0; k < 2; ++k) S3D_CUDA(ctx, cudaEventCreate(&ctx->ev_plane[k]));
+        for (int k = 0; k < 2 * S3D_MAX_PLANES; ++k) S3D_CUDA(ctx, cudaEventCreate(&ctx->ev_eval[k]));
     }
+    cudaEventRecord(ctx->ev_plane[0], st);
+    plane_init_kernel<<<g_wide, 256, 0, st>>>(cloud->d_pts, n, rem, cloud->d_labels, cloud->d_nrm, state);
+    S3D_LAUNCHED(ctx);
+    // worst-case grids (the first round scans all n points); kernels of rounds the device loop has left return at once
+    const dim3 ge(std::max(1, std::min(ctx->sm_count * 2, (n + PLANE_BLOCK - 1) / PLANE_BLOCK)), (n_cand + PLANE_CHUNK - 1) / PLANE_CHUNK);
+    const int nb = std::max(1, (n + S3D_COMPACT_BLOCK - 1) / S3D_COMPACT_BLOCK);
+    for (int round = 0; round < prm->max_planes; ++round) {
+        plane_hyp_kernel<<<1, PLANE_MAX_CAND, 0, st>>>(rem, n, prm->plane_percent, prm->max_planes, prm->seed, round, n_cand, coefs, valid, counts, state);
+        S3D_LAUNCHED(ctx);
+        cudaEventRecord(ctx->ev_eval[2 * round], st);
+        plane_eval_kernel<<<ge, PLANE_BLOCK, 0, st>>>(rem, coefs, valid, n_cand, tau, counts, prm->max_iterations, (double)prm->probability, state);
+        S3D_LAUNCHED(ctx);
+        cudaEventRecord(ctx->ev_eval[2 * round + 1], st);
+        plane_refit_kernel<<<ctx->sm_count, PLANE_BLOCK, 0, st>>>(rem, tau, cloud->d_absmax, state, partials);   // one CTA per SM: the kernel is mostly its reduction
+        S3D_LAUNCHED(ctx);
+        plane_count_kernel<<<nb, S3D_COMPACT_BLOCK, 0, st>>>(rem, tau, state, blk);
+        S3D_LAUNCHED(ctx);
+        plane_write_kernel<<<nb, S3D_COMPACT_BLOCK, 0, st>>>(rem, rem2, tau, blk, cloud->d_labels, cloud->d_nrm, state);
+        S3D_LAUNCHED(ctx);
+        std::swap(rem, rem2);
+    }
+    cudaEventRecord(ctx->ev_plane[1], st);
+    S3D_CUDA(ctx, cudaMemcpyAsync(hb, state, sizeof(PlaneState), cudaMemcpyDeviceToHost, st));
+    S3D_CUDA(ctx, cudaStreamSynchronize(st));
+    const int n_planes = hb->n_planes;
+    for (int k = 0; k < n_planes; ++k) planes_out[k] = hb->planes[k];
     *n_planes_out = n_planes;
+    // bookkeeping for s3d_last_plane_timing: points scanned by the evaluation passes
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ctx->ev_plane[0], ctx->ev_plane[1]);
+    ctx->plane_timing.total_ms = ms;
+    ctx->plane_timing.rounds = 0; ctx->plane_timing.points_scanned = 0;
+    for (int k = 0; k < S3D_MAX_PLANES; ++k) if (hb->rem_at_round[k] > 0) { ctx->plane_timing.rounds++; ctx->plane_timing.points_scanned += hb->rem_at_round[k]; }
+    ctx->plane_timing.eval_passes_per_round = (int)ge.y;
+    ctx->plane_timing.eval_ms = 0.f;
+    for (int k = 0; k < ctx->plane_timing.rounds && k < prm->max_planes; ++k) {
+        float e = 0.f;
+        cudaEventElapsedTime(&e, ctx->ev_eval[2 * k], ctx->ev_eval[2 * k + 1]);
+        ctx->plane_timing.eval_ms += e;
+    }
+    return S3D_OK;
+}
+
+extern "C" int s3d_last_plane_timing(const s3d_ctx *ctx, s3d_plane_timing *out)
+{
+    if (!ctx || !out) return S3D_E_ARG;
+    *out = ctx->plane_timing;
     return S3D_OK;
 }

@@ -32,15 +32,17 @@ def test_library_exports_every_declared_symbol():
 
 def test_struct_layouts_match_c(tmp_path):
     src = tmp_path / "sz.c"
-    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "slam3d_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n",'
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "slam3d_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n",'
                    'sizeof(s3d_icp_params),sizeof(s3d_result),sizeof(s3d_plane_params),sizeof(s3d_plane),sizeof(s3d_camera),'
-                   'sizeof(s3d_timing),offsetof(s3d_result,inliers),offsetof(s3d_icp_params,pivot_eps));return 0;}\n')
+                   'sizeof(s3d_timing),offsetof(s3d_result,inliers),offsetof(s3d_icp_params,pivot_eps),sizeof(s3d_plane_timing),'
+                   'offsetof(s3d_plane_timing,points_scanned));return 0;}\n')
     exe = tmp_path / "sz"
     subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True,
                    env={**os.environ, "CC": "gcc"})
     got = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
     want = [C.sizeof(_abi.IcpParams), C.sizeof(_abi.Result), C.sizeof(_abi.PlaneParams), C.sizeof(_abi.Plane),
-            C.sizeof(_abi.CameraC), C.sizeof(_abi.Timing), _abi.Result.inliers.offset, _abi.IcpParams.pivot_eps.offset]
+            C.sizeof(_abi.CameraC), C.sizeof(_abi.Timing), _abi.Result.inliers.offset, _abi.IcpParams.pivot_eps.offset,
+            C.sizeof(_abi.PlaneTiming), _abi.PlaneTiming.points_scanned.offset]
     assert got == want
 
 

@@ -86,7 +86,9 @@ def test_real_pair_cuda_matches_oracle(ctx):
     got = ct.download(xyz=False, normals=True, labels=True)
     seg = oracle.segment_planes(tgt, prm)
     assert len(planes) == len(seg["planes"])
-    assert (got["labels"] != seg["labels"]).sum() <= 4
+    assert np.array_equal(got["labels"], seg["labels"])
+    for a, b in zip(planes, seg["planes"]):
+        assert np.array_equal(a["coef"], b["coef"]) and a["inliers"] == b["inliers"] and a["hypotheses"] == b["hypotheses"]
     icp = _abi.icp_params(10, max_corr_dist=0.3)
     r = ctx.register(cs, ct, None, icp)
     nrm4 = np.c_[got["normals"], (got["labels"] >= 0).astype(np.float32)].astype(np.float32)
@@ -95,4 +97,5 @@ def test_real_pair_cuda_matches_oracle(ctx):
     if o["status"] == 0:
         ok, err = pose_close(r["T"], o["T"], 1e-4, 1e-4)
         assert ok, err
+        assert np.array_equal(r["T"], o["T"]) and r["inliers"] == o["inliers"]
     cs.free(); ct.free()

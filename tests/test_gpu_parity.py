@@ -1,6 +1,8 @@
 """GPU parity tests (run with -m gpu on the B200): the CUDA path, called through the C ABI, against the CPU
 oracle on the same seeded inputs.  Bar: bit-exact for integer/index results (correspondences, inlier counts,
-labels, flags); pose within 1e-4 rad / 1e-4 m (the tolerance BASELINE.json's north_star states)."""
+labels, flags) at EVERY iteration; the north star's pose tolerance is 1e-4 rad / 1e-4 m, and because the sums
+are order independent (fixed-point accumulation) and the small solvers run in strict double with the oracle's
+operation order, the poses, fitness values and plane coefficients are in fact equal bit for bit."""
 import numpy as np
 import pytest
 
@@ -33,7 +35,7 @@ def test_correspondences_bit_exact(ctx, small_pair, search):
     o = oracle.icp(p["src"], p["tgt"], p["tgt_normals"], params=prm, want_nn=True)
     assert np.array_equal(nn, o["nn"])
     assert r["inliers"] == o["inliers"] and r["status"] == o["status"] == 0
-    assert abs(r["fitness"] - o["fitness"]) <= 1e-6 * o["fitness"]
+    assert r["fitness"] == o["fitness"] and np.array_equal(r["T"], o["T"])
 
 
 @pytest.mark.parametrize("stride", [3, 4])
@@ -101,23 +103,20 @@ def test_icp_pose_parity_small(ctx, small_pair, est, search):
     assert r["status"] == 0 and r["iterations"] == 10
     ok, err = pose_close(r["T"], o["T"], ROT_TOL, TRANS_TOL)
     assert ok, err
-    assert abs(r["norm"] - o["norm"]) < 1e-4
-    assert (nn != o["nn"]).mean() < 1e-3       # identical up to float near-ties after 10 iterations
-    assert abs(r["inliers"] - o["inliers"]) <= 2
+    assert np.array_equal(nn, o["nn"]) and r["inliers"] == o["inliers"]
+    assert np.array_equal(r["T"], o["T"]) and r["norm"] == o["norm"] and r["fitness"] == o["fitness"]
 
 
 def test_grid_and_brute_agree_bitwise(ctx, small_pair):
-    """Three independent exact searches: identical correspondences after 6 iterations.  The per-iteration-launch
-    modes also share the reduction order (same pose bits); the persistent kernel sums in another fixed order."""
+    """Three independent exact searches: identical correspondences and identical pose bits after 6 iterations (the sums do
+    not depend on the order in which a kernel adds them)."""
     p = small_pair
     a, nna = _gpu_icp(ctx, p, _abi.icp_params(6, search=_abi.SEARCH_GRID))
     b, nnb = _gpu_icp(ctx, p, _abi.icp_params(6, search=_abi.SEARCH_BRUTE))
     c, nnc = _gpu_icp(ctx, p, _abi.icp_params(6, search=_abi.SEARCH_GRID_LANE))
     assert np.array_equal(nna, nnb) and np.array_equal(nnc, nnb)
-    assert np.array_equal(c["T"], b["T"])
-    assert a["inliers"] == b["inliers"]
-    ok, err = pose_close(a["T"], b["T"], 1e-7, 1e-7)
-    assert ok, err
+    assert np.array_equal(c["T"], b["T"]) and np.array_equal(a["T"], b["T"])
+    assert a["inliers"] == b["inliers"] == c["inliers"] and a["fitness"] == b["fitness"] == c["fitness"]
 
 
 @pytest.mark.parametrize("k", [2, 3, 5, 9, 16])
@@ -153,6 +152,7 @@ def test_icp_parity_ragged_and_quantised(ctx, small_cam, kw):
     ok, err = pose_close(r["T"], o["T"], ROT_TOL, TRANS_TOL)
     assert ok, err
     assert r["status"] == o["status"]
+    assert np.array_equal(nn, o["nn"]) and np.array_equal(r["T"], o["T"]) and r["inliers"] == o["inliers"]
 
 
 def test_icp_guess_and_gate(ctx, small_pair):
@@ -162,7 +162,7 @@ def test_icp_guess_and_gate(ctx, small_pair):
     o = oracle.icp(p["src"], p["tgt"], p["tgt_normals"], guess=p["T_gt"], params=prm, want_nn=True)
     ok, err = pose_close(r["T"], o["T"], ROT_TOL, TRANS_TOL)
     assert ok, err
-    assert abs(r["inliers"] - o["inliers"]) <= 2
+    assert r["inliers"] == o["inliers"] and np.array_equal(nn, o["nn"]) and np.array_equal(r["T"], o["T"])
     assert (nn == -1).sum() > 0 or r["inliers"] == len(p["src"])
 
 
@@ -224,6 +224,7 @@ def test_batch_shared_target_matches_single(ctx, small_cam):
         o = oracle.icp(s, base["tgt"], base["tgt_normals"], params=prm)
         ok, err = pose_close(r["T"], o["T"], ROT_TOL, TRANS_TOL)
         assert ok, (i, err)
+        assert np.array_equal(r["T"], o["T"]) and r["inliers"] == o["inliers"], i
         ok, err = pose_close(r["T"], gts[i], 3e-3, 8e-3)
         assert ok, (i, err)
     for c in clouds:
@@ -247,8 +248,7 @@ def test_batch_with_more_pairs_than_ctas(ctx):
     for k, i in enumerate(idx):
         assert res[k]["status"] == singles[i]["status"] == 0
         assert res[k]["inliers"] == singles[i]["inliers"]
-        ok, err = pose_close(res[k]["T"], singles[i]["T"], 1e-9, 1e-9)
-        assert ok, (k, err)
+        assert np.array_equal(res[k]["T"], singles[i]["T"]) and res[k]["fitness"] == singles[i]["fitness"], k
     for c in srcs + tgts:
         c.free()
 
@@ -274,7 +274,7 @@ def test_full_size_config1_gate(ctx, full_pair):
     o = oracle.icp(p["src"], p["tgt"], p["tgt_normals"], params=prm, want_nn=True, nthreads=0)
     ok, err = pose_close(r["T"], o["T"], ROT_TOL, TRANS_TOL)
     assert ok, err
-    assert (nn != o["nn"]).mean() < 1e-3
+    assert np.array_equal(nn, o["nn"]) and np.array_equal(r["T"], o["T"]) and r["inliers"] == o["inliers"] and r["fitness"] == o["fitness"]
     # first-iteration correspondences are bit exact at full size
     r1, nn1 = _gpu_icp(ctx, p, _abi.icp_params(1))
     idx, _ = oracle.nn(p["src"], p["tgt"], None, nthreads=0)
@@ -300,6 +300,7 @@ def test_full_size_config2_30_iterations(ctx, full_pair):
     o = oracle.icp(p["src"], p["tgt"], p["tgt_normals"], params=prm, nthreads=0)
     ok, err = pose_close(r["T"], o["T"], ROT_TOL, TRANS_TOL)
     assert ok, err
+    assert np.array_equal(r["T"], o["T"]) and r["inliers"] == o["inliers"] and r["norm"] == o["norm"]
     ok, err = pose_close(r["T"], p["T_gt"], 1e-3, 3e-3)
     assert ok, err
 
@@ -309,9 +310,7 @@ def test_full_size_brute_force_matches_grid(ctx, full_pair):
     a, nna = _gpu_icp(ctx, p, _abi.icp_params(2, search=_abi.SEARCH_GRID))
     b, nnb = _gpu_icp(ctx, p, _abi.icp_params(2, search=_abi.SEARCH_BRUTE))
     c, nnc = _gpu_icp(ctx, p, _abi.icp_params(2, search=_abi.SEARCH_GRID_LANE))
-    assert np.array_equal(nna, nnb) and np.array_equal(nnc, nnb) and np.array_equal(c["T"], b["T"])
-    ok, err = pose_close(a["T"], b["T"], 1e-7, 1e-7)
-    assert ok, err
+    assert np.array_equal(nna, nnb) and np.array_equal(nnc, nnb) and np.array_equal(c["T"], b["T"]) and np.array_equal(a["T"], b["T"])
 
 
 def test_roundtrip_property_full_size(ctx, full_pair):
@@ -347,12 +346,9 @@ def test_plane_segmentation_parity(ctx, small_cam, kw):
     assert len(planes) == len(o["planes"]) == 3
     for a, b in zip(planes, o["planes"]):
         assert a["hypotheses"] == b["hypotheses"]
-        assert np.allclose(a["coef"], b["coef"], atol=2e-6)
-        assert abs(a["inliers"] - b["inliers"]) <= 2           # a point exactly on the threshold may flip with 1-ulp coefficient noise
-    mism = (got["labels"] != o["labels"]).sum()
-    assert mism <= 4, mism
-    same = got["labels"] == o["labels"]
-    assert np.allclose(got["normals"][same], o["normals"][same, :3], atol=2e-6)
+        assert np.array_equal(a["coef"], b["coef"]) and a["inliers"] == b["inliers"]
+    assert np.array_equal(got["labels"], o["labels"])
+    assert np.array_equal(got["normals"], o["normals"][:, :3])
 
 
 def test_plane_segmentation_full_size_and_icp_with_segmented_normals(ctx, full_pair):
@@ -363,9 +359,9 @@ def test_plane_segmentation_full_size_and_icp_with_segmented_normals(ctx, full_p
     got = tgt.download(xyz=False, normals=True, labels=True)
     o = oracle.segment_planes(p["tgt"], prm)
     assert len(planes) == len(o["planes"]) == 3
-    assert (got["labels"] != o["labels"]).sum() <= 8
+    assert np.array_equal(got["labels"], o["labels"]) and np.array_equal(got["normals"], o["normals"][:, :3])
     for a, b in zip(planes, o["planes"]):
-        assert a["hypotheses"] == b["hypotheses"] and np.allclose(a["coef"], b["coef"], atol=2e-6)
+        assert a["hypotheses"] == b["hypotheses"] and np.array_equal(a["coef"], b["coef"]) and a["inliers"] == b["inliers"]
     # the reference flow: extract planes, then register against them
     src = ctx.upload(p["src"])
     icp = _abi.icp_params(10)
@@ -374,6 +370,9 @@ def test_plane_segmentation_full_size_and_icp_with_segmented_normals(ctx, full_p
     oi = oracle.icp(p["src"], p["tgt"], nrm4, params=icp, nthreads=0)
     ok, err = pose_close(r["T"], oi["T"], ROT_TOL, TRANS_TOL)
     assert ok, err
+    assert np.array_equal(r["T"], oi["T"]) and r["inliers"] == oi["inliers"]
+    tm = ctx.last_plane_timing()
+    assert tm["rounds"] == 3 and tm["eval_passes_per_round"] == 1 and 307200 < tm["points_scanned"] < 3 * 307200 and 0 < tm["eval_ms"] <= tm["total_ms"]
     src.free(); tgt.free()
 
 
@@ -393,7 +392,7 @@ def test_plane_segmentation_edge_cases(ctx):
     c.free()
     o = oracle.segment_planes(np.c_[pts, np.ones(len(pts), np.float32)], prm)
     assert len(planes) == len(o["planes"]) == 1 and (lab == 0).all()
-    assert np.allclose(planes[0]["coef"], o["planes"][0]["coef"], atol=2e-6)
+    assert np.array_equal(planes[0]["coef"], o["planes"][0]["coef"])
 
 
 # ---- ingest and keypoint planarity ------------------------------------------------------------------------
