@@ -451,6 +451,9 @@ void GraphicEnd::findMoreLoops()
         }
     }
     cout << BOLDRED << "Total " << _moreLoops << " loops found. " << RESET << endl;
+    size_t live = 0, peak = 0;
+    s3d_memory_stats(_ctx, &live, &peak, 0);
+    cout << "Peak resident clouds: " << _peakClouds << " peak device bytes: " << peak << endl;
 }
 
 bool GraphicEnd::check(int frame1, int frame2)
