@@ -91,7 +91,8 @@ static inline int orc_plane_from3(const float *p0, const float *p1, const float 
 }
 
 /* cyclic Jacobi eigen-decomposition of a symmetric 3x3 (double). A is destroyed; V columns are
- * eigenvectors, w eigenvalues (unsorted). Fixed 12 sweeps: identical control flow on CPU/GPU. */
+ * eigenvectors, w eigenvalues (unsorted). At most 12 sweeps, left when the off-diagonal part is negligible; the test
+ * uses the same strict operations on CPU and GPU, so the control flow is identical. */
 static inline void orc_jacobi3(double A[3][3], double V[3][3], double w[3])
 {
     for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) V[i][j] = (i == j);
@@ -115,6 +116,10 @@ static inline void orc_jacobi3(double A[3][3], double V[3][3], double w[3])
                 V[k][p] = c * vkp - s * vkq; V[k][q] = s * vkp + c * vkq;
             }
         }
+        /* converged: the off-diagonal part is below 1e-22 of the diagonal (quadratic convergence: typically 4-5 sweeps) */
+        double off = (fabs(A[0][1]) + fabs(A[0][2])) + fabs(A[1][2]);
+        double dia = (fabs(A[0][0]) + fabs(A[1][1])) + fabs(A[2][2]);
+        if (off <= 1e-22 * dia) break;
     }
     for (int i = 0; i < 3; ++i) w[i] = A[i][i];
 }

@@ -131,7 +131,7 @@ extern "C" void s3d_destroy(s3d_ctx *ctx)
     cudaFree(ctx->d_desc); cudaFreeHost(ctx->h_desc);
     cudaFree(ctx->d_state); cudaFreeHost(ctx->h_state);
     cudaFree(ctx->d_partials); cudaFree(ctx->d_nn_idx); cudaFree(ctx->d_nn_d2); cudaFree(ctx->d_nn_pos); cudaFree(ctx->d_last_nn);
-    cudaFree(ctx->d_cq); cudaFree(ctx->d_cn); cudaFree(ctx->d_lb); cudaFree(ctx->d_cq2); cudaFree(ctx->d_barriers);
+    cudaFree(ctx->d_cq); cudaFree(ctx->d_cn); cudaFree(ctx->d_flags); cudaFree(ctx->d_cq2); cudaFree(ctx->d_pend); cudaFree(ctx->d_barriers);
     cudaFree(ctx->d_seg);
     cudaFree(ctx->d_gather_send); cudaFree(ctx->d_gather_recv);
     if (ctx->h_gather) cudaFreeHost(ctx->h_gather);

@@ -101,7 +101,7 @@ __device__ __forceinline__ bool operator>=(sd a, sd b) { return a.v >= b.v; }
 __device__ __forceinline__ sd sd_sqrt(sd a) { return sd(__dsqrt_rn(a.v)); }
 __device__ __forceinline__ sd sd_fabs(sd a) { return sd(fabs(a.v)); }
 
-// cyclic Jacobi on a symmetric 3x3 in strict double, fixed 12 sweeps (same operations as orc_jacobi3)
+// cyclic Jacobi on a symmetric 3x3 in strict double, at most 12 sweeps with orc_jacobi3's convergence exit (same operations)
 __device__ inline void s3d_jacobi3(sd A[3][3], sd V[3][3], sd w[3])
 {
     for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) V[i][j] = sd(i == j ? 1.0 : 0.0);
@@ -125,6 +125,10 @@ __device__ inline void s3d_jacobi3(sd A[3][3], sd V[3][3], sd w[3])
                 V[k][p] = c * vkp - s * vkq; V[k][q] = s * vkp + c * vkq;
             }
         }
+        // converged: the off-diagonal part is below 1e-22 of the diagonal (the oracle takes the same exit)
+        const sd off = (sd_fabs(A[0][1]) + sd_fabs(A[0][2])) + sd_fabs(A[1][2]);
+        const sd dia = (sd_fabs(A[0][0]) + sd_fabs(A[1][1])) + sd_fabs(A[2][2]);
+        if (off.v <= (sd(1e-22) * dia).v) break;
     }
     for (int i = 0; i < 3; ++i) w[i] = A[i][i];
 }

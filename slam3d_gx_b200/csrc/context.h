@@ -103,7 +103,8 @@ struct s3d_ctx {
     int last_nn_n = 0; int32_t *d_last_nn = nullptr; int cap_last_nn = 0;
     // persistent tile-search path: per-query correspondence cache + group barriers
     size_t cap_tile_nn = 0;
-    float4 *d_cq = nullptr; float4 *d_cn = nullptr; float4 *d_lb = nullptr; float4 *d_cq2 = nullptr;
+    float4 *d_cq = nullptr; float4 *d_cn = nullptr; float4 *d_cq2 = nullptr; uint8_t *d_flags = nullptr;
+    uint32_t *d_pend = nullptr; size_t cap_pend = 0;    // pending lists of the CTAs (octets that need a search)
     unsigned *d_barriers = nullptr; int cap_barriers = 0;
     int persist_resident[2] = {0, 0};   // co-resident CTAs of icp_persist_kernel<EST> on this device
     bool brute_attr_done = false;       // dynamic shared-memory opt-in of nn_brute_tma_kernel done on this ctx's device

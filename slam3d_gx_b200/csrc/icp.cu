@@ -599,7 +599,12 @@ __global__ void __launch_bounds__(ICP_BLOCK, 2) icp_accum_kernel(const PairDesc 
 #endif
 static_assert(TS_CAP * 16 >= 29 * 33 * 8, "the warp tile also carries the transposed 29 x 33 int64 reduction");
 #define TS_WARPS (TS_BLOCK / 32)
-#define TS_STAGE (TS_CAP / 128)     // chunks of per-query state (32 lanes x 4 float4) a warp's tile holds
+#define PS_CHUNK_BYTES 1600u                        // one staged chunk of 32 queries: point, correspondence, normal+bound (3 x 512 B), 32 flag bytes, padding
+#define PS_STAGE ((TS_CAP * 16) / PS_CHUNK_BYTES)   // chunks a warp's tile stages at a time (6)
+#define PS_HIST 64                                  // poses kept (ring): a query's position at its last search is recomputed from them
+#define PS_REBASE_AGE 48                            // a kept query is re-based onto the current pose before its ring slot is reused
+#define PS_FLAG_TIE 64u
+#define PS_FLAG_NRM 128u
 
 #if defined(S3D_STATS) || defined(S3D_PHASES)
 #define PHASE_T0() long long ph_t = clock64()
@@ -613,12 +618,15 @@ struct PersistArgs {
     const PairDesc *descs; PairState *states;
     long long *partials;         // [2][groups][group_ctas][S3D_ROW]: (hi, lo) partial sums, double buffered by barrier parity
     unsigned *barriers;          // [groups], zero at launch, monotonic
-    float4 *cq;                  // per query: its correspondence (x,y,z, original target index; -1: none)
-    float4 *cn;                  // per query: the correspondence's normal (nx,ny,nz,valid)   (point-to-plane)
-    float4 *cq2;                 // per query with a near tie (xl.w < 0): the runner-up (x,y,z, original index)
-    float4 *xl;                  // per query: its transformed position when it was last searched (x,y,z) and, in .w, the lower
-                                 // bound found then on its distance to every target point other than the correspondence
-    long long nn_stride;         // queries per pair in the three arrays above
+    // per-query state between iterations (49 bytes per query are read by the streaming pass):
+    float4 *cq;                  // its correspondence (x,y,z, original target index; -1: none)
+    float4 *cn;                  // the correspondence's normal (nx,ny,nz) and, in .w, the lower bound found at the query's last search on
+                                 // its distance to every target point other than the correspondence (near ties: other than it and the runner-up)
+    float4 *cq2;                 // near ties only (PS_FLAG_TIE): the runner-up (x,y,z, original index)
+    uint8_t *flags;              // bits 0-5: ring slot of the iteration of the last search, PS_FLAG_TIE, PS_FLAG_NRM (the normal is valid)
+    uint32_t *pend;              // [ctas][pend_stride]: octets of the CTA with queries that need a search, (local octet << 8) | lane mask
+    long long nn_stride;         // queries per pair in the per-query arrays (a multiple of 8)
+    int pend_stride;
     int n_pairs, groups, group_ctas, iterations;
     float max_d2; int min_corr; double pivot_eps;
     int32_t *nn_out;             // correspondences of the last iteration (single pair) or null
@@ -626,54 +634,47 @@ struct PersistArgs {
     float first_cells;           // first-guess search radius of the first iteration when the decimated index is not used, in cells
     int use_coarse;              // first iteration: bound the search with the nearest point of the decimated index
     float slack_cells;           // extra search radius beyond the seed distance, in cells: buys the skip test its margin
-    int dyn_octets;              // octets handed out at a time (1, 2 or 4: one per 8 lanes of the taking warp)
-    int dyn_div;                 // octets are handed out dynamically while more than 1/dyn_div of a CTA's queries needed a search
-                                 // in its previous iteration (0: always the fixed assignment)
+    int item_octets;             // octets a warp takes from the pending list at a time (1, 2 or 4: one per 8 lanes)
 };
 
-__device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned *p)      // polling load: no L1 invalidate per poll
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p)
 {
     unsigned v;
-    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
-
-
-// Near tie (rare path of the skip test, a real call to keep it out of the streaming loop's registers): the runner-up q2
-// of the query's last search was kept, and every target point other than q and q2 is at least `bound3` away from the
-// query's present position.  Both are evaluated; the nearer (lower original index on equality) is the exact nearest
-// neighbour if it beats that bound.  When the two swap roles the stored state is swapped too.
-template <int EST>
-__device__ __noinline__ int resolve_near_tie(float4 *cq, float4 *cq2, float4 *cn, const float4 *tgt_nrm, int i, float x, float y, float z,
-                                             float bound3, float4 q, float d2q)
+__device__ __forceinline__ void red_release_add_u32(unsigned *p, unsigned v)
 {
-    // returns 0: not settled (search), 1: q stays, 2: q2 took over (cq/cq2/cn of the query rewritten; the caller reloads them).
-    // Everything by value: nothing of the caller's streaming loop has its address taken.
-    const float4 q2 = __ldcg(&cq2[i]);
-    const float d2b = s3d_dist2(x, y, z, q2.x, q2.y, q2.z);
-    const bool second = d2b < d2q || (d2b == d2q && __float_as_int(q2.w) < __float_as_int(q.w));
-    const float dw = sqrtf(second ? d2b : d2q);
-    if (!(dw * 1.000002f + 2e-7f < bound3)) return 0;
-    if (!second) return 1;
-    cq[i] = q2; cq2[i] = q;
-    if (EST == S3D_ESTIMATOR_POINT_TO_PLANE) cn[i] = __ldg(&tgt_nrm[__float_as_int(q2.w)]);
-    return 2;
+    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+__device__ __forceinline__ void smem_add_i64(long long *p, long long v) { atomicAdd(reinterpret_cast<unsigned long long *>(p), (unsigned long long)v); }
 
+// How an iteration runs (one group of CTAs per pair; octet u = 8 consecutive source points belongs to CTA u mod group_ctas):
+//   pass 1  streaming: every warp walks its share of the CTA's octets once, 49 bytes per query (point, correspondence, normal + bound,
+//           flag byte; staged into the warp's tile by cp.async, all loads of up to PS_STAGE chunks in flight at once).  Skip test
+//           (triangle inequality): the query was at xs = T[its] * p when it was last searched and every other target point was at least
+//           `lb` away from there; if |x - xs| + |x - q| < lb (with explicit rounding allowances) the stored correspondence is provably
+//           still the exact nearest neighbour, and its terms go straight into the 29 order-independent sums.  Near ties (runner-up
+//           within 1e-5 m: the float noise of the test would fail them every time) carry their runner-up: both are evaluated exactly
+//           and swapped if their order changed.  Queries that fail are appended, per octet, to the CTA's pending list.
+//   pass 2  searching: warps take octets from the pending list (dynamically: search cost varies several-fold with depth and surface
+//           orientation), search them in a TMA-staged shared-memory tile (tile_search.cuh), write the new per-query state and add
+//           the terms of the searched queries.  In the first iteration every octet is pending and there is no pass 1.
+//   then    the CTA's sums (integers, smem atomics) go to the group as one row, group barrier (red.release / ld.acquire), every CTA
+//           adds the rows and solves redundantly in strict double: all CTAs hold bit-identical poses, no second barrier.
+// Because the sums do not depend on the order of the additions, a query can be accumulated by whichever pass decides it.
 template <int EST>
 __global__ void __launch_bounds__(TS_BLOCK, 1) icp_persist_kernel(const PersistArgs a)
 {
     extern __shared__ __align__(16) unsigned char ts_smem[];
     float4 *tiles = reinterpret_cast<float4 *>(ts_smem);          // TS_WARPS tiles of TS_CAP candidates
     __shared__ PairState st;                                      // this CTA's copy of the pair state (all CTAs of a group agree bit for bit)
-    __shared__ long long whi[TS_WARPS][S3D_NACC], wlo[TS_WARPS][S3D_NACC];     // per-warp (hi, lo) sums of the iteration
-    __shared__ long long thi[TS_WARPS][S3D_NACC], tlo[TS_WARPS][S3D_NACC];     // group totals, one part per warp
+    __shared__ float hist[PS_HIST][12];                           // float poses of the last PS_HIST iterations (ring)
+    __shared__ long long ctot[S3D_ROW];                           // the CTA's (hi, lo) sums of this iteration, then the group's totals
     __shared__ double total[S3D_NACC];                            // the pair's 29 sums as doubles, input of the solve
     __shared__ FxScale fxs;                                       // resolution of this iteration's sums (from the pose and the data bounds)
     __shared__ TileCfg cfg[2];                                    // search levels of the current pair: [0] decimated grid, [1] full grid
-    __shared__ int dyn_next;                                      // dynamic decide pass: next octet of this CTA to hand out
-    __shared__ float4 dyn_pre[TS_WARPS][96];                      // ... and the state of each warp's NEXT item (32 x point, correspondence, search state)
-    __shared__ int n_pending, n_pending_prev;                     // queries of this CTA that needed a search: this / the previous iteration
+    __shared__ int pend_count, pend_next;                         // pending list of this CTA: entries appended / handed out
 #ifdef TS_USE_TMA
     __shared__ __align__(8) uint64_t tile_bar[TS_WARPS];         // one mbarrier per warp: completion of its TMA row copies
 #endif
@@ -681,6 +682,7 @@ __global__ void __launch_bounds__(TS_BLOCK, 1) icp_persist_kernel(const PersistA
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int group = blockIdx.x / a.group_ctas, rank = blockIdx.x - group * a.group_ctas;
     float4 *buf = tiles + warp * TS_CAP;
+    const uint32_t sbuf = ts_smem_u32(buf);
 #ifdef TS_USE_TMA
     uint64_t *bar_w = &tile_bar[warp];
     uint32_t parity = 0u;
@@ -693,6 +695,7 @@ __global__ void __launch_bounds__(TS_BLOCK, 1) icp_persist_kernel(const PersistA
     unsigned *bar = a.barriers + group;
     unsigned epoch = 0;
     const float gate_r = a.max_d2 < INFINITY ? sqrtf(a.max_d2) : INFINITY;
+    uint32_t *my_pend = a.pend + (size_t)blockIdx.x * a.pend_stride;
 
     for (int pair = group; pair < a.n_pairs; pair += a.groups) {
         const PairDesc d = a.descs[pair];
@@ -701,7 +704,7 @@ __global__ void __launch_bounds__(TS_BLOCK, 1) icp_persist_kernel(const PersistA
         if (threadIdx.x == 0) {
             st = a.states[pair];
             fxs = s3d_fx_make(s3d_icp_bound(*d.src_absmax, *d.tgt_absmax, EST == S3D_ESTIMATOR_POINT_TO_PLANE ? d.tgt_absmax[1] : 1.0f, st.T));
-            dyn_next = 0; n_pending = 0; n_pending_prev = 0;
+            pend_count = 0; pend_next = 0;
             cfg[1].gp = *d.grid; cfg[1].cell_start = d.cell_start; cfg[1].pts = d.sorted_pts;
             cfg[1].slack = a.slack_cells * cfg[1].gp.cell; cfg[1].gate_r = gate_r;
             cfg[0] = cfg[1];
@@ -710,168 +713,188 @@ __global__ void __launch_bounds__(TS_BLOCK, 1) icp_persist_kernel(const PersistA
                 cfg[0].slack = 0.2f * cfg[0].gp.cell;
             }
         }
+        if (threadIdx.x < S3D_ROW) ctot[threadIdx.x] = 0;
         __syncthreads();
+        if (threadIdx.x < 12) hist[0][threadIdx.x] = st.Tf[threadIdx.x];
         const float cell = cfg[1].gp.cell, slack = cfg[1].slack, ccell = cfg[0].gp.cell;
         float4 *my_cq = a.cq + (size_t)pair * a.nn_stride;
         float4 *my_cn = a.cn + (size_t)pair * a.nn_stride;
-        float4 *my_xl = a.xl + (size_t)pair * a.nn_stride;
         float4 *my_cq2 = a.cq2 + (size_t)pair * a.nn_stride;
-        // Work is dealt out in OCTETS (8 consecutive source points = 128 contiguous bytes of every per-query array):
-        // octet u belongs to warp slot (u mod W) of the group (W = all its warps; slot = rank + group_ctas * warp, so
-        // consecutive octets go to different CTAs).  A warp's k-th chunk is its octets 4k..4k+3, one per 8 lanes: every
-        // warp samples the whole cloud evenly (the search cost varies smoothly with depth) and warps differ by at most
-        // one octet, which keeps both the CTA and the group barrier waits short.  An octet is also the group one
-        // search box is built for (tile_search.cuh).
+        uint8_t *my_fl = a.flags + (size_t)pair * a.nn_stride;
+        // Octet u belongs to CTA (u mod group_ctas): every CTA samples the whole cloud evenly (the search cost varies smoothly
+        // with depth).  The CTA's octets are m = 0 .. cta_units-1 (u = rank + group_ctas * m); in pass 1 chunk c = four
+        // consecutive local octets 4c .. 4c+3 (one per 8 lanes) and warp w walks chunks w, w + TS_WARPS, ...
         const int nunits = (d.n_src + 7) >> 3;
-        const int W = a.group_ctas * TS_WARPS, wslot = rank + a.group_ctas * warp;
-#define CHUNK_UNIT(kc) (wslot + W * (4 * (kc) + (lane >> 3)))        // octet handled by this lane in the warp's kc-th chunk
+        const int cta_units = rank < nunits ? (nunits - rank + a.group_ctas - 1) / a.group_ctas : 0;
+        const int cta_chunks = (cta_units + 3) >> 2;
+        __syncthreads();
 
         for (int it = 0; it < a.iterations; ++it) {
             if (st.status != 0) break;            // failed pairs stop; every CTA of the group sees the same state
-            const float *T = st.Tf;               // the pose is read from shared memory where it is used: 12 registers less in a
-                                                  // loop that also carries 29 double accumulators
+            const float *T = st.Tf;               // the pose is read from shared memory where it is used
             const bool last = (it == a.iterations - 1);
-            // float pose bitwise unchanged since the previous iteration: every transformed point is bitwise the same,
-            // so every correspondence of the previous iteration is still the exact answer
-            bool same_pose = it > 0;
-            #pragma unroll
-            for (int k = 0; k < 12; ++k) same_pose = same_pose && (__float_as_uint(T[k]) == __float_as_uint(st.Tf_prev[k]));
+            const unsigned long long mbits = fxs.mbits;
+            const double M = __longlong_as_double((long long)mbits);
             PHASE_T0();
-#if defined(S3D_STATS) || defined(S3D_PHASES)
-            if (blockIdx.x == 0 && threadIdx.x == 0 && same_pose) atomicAdd(&g_stats[30], 1ull);
-#endif
-#if defined(S3D_STATS) || defined(S3D_PHASES)
-            const long long wl_t0 = clock64(); long long ws_t = 0; int ws_n = 0;
-#if defined(S3D_PHASES)
-            long long tm[5] = {0, 0, 0, 0, 0};
-#endif
-#endif
 
-            // Every warp walks its chunks of 32 queries twice per iteration (fixed assignment: the same thread sees the same
-            // query every iteration):
-            //   decide pass      skip test / near-tie check / search; what changes is written to the per-query state.  No
-            //                    accumulator is alive here, so the searches (real calls) cost no spills in the hot loops.
-            //   accumulate pass  re-reads point, correspondence and normal, forms the 29 sums: no call, no branch on the search.
-            // The per-query state of up to TS_STAGE chunks (16 B per query and array) is brought into the warp's tile by
-            // cp.async up front, every load in flight at once and no registers spent on prefetching: a late iteration
-            // (nearly every query keeps its correspondence) exposes two memory latencies in all.  A search uses the tile
-            // itself, so what was staged beyond the current chunk is staged again afterwards (then only one chunk ahead: in
-            // the first iterations every chunk searches).
-            // While most queries still need a search (the first iterations) the cost of an octet varies several-fold with
-            // depth and surface orientation, and a fixed assignment leaves warps waiting for the slowest one of their CTA
-            // (and CTAs for the slowest CTA): 32 % of the warp time of the first build of this kernel.  In those iterations
-            // (`dyn`, decided per CTA from its own count of the previous iteration) the CTA's octets are handed out one
-            // or two at a time (a.dyn_octets) from a shared-memory counter, one per 8 lanes of the taking warp, and all 32
-            // lanes search for them.  The per-query state lives in global memory and an octet always belongs to the same CTA, so
-            // who decides it changes nothing in what is found.
-            const int cta_units = rank < nunits ? (nunits - rank + a.group_ctas - 1) / a.group_ctas : 0;      // octets rank, rank + group_ctas, ...
-            const bool dyn = !same_pose && a.dyn_div > 0 && (it == 0 || (long long)n_pending_prev * a.dyn_div > (long long)cta_units * 8);
-            int npend = 0, dyn_m = 0;
-            const uint32_t spre = ts_smem_u32(&dyn_pre[warp][0]) + 16u * (uint32_t)lane;
-            // an item = a.dyn_octets (1, 2 or 4) consecutive octets of this CTA, one per 8 lanes
-            auto dyn_take_and_stage = [&]() -> int {
-                int m = 0;
-                if (lane == 0) m = atomicAdd(&dyn_next, a.dyn_octets);
-                m = __shfl_sync(full, m, 0);
-                const int mo = m + (lane >> 3);
-                const int is = ((rank + a.group_ctas * mo) << 3) + (lane & 7);
-                if (mo < cta_units && lane < 8 * a.dyn_octets && is < d.n_src) {
-                    ts_cp_async16_s(spre, &d.src[is]);
-                    if (it > 0) {
-                        ts_cp_async16_s(spre + 512u, &my_cq[is]);
-                        ts_cp_async16_s(spre + 1024u, &my_xl[is]);
+            // 29 wrapping int64 accumulators per thread.  hand_over(): unbias, add the 32 lanes through the warp's tile
+            // (transposed: lane k adds slot k of the 32 lanes), split into (hi, lo), add to the CTA's sums (smem atomics).
+            long long acc[29];
+            #pragma unroll
+            for (int k = 0; k < 29; ++k) acc[k] = 0;
+            int cnt = 0;
+#define PS_HAND_OVER() do {                                                                                               \
+                long long *tr_ = reinterpret_cast<long long *>(buf);          /* 29 x 33 int64 <= TS_CAP float4 */          \
+                __syncwarp();                                                                                             \
+                _Pragma("unroll") for (int k = 0; k < 28; ++k) tr_[k * 33 + lane] = fx_unbias<EST>(acc[k], k, cnt, mbits); \
+                tr_[28 * 33 + lane] = (long long)cnt;                                                                     \
+                __syncwarp();                                                                                             \
+                if (lane < 29) {                                                                                          \
+                    long long v_ = 0;                                                                                     \
+                    _Pragma("unroll 8") for (int l = 0; l < 32; ++l) v_ += tr_[lane * 33 + l];                            \
+                    if (v_ != 0) {                                                                                        \
+                        long long hi_, lo_; s3d_fx_split(v_, hi_, lo_);                                                   \
+                        if (lane == 28) { hi_ = 0; lo_ = v_; }                                                            \
+                        if (hi_ != 0) smem_add_i64(&ctot[lane], hi_);                                                     \
+                        smem_add_i64(&ctot[32 + lane], lo_);                                                              \
+                    }                                                                                                     \
+                }                                                                                                         \
+                __syncwarp();                                                                                             \
+                _Pragma("unroll") for (int k = 0; k < 29; ++k) acc[k] = 0;                                                \
+                cnt = 0;                                                                                                  \
+            } while (0)
+
+            // ---------------------------------------------------------------- pass 1: streaming skip test + accumulate
+            if (it > 0) {
+                int since = 0;
+                for (int c0 = warp; c0 < cta_chunks; c0 += TS_WARPS * PS_STAGE) {
+                    #pragma unroll
+                    for (int s = 0; s < PS_STAGE; ++s) {
+                        const int m = 4 * (c0 + s * TS_WARPS) + (lane >> 3);
+                        const int i = ((rank + a.group_ctas * m) << 3) + (lane & 7);
+                        if (m < cta_units && i < d.n_src) {
+                            const uint32_t dst = sbuf + PS_CHUNK_BYTES * (uint32_t)s + 16u * (uint32_t)lane;
+                            ts_cp_async16_s(dst, &d.src[i]);
+                            ts_cp_async16_s(dst + 512u, &my_cq[i]);
+                            ts_cp_async16_s(dst + 1024u, &my_cn[i]);
+                            if ((lane & 7) == 0)
+                                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sbuf + PS_CHUNK_BYTES * (uint32_t)s + 1536u + (uint32_t)lane), "l"(my_fl + i) : "memory");
+                        }
                     }
-                }
-                return m;
-            };
-            const uint32_t sbuf = ts_smem_u32(buf);
-            int staged_hi = 0, stage_lo = 0, stage_depth = TS_STAGE;
-            for (int kc = 0; dyn || wslot + W * 4 * kc < nunits; ++kc) {   // warp-uniform: the chunk's first octet exists
-                int u, i; bool in;
-                float4 p, q_old, xl;
-                if (dyn) {
-                    // the octet worked on now was staged while the previous one was searched; the next one is taken and
-                    // staged (cp.async: no registers held across the search call) before this one is worked on
-                    if (kc == 0) dyn_m = dyn_take_and_stage();
-                    const int m = dyn_m;
-                    if (m >= cta_units) break;
                     ts_cp_async_wait_all();
-                    u = rank + a.group_ctas * (m + (lane >> 3)); i = (u << 3) + (lane & 7);
-                    in = m + (lane >> 3) < cta_units && lane < 8 * a.dyn_octets && i < d.n_src;
-                    p = q_old = xl = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (in) {
-                        p = ts_lds128(spre);
-                        if (it > 0) { q_old = ts_lds128(spre + 512u); xl = ts_lds128(spre + 1024u); }
+                    __syncwarp();
+                    #pragma unroll 1
+                    for (int s = 0; s < PS_STAGE; ++s) {
+                        const int m = 4 * (c0 + s * TS_WARPS) + (lane >> 3);
+                        if (4 * (c0 + s * TS_WARPS) >= cta_units) break;                                  // warp-uniform
+                        const int i = ((rank + a.group_ctas * m) << 3) + (lane & 7);
+                        const bool in = m < cta_units && i < d.n_src;
+                        bool pending = false;
+                        if (in) {
+                            const uint32_t sl = sbuf + PS_CHUNK_BYTES * (uint32_t)s + 16u * (uint32_t)lane;
+                            const float4 p = ts_lds128(sl);
+                            float4 q = ts_lds128(sl + 512u), nv = ts_lds128(sl + 1024u);
+                            unsigned f;
+                            asm volatile("ld.shared.u8 %0, [%1];" : "=r"(f) : "r"(sbuf + PS_CHUNK_BYTES * (uint32_t)s + 1536u + (uint32_t)lane));
+                            const float3 x = s3d_xform(T, p.x, p.y, p.z);
+                            pending = true;
+                            if (__float_as_int(q.w) >= 0) {
+                                // the query was at xs when it was last searched; every other target point was >= lb away from there
+                                const int its = (int)(f & 63u);
+                                const float3 xs = s3d_xform(hist[its], p.x, p.y, p.z);
+                                float d2q = s3d_dist2(x.x, x.y, x.z, q.x, q.y, q.z);
+                                const float moved = sqrtf(s3d_dist2(x.x, x.y, x.z, xs.x, xs.y, xs.z)) * 1.000002f + 5e-8f;
+                                const float lb = nv.w;
+                                bool keep;
+                                if (!(f & PS_FLAG_TIE)) keep = sqrtf(d2q) * 1.000002f + 2e-7f < lb - moved;      // still the exact nearest neighbour
+                                else {
+                                    // near tie (rare): the runner-up q2 was kept and everything else is >= lb away.  Both are evaluated;
+                                    // the nearer (lower original index on equality) is the exact nearest neighbour if it beats the bound.
+                                    const float4 q2 = __ldcg(&my_cq2[i]);
+                                    const float d2b = s3d_dist2(x.x, x.y, x.z, q2.x, q2.y, q2.z);
+                                    const bool second = d2b < d2q || (d2b == d2q && __float_as_int(q2.w) < __float_as_int(q.w));
+                                    keep = sqrtf(second ? d2b : d2q) * 1.000002f + 2e-7f < lb - moved;
+                                    if (keep && second) {                         // the two swap roles: state rewritten
+                                        my_cq[i] = q2; my_cq2[i] = q;
+                                        float4 n2 = make_float4(0.f, 0.f, 0.f, 1.f);
+                                        if (EST == S3D_ESTIMATOR_POINT_TO_PLANE) n2 = __ldg(&d.tgt_nrm[__float_as_int(q2.w)]);
+                                        f = (f & ~PS_FLAG_NRM) | (n2.w != 0.f ? PS_FLAG_NRM : 0u);
+                                        my_cn[i] = make_float4(n2.x, n2.y, n2.z, lb);
+                                        my_fl[i] = (uint8_t)f;
+                                        q = q2; d2q = d2b; nv = make_float4(n2.x, n2.y, n2.z, lb);
+                                    }
+                                }
+                                if (keep) {
+                                    pending = false;
+                                    STAT(1, 1);
+                                    const bool ok = (d2q <= a.max_d2) && (f & PS_FLAG_NRM);
+                                    if (ok) { accumulate_fx<EST>(acc, M, x.x, x.y, x.z, q, nv, d2q); ++cnt; }
+                                    if (last && a.nn_out) a.nn_out[i] = ok ? __float_as_int(q.w) : -1;
+                                    if (((it - its) & 63) >= PS_REBASE_AGE) {
+                                        // re-base onto the current pose before the ring slot is reused: everything else is at least
+                                        // lb - moved away from where the query is now
+                                        my_cn[i] = make_float4(nv.x, nv.y, nv.z, fmaxf((lb - moved) * 0.999999f - 1e-7f, 0.f));
+                                        my_fl[i] = (uint8_t)((f & ~63u) | (unsigned)(it & 63));
+                                    }
+                                }
+                            }
+                        }
+                        // queries that need a search: one list entry per octet
+                        const unsigned pm = __ballot_sync(full, pending);
+                        if (pm) {
+                            const unsigned mine = (pm >> (lane & 24)) & 0xffu;
+                            if ((lane & 7) == 0 && mine) {
+                                const int slot = atomicAdd(&pend_count, 1);
+                                my_pend[slot] = ((uint32_t)m << 8) | mine;
+                            }
+                        }
                     }
                     __syncwarp();
-                    dyn_m = dyn_take_and_stage();
-                } else {
-                if (kc >= staged_hi) {
-                    stage_lo = kc;
-                    staged_hi = kc + stage_depth;
-                    for (int c = 0; c < stage_depth; ++c) {
-                        const int us = CHUNK_UNIT(kc + c), is = (us << 3) + (lane & 7);
-                        if (us < nunits && is < d.n_src) {
-                            const uint32_t dst = sbuf + 16u * (uint32_t)(c * 128 + lane);
-                            ts_cp_async16_s(dst, &d.src[is]);
-                            if (it > 0) {
-                                ts_cp_async16_s(dst + 512u, &my_cq[is]);
-                                ts_cp_async16_s(dst + 1024u, &my_xl[is]);
-                            }
+                    since += PS_STAGE;
+                    if (since >= S3D_FX_SEGMENT - PS_STAGE) { PS_HAND_OVER(); since = 0; }      // warp-uniform
+                }
+                PS_HAND_OVER();
+                __threadfence_block();
+                __syncthreads();                  // the pending list is complete
+            }
+            PHASE(8);
+
+            // ---------------------------------------------------------------- pass 2: search what is pending
+            {
+                const int n_items = it == 0 ? cta_units : pend_count;
+                const uint32_t spre = sbuf;       // (the tile is also the staging area of the item's 2 x 32 float4)
+                for (;;) {
+                    int e0 = 0;
+                    if (lane == 0) e0 = atomicAdd(&pend_next, a.item_octets);
+                    e0 = __shfl_sync(full, e0, 0);
+                    if (e0 >= n_items) break;
+                    const int e = e0 + (lane >> 3);
+                    uint32_t ent = 0u;
+                    if (e < n_items && lane < 8 * a.item_octets) ent = it == 0 ? (((uint32_t)e << 8) | 0xffu) : __ldcg(&my_pend[e]);
+                    const int m = (int)(ent >> 8);
+                    const int i = ((rank + a.group_ctas * m) << 3) + (lane & 7);
+                    const bool pending = ((ent >> (lane & 7)) & 1u) && i < d.n_src;
+                    float4 p = make_float4(0.f, 0.f, 0.f, 0.f), q = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
+                    if (pending) {
+                        p = d.src[i];
+                        if (it > 0) q = __ldcg(&my_cq[i]);
+                    }
+                    (void)spre;
+                    float3 x = make_float3(0.f, 0.f, 0.f);
+                    float r = a.first_cells * cell;
+                    if (pending) {
+                        x = s3d_xform(T, p.x, p.y, p.z);
+                        if (__float_as_int(q.w) >= 0) {
+                            // The old correspondence is a real target point, so its distance bounds the ball.  After a small move it is
+                            // also tight; after a big pose update (first iterations) the point slid along the surface and one cell
+                            // is the better first guess (tile_search verifies and widens when needed).
+                            const float dq = sqrtf(s3d_dist2(x.x, x.y, x.z, q.x, q.y, q.z));
+                            const float3 xo = s3d_xform(st.Tf_prev, p.x, p.y, p.z);
+                            const float step_mv = sqrtf(s3d_dist2(x.x, x.y, x.z, xo.x, xo.y, xo.z));
+                            r = dq * 1.00001f + slack;
+                            if (step_mv > 0.25f * cell) r = fminf(r, a.hint_cells * cell + slack);
                         }
                     }
-                    ts_cp_async_wait_all();
-                }
-                u = CHUNK_UNIT(kc); i = (u << 3) + (lane & 7);
-                in = u < nunits && i < d.n_src;
-                const uint32_t sl = sbuf + 16u * (uint32_t)((kc - stage_lo) * 128 + lane);
-                p = ts_lds128(sl); q_old = ts_lds128(sl + 512u); xl = ts_lds128(sl + 1024u);
-                }
-                float3 x = make_float3(0.f, 0.f, 0.f);
-                float4 q = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
-                float d2q = INFINITY, r = a.first_cells * cell;
-                bool pending = in;
-                if (in) {
-                    x = s3d_xform(T, p.x, p.y, p.z);
-                    if (it > 0) {
-                        q = q_old;
-                        if (same_pose) {
-                            pending = false;
-                            STAT(1, 1);
-                        } else if (__float_as_int(q.w) >= 0) {
-                            // Triangle inequality against the state of the last search of this query: it was at xl.xyz, and every
-                            // target point other than q was at least xl.w away from there.
-                            d2q = s3d_dist2(x.x, x.y, x.z, q.x, q.y, q.z);
-                            const float mv = sqrtf(s3d_dist2(x.x, x.y, x.z, xl.x, xl.y, xl.z));
-                            const float moved = mv * 1.000002f + 5e-8f;
-                            const float dq = sqrtf(d2q);
-                            bool keep = dq * 1.000002f + 2e-7f < xl.w - moved;       // still the exact nearest neighbour
-                            if (!keep && xl.w < 0.f) {        // near tie (rare): settle it with the runner-up that was kept
-                                const int rc = resolve_near_tie<EST>(my_cq, my_cq2, my_cn, d.tgt_nrm, i, x.x, x.y, x.z, -xl.w - moved, q, d2q);
-                                keep = rc != 0;               // (rc == 2: the runner-up took over, the helper rewrote the state)
-                            }
-                            if (keep) {                                               // no search
-                                pending = false;
-                                STAT(1, 1);
-                            } else {
-                                // The old correspondence is a real target point, so dq bounds the ball.  After a small move it is
-                                // also tight; after a big pose update (first iterations) the point slid along the surface and one
-                                // cell is the better first guess (tile_search verifies and widens when needed).
-                                const float3 xo = s3d_xform(st.Tf_prev, p.x, p.y, p.z);
-                                const float step_mv = sqrtf(s3d_dist2(x.x, x.y, x.z, xo.x, xo.y, xo.z));
-                                r = dq * 1.00001f + slack;
-                                if (step_mv > 0.25f * cell) r = fminf(r, a.hint_cells * cell + slack);
-                            }
-                        }
-                    }
-                }
-                const unsigned pendmask = __ballot_sync(full, pending);
-                npend += __popc(pendmask);
-                if (pendmask) {
-                    staged_hi = kc + 1; stage_depth = 1;        // the search uses the tile: stage the next chunk afresh
-#if defined(S3D_STATS) || defined(S3D_PHASES)
-                    const long long s_t0 = clock64();
-#endif
                     // first iteration: the nearest point of the decimated target (level 0) bounds the fine search (level 1)
                     TileOut b;
                     for (int level = (it == 0 && have_coarse) ? 0 : 1; level < 2; ++level) {
@@ -883,160 +906,71 @@ __global__ void __launch_bounds__(TS_BLOCK, 1) icp_persist_kernel(const PersistA
 #endif
                         if (level == 0 && pending && b.bd < INFINITY) r = sqrtf(b.bd) * 1.00001f + slack;
                     }
-                    const float lbv = b.lb;
                     if (pending) {
-                        q = b.bq; d2q = b.bd;
+                        q = b.bq;
+                        const float d2q = b.bd;
                         if (!(b.bd < INFINITY)) q.w = __int_as_float(-1);      // nothing within reach
-                        my_cq[i] = q;
-                        if (b.lb3 > 0.f) { my_cq2[i] = b.q2; my_xl[i] = make_float4(x.x, x.y, x.z, -b.lb3); }     // near tie: keep the runner-up too
-                        else my_xl[i] = make_float4(x.x, x.y, x.z, lbv);
-                        if (EST == S3D_ESTIMATOR_POINT_TO_PLANE && __float_as_int(q.w) >= 0)
-                            my_cn[i] = __ldg(&d.tgt_nrm[__float_as_int(q.w)]);
-                    }
-#if defined(S3D_STATS) || defined(S3D_PHASES)
-                    ws_t += clock64() - s_t0; ++ws_n;
-#endif
-                }
-            }
-
-            if (lane == 0 && npend) atomicAdd(&n_pending, npend);
-            // the accumulate pass keeps the fixed assignment: after a dynamic decide pass it reads what other warps of the CTA wrote
-            if (dyn) __syncthreads();
-
-            // ---- accumulate pass ----
-            // Order-independent fixed-point sums (common.cuh): 29 wrapping int64 accumulators per thread.  Every
-            // S3D_FX_SEGMENT queries per thread (and at the end) the warp hands its partial sums over: unbias, add the 32
-            // lanes through the warp's tile (transposed: lane k adds slot k of the 32 lanes, ~100 instructions instead of
-            // 29 five-step shuffle trees), split into (hi, lo) and add to the warp's running sums in shared memory.
-            const unsigned long long mbits = fxs.mbits;
-            const double M = __longlong_as_double((long long)mbits);
-            long long acc[29];
-            #pragma unroll
-            for (int k = 0; k < 29; ++k) acc[k] = 0;
-            int cnt = 0, cnt_total = 0, since = 0;
-            if (lane < 29) { whi[warp][lane] = 0; wlo[warp][lane] = 0; }
-            auto hand_over = [&]() {
-                long long *tr = reinterpret_cast<long long *>(buf);          // 29 x 33 int64 <= TS_CAP float4
-                __syncwarp();
-                #pragma unroll
-                for (int k = 0; k < 28; ++k) tr[k * 33 + lane] = fx_unbias<EST>(acc[k], k, cnt, mbits);
-                __syncwarp();
-                if (lane < 28) {
-                    long long v = 0;
-                    #pragma unroll 8
-                    for (int l = 0; l < 32; ++l) v += tr[lane * 33 + l];
-                    long long hi, lo; s3d_fx_split(v, hi, lo);
-                    whi[warp][lane] += hi; wlo[warp][lane] += lo;
-                }
-                __syncwarp();
-                #pragma unroll
-                for (int k = 0; k < 29; ++k) acc[k] = 0;
-                cnt_total += cnt; cnt = 0; since = 0;
-            };
-            for (int kc0 = 0; wslot + W * 4 * kc0 < nunits; kc0 += TS_STAGE) {
-                #pragma unroll
-                for (int c = 0; c < TS_STAGE; ++c) {
-                    const int us = CHUNK_UNIT(kc0 + c), is = (us << 3) + (lane & 7);
-                    if (us < nunits && is < d.n_src) {
-                        const uint32_t dst = sbuf + 16u * (uint32_t)(c * 128 + lane);
-                        ts_cp_async16_s(dst, &d.src[is]);
-                        ts_cp_async16_s(dst + 512u, &my_cq[is]);
-                        if (EST == S3D_ESTIMATOR_POINT_TO_PLANE) ts_cp_async16_s(dst + 1024u, &my_cn[is]);
-                    }
-                }
-                ts_cp_async_wait_all();
-                #pragma unroll
-                for (int c = 0; c < TS_STAGE; ++c) {
-                    const int u = CHUNK_UNIT(kc0 + c), i = (u << 3) + (lane & 7);
-                    if (u < nunits && i < d.n_src) {
-                        const uint32_t sl = sbuf + 16u * (uint32_t)(c * 128 + lane);
-                        const float4 p = ts_lds128(sl), q = ts_lds128(sl + 512u);
                         float4 nv = make_float4(0.f, 0.f, 0.f, 1.f);
-                        if (EST == S3D_ESTIMATOR_POINT_TO_PLANE) nv = ts_lds128(sl + 1024u);
-                        const float3 x = s3d_xform(T, p.x, p.y, p.z);
-                        const int j = __float_as_int(q.w);
-                        const float d2q = s3d_dist2(x.x, x.y, x.z, q.x, q.y, q.z);    // same expression as in the search: identical bits
-                        const bool ok = (j >= 0) && (d2q <= a.max_d2) && (nv.w != 0.f);
+                        if (EST == S3D_ESTIMATOR_POINT_TO_PLANE && __float_as_int(q.w) >= 0) nv = __ldg(&d.tgt_nrm[__float_as_int(q.w)]);
+                        const bool tie = b.lb3 > 0.f;
+                        const unsigned f = (unsigned)(it & 63) | (tie ? PS_FLAG_TIE : 0u) | (nv.w != 0.f ? PS_FLAG_NRM : 0u);
+                        my_cq[i] = q;
+                        my_cn[i] = make_float4(nv.x, nv.y, nv.z, tie ? b.lb3 : b.lb);
+                        my_fl[i] = (uint8_t)f;
+                        if (tie) my_cq2[i] = b.q2;                             // near tie: keep the runner-up too
+                        const bool ok = (__float_as_int(q.w) >= 0) && (d2q <= a.max_d2) && (nv.w != 0.f);
                         if (ok) { accumulate_fx<EST>(acc, M, x.x, x.y, x.z, q, nv, d2q); ++cnt; }
-                        if (last && a.nn_out) a.nn_out[i] = ok ? j : -1;
+                        if (last && a.nn_out) a.nn_out[i] = ok ? __float_as_int(q.w) : -1;
                     }
+                    PS_HAND_OVER();
                 }
-                since += TS_STAGE;
-                if (since >= S3D_FX_SEGMENT - TS_STAGE) hand_over();      // warp-uniform
             }
-            hand_over();
-            cnt_total = warp_sum_i(cnt_total);
-            if (lane == 0) wlo[warp][S3D_ACC_COUNT] = cnt_total;
-
-#if defined(S3D_STATS) || defined(S3D_PHASES)
-            if (blockIdx.x == 0 && lane == 0) {
-                const unsigned long long wl = (unsigned long long)(clock64() - wl_t0);
-                atomicMax(&g_stats[16], wl); atomicAdd(&g_stats[17], wl);                 // chunk loop of one warp: max (over the run), sum
-                atomicAdd(&g_stats[18], (unsigned long long)ws_t); atomicAdd(&g_stats[19], (unsigned long long)ws_n);   // inside searches: cycles, count
-                atomicMax(&g_stats[20], (unsigned long long)ws_t);
-#if defined(S3D_PHASES)
-                for (int k = 0; k < 5; ++k) atomicAdd(&g_stats[21 + k], (unsigned long long)tm[k]);
-#endif
-            }
-#endif
-            PHASE(8);
-            // CTA reduction: the warps' (hi, lo) sums are integers, any order of addition gives the same bits
+            PHASE(9);
+            // ---------------------------------------------------------------- the CTA's row, group barrier, totals, solve
             __syncthreads();
             long long *rows = a.partials + ((size_t)(epoch & 1u) * a.groups + group) * a.group_ctas * S3D_ROW;
-            if (threadIdx.x < 29) {
-                long long hi = 0, lo = 0;
-                #pragma unroll
-                for (int w = 0; w < TS_WARPS; ++w) { hi += whi[w][threadIdx.x]; lo += wlo[w][threadIdx.x]; }
-                __stcg(&rows[(size_t)rank * S3D_ROW + threadIdx.x], hi);
-                __stcg(&rows[(size_t)rank * S3D_ROW + 32 + threadIdx.x], lo);
-            }
-            if (threadIdx.x == 32) { n_pending_prev = n_pending; n_pending = 0; dyn_next = 0; }     // every warp is past its decide pass
-            // group barrier (all CTAs are co-resident: cooperative launch)
-            ++epoch;
-            __syncthreads();
-            PHASE(9);
-            if (a.group_ctas > 1 && threadIdx.x == 0) {
-                // release (this CTA's row, written by its other threads before the __syncthreads above) -> arrive -> wait ->
-                // acquire (the other CTAs' rows); acq_rel fences, not the sequentially consistent __threadfence
-                asm volatile("fence.acq_rel.gpu;" ::: "memory");
-                atomicAdd(bar, 1u);
-                const unsigned target = epoch * (unsigned)a.group_ctas;
-                while (ld_relaxed_u32(bar) < target) { }
-                asm volatile("fence.acq_rel.gpu;" ::: "memory");
-            }
-            __syncthreads();
-            PHASE(10);
-            // every CTA: the sum of the group's rows (integers), converted to doubles once, then the same solve
-            {
-                // (loads of up to 10 rows in flight per thread)
-                long long hi = 0, lo = 0;
-                if (lane < 29) {
-                    for (int c0 = warp; c0 < a.group_ctas; c0 += 10 * TS_WARPS) {
-                        long long vh[10], vl[10];
-                        #pragma unroll
-                        for (int j = 0; j < 10; ++j) {
-                            const int c = c0 + j * TS_WARPS;
-                            vh[j] = c < a.group_ctas ? __ldcg(&rows[(size_t)c * S3D_ROW + lane]) : 0ll;
-                            vl[j] = c < a.group_ctas ? __ldcg(&rows[(size_t)c * S3D_ROW + 32 + lane]) : 0ll;
-                        }
-                        #pragma unroll
-                        for (int j = 0; j < 10; ++j) { hi += vh[j]; lo += vl[j]; }
-                    }
+            if (a.group_ctas > 1) {
+                if (threadIdx.x < S3D_ROW) __stcg(&rows[(size_t)rank * S3D_ROW + threadIdx.x], ctot[threadIdx.x]);
+                ++epoch;
+                __syncthreads();
+                if (threadIdx.x < S3D_ROW) ctot[threadIdx.x] = 0;
+                if (threadIdx.x == 0) {
+                    // release (this CTA's row, written by its other threads before the __syncthreads above) -> arrive -> wait -> acquire
+                    __threadfence();
+                    red_release_add_u32(bar, 1u);
+                    const unsigned target = epoch * (unsigned)a.group_ctas;
+                    while (ld_acquire_u32(bar) < target) { }
+                    __threadfence();
                 }
-                thi[warp][lane] = hi; tlo[warp][lane] = lo;
+                __syncthreads();
+                PHASE(10);
+                // every CTA adds the group's rows (integers: any order): 64 values per row, 8 rows per sweep of the 512 threads
+                {
+                    const int slot = threadIdx.x & (S3D_ROW - 1), part = threadIdx.x / S3D_ROW;
+                    long long v = 0;
+                    for (int c = part; c < a.group_ctas; c += 4 * (TS_BLOCK / S3D_ROW)) {
+                        long long w0 = 0, w1 = 0, w2 = 0, w3 = 0;
+                        const int c1 = c + (TS_BLOCK / S3D_ROW), c2 = c1 + (TS_BLOCK / S3D_ROW), c3 = c2 + (TS_BLOCK / S3D_ROW);
+                        w0 = __ldcg(&rows[(size_t)c * S3D_ROW + slot]);
+                        if (c1 < a.group_ctas) w1 = __ldcg(&rows[(size_t)c1 * S3D_ROW + slot]);
+                        if (c2 < a.group_ctas) w2 = __ldcg(&rows[(size_t)c2 * S3D_ROW + slot]);
+                        if (c3 < a.group_ctas) w3 = __ldcg(&rows[(size_t)c3 * S3D_ROW + slot]);
+                        v += (w0 + w1) + (w2 + w3);
+                    }
+                    if (v != 0) smem_add_i64(&ctot[slot], v);
+                }
+                __syncthreads();
             }
+            if (threadIdx.x < 32) total[threadIdx.x] = threadIdx.x < 29 ? fx_total<EST>(ctot[threadIdx.x], ctot[32 + threadIdx.x], threadIdx.x, fxs.scale) : 0.0;
             __syncthreads();
-            if (threadIdx.x < 32) {
-                long long hi = 0, lo = 0;
-                #pragma unroll
-                for (int w = 0; w < TS_WARPS; ++w) { hi += thi[w][threadIdx.x]; lo += tlo[w][threadIdx.x]; }
-                total[threadIdx.x] = threadIdx.x < 29 ? fx_total<EST>(hi, lo, threadIdx.x, fxs.scale) : 0.0;
-            }
-            __syncthreads();
+            if (threadIdx.x < S3D_ROW) ctot[threadIdx.x] = 0;
             PHASE(11);
             if (threadIdx.x == 0) {
                 solve_and_update<EST>(total, &st, a.min_corr, a.pivot_eps);
                 fxs = s3d_fx_make(s3d_icp_bound(*d.src_absmax, *d.tgt_absmax, EST == S3D_ESTIMATOR_POINT_TO_PLANE ? d.tgt_absmax[1] : 1.0f, st.T));
+                #pragma unroll
+                for (int k = 0; k < 12; ++k) hist[(it + 1) & (PS_HIST - 1)][k] = st.Tf[k];
+                pend_count = 0; pend_next = 0;
             }
             __syncthreads();
             PHASE(12);
@@ -1179,16 +1113,24 @@ int s3d_register_issue(s3d_ctx *ctx, const s3d_cloud *const *src, const s3d_clou
             ctx->cap_nn = (int)need;
         }
     }
+    const int nn_stride8 = (std::max(n_max, 1) + 7) & ~7;          // per-pair stride of the per-query arrays: octets stay aligned
+    const int pend_stride = persist ? ((nn_stride8 / 8) + p_group_ctas - 1) / p_group_ctas + 1 : 0;      // octets one CTA of a group owns
     if (persist) {
-        size_t need = (size_t)n_pairs * std::max(n_max, 1);
+        size_t need = (size_t)n_pairs * nn_stride8;
         if (need > ctx->cap_tile_nn) {
-            cudaFree(ctx->d_cq); cudaFree(ctx->d_cn); cudaFree(ctx->d_lb); cudaFree(ctx->d_cq2);
-            ctx->d_cq = nullptr; ctx->d_cn = nullptr; ctx->d_lb = nullptr; ctx->d_cq2 = nullptr; ctx->cap_tile_nn = 0;
+            cudaFree(ctx->d_cq); cudaFree(ctx->d_cn); cudaFree(ctx->d_flags); cudaFree(ctx->d_cq2);
+            ctx->d_cq = nullptr; ctx->d_cn = nullptr; ctx->d_flags = nullptr; ctx->d_cq2 = nullptr; ctx->cap_tile_nn = 0;
             S3D_CUDA(ctx, cudaMalloc(&ctx->d_cq, sizeof(float4) * need));
             S3D_CUDA(ctx, cudaMalloc(&ctx->d_cn, sizeof(float4) * need));
             S3D_CUDA(ctx, cudaMalloc(&ctx->d_cq2, sizeof(float4) * need));
-            S3D_CUDA(ctx, cudaMalloc(&ctx->d_lb, sizeof(float4) * need));
+            S3D_CUDA(ctx, cudaMalloc(&ctx->d_flags, need + 16));
             ctx->cap_tile_nn = need;
+        }
+        const size_t need_pend = (size_t)p_groups * p_group_ctas * pend_stride;
+        if (need_pend > ctx->cap_pend) {
+            cudaFree(ctx->d_pend); ctx->d_pend = nullptr; ctx->cap_pend = 0;
+            S3D_CUDA(ctx, cudaMalloc(&ctx->d_pend, sizeof(uint32_t) * need_pend));
+            ctx->cap_pend = need_pend;
         }
         if (p_groups > ctx->cap_barriers) {
             cudaFree(ctx->d_barriers); ctx->d_barriers = nullptr; ctx->cap_barriers = 0;
@@ -1240,15 +1182,15 @@ int s3d_register_issue(s3d_ctx *ctx, const s3d_cloud *const *src, const s3d_clou
         S3D_CUDA(ctx, cudaMemsetAsync(ctx->d_barriers, 0, sizeof(unsigned) * p_groups, ctx->stream));
         PersistArgs pa;
         pa.descs = ctx->d_desc; pa.states = ctx->d_state; pa.partials = ctx->d_partials; pa.barriers = ctx->d_barriers;
-        pa.cq = ctx->d_cq; pa.cn = ctx->d_cn; pa.cq2 = ctx->d_cq2; pa.xl = ctx->d_lb; pa.nn_stride = std::max(n_max, 1);
+        pa.cq = ctx->d_cq; pa.cn = ctx->d_cn; pa.cq2 = ctx->d_cq2; pa.flags = ctx->d_flags; pa.pend = ctx->d_pend;
+        pa.nn_stride = nn_stride8; pa.pend_stride = pend_stride;
         pa.n_pairs = n_pairs; pa.groups = p_groups; pa.group_ctas = p_group_ctas; pa.iterations = prm->max_iterations;
         pa.max_d2 = max_d2; pa.min_corr = min_corr; pa.pivot_eps = pivot_eps; pa.nn_out = nn_out;
         { static const char *e = getenv("S3D_HINT_CELLS"); pa.hint_cells = e ? (float)atof(e) : 1.0f; }
         { static const char *e = getenv("S3D_FIRST_CELLS"); pa.first_cells = e ? (float)atof(e) : 1.5f; }
         { static const char *e = getenv("S3D_USE_COARSE"); pa.use_coarse = e ? atoi(e) : 1; }
         { static const char *e = getenv("S3D_SLACK_CELLS"); pa.slack_cells = e ? (float)atof(e) : 0.08f; }
-        { static const char *e = getenv("S3D_DYN_DIV"); pa.dyn_div = e ? atoi(e) : 8; }
-        { static const char *e = getenv("S3D_DYN_OCTETS"); const int v = e ? atoi(e) : 2; pa.dyn_octets = v >= 4 ? 4 : v >= 2 ? 2 : 1; }
+        { static const char *e = getenv("S3D_ITEM_OCTETS"); const int v = e ? atoi(e) : 2; pa.item_octets = v >= 4 ? 4 : v >= 2 ? 2 : 1; }
         void *kargs[] = {&pa};
         const void *fn = plane ? (const void *)icp_persist_kernel<S3D_ESTIMATOR_POINT_TO_PLANE> : (const void *)icp_persist_kernel<S3D_ESTIMATOR_SVD>;
         S3D_CUDA(ctx, cudaLaunchCooperativeKernel(fn, dim3(p_groups * p_group_ctas), dim3(TS_BLOCK), kargs, p_smem, ctx->stream));

@@ -79,36 +79,14 @@ __global__ void __launch_bounds__(PLANE_MAX_CAND) plane_hyp_kernel(const float4 
     coefs[c] = coef; valid[c] = ok ? 1 : 0; counts[c] = 0u;
 }
 
-// replay of pcl::RandomSampleConsensus::computeModel over the pre-evaluated candidates (one thread)
-__device__ void plane_select(const float4 *__restrict__ coefs, const int *__restrict__ valid, const uint32_t *__restrict__ counts,
-                             int n_cand, int n_points, int max_iterations, double probability, PlaneState *st)
-{
-    int iterations = 0, best = -1, best_count = -2147483647;
-    double k = 1.0;
-    const double log_prob = log(1.0 - probability);
-    const double one_over = n_points > 0 ? 1.0 / (double)n_points : 0.0;
-    const double eps = 2.220446049250313e-16;
-    for (int c = 0; c < n_cand && iterations < k; ++c) {
-        if (!valid[c]) continue;
-        int cc = (int)__ldcg(&counts[c]);
-        if (cc > best_count) {
-            best_count = cc; best = c;
-            double w = best_count * one_over;
-            double p_no = 1.0 - w * w * w;
-            if (p_no < eps) p_no = eps;
-            if (p_no > 1.0 - eps) p_no = 1.0 - eps;
-            k = log_prob / log(p_no);
-        }
-        ++iterations;
-        if (iterations > max_iterations) break;
-    }
-    st->best_count = best >= 0 ? best_count : 0; st->iterations = iterations;
-    if (best < 0 || best_count == 0) { st->stopped = 1; st->active = 0; }          // reference :376-379
-    else { st->ransac = coefs[best]; st->refined = coefs[best]; }
-}
-
 // ONE pass over the remaining points evaluates up to PLANE_CHUNK (64) candidates (chunk index = blockIdx.y; the stock
-// 50 + 14 candidates are one chunk): 16 bytes per point and pass.  The last CTA to finish replays the RANSAC loop.
+// 50 + 14 candidates are one chunk): 16 bytes per point and pass.  A lane holds ONE point at a time and walks the candidates
+// (coefficients broadcast from shared memory); the inliers of a candidate among the warp's 32 points are a ballot, and lane
+// k (k + 32) keeps the running count of candidate k: two counters per thread instead of 64, so the kernel runs at full
+// occupancy.  Counts: shared-memory atomics per warp, one global atomic per candidate and CTA (integers: deterministic).
+// The last CTA to finish replays pcl::RandomSampleConsensus::computeModel over the counts: the adaptive-stop value
+// k(c) = log(1 - p) / log(1 - w(c)^3) of every candidate is computed in parallel, one thread then walks the candidates
+// in order exactly like the sequential loop (the chosen model is the one PCL's loop picks).
 __global__ void __launch_bounds__(PLANE_BLOCK) plane_eval_kernel(const float4 *__restrict__ rem, const float4 *__restrict__ coefs,
                                                                  const int *__restrict__ valid, int n_cand, float tau,
                                                                  uint32_t *__restrict__ counts, int max_iterations, double probability,
@@ -119,6 +97,7 @@ __global__ void __launch_bounds__(PLANE_BLOCK) plane_eval_kernel(const float4 *_
     __shared__ float4 sc[PLANE_CHUNK];
     __shared__ uint32_t s_cnt[PLANE_CHUNK];
     __shared__ bool is_last;
+    const int lane = threadIdx.x & 31;
     const int c0 = blockIdx.y * PLANE_CHUNK;
     if (threadIdx.x < PLANE_CHUNK) {
         int c = c0 + threadIdx.x;
@@ -127,33 +106,62 @@ __global__ void __launch_bounds__(PLANE_BLOCK) plane_eval_kernel(const float4 *_
         s_cnt[threadIdx.x] = 0u;
     }
     __syncthreads();
-    int cnt[PLANE_CHUNK];
-    #pragma unroll
-    for (int k = 0; k < PLANE_CHUNK; ++k) cnt[k] = 0;
-    for (int i = blockIdx.x * PLANE_BLOCK + threadIdx.x; i < n_rem; i += gridDim.x * PLANE_BLOCK) {
-        const float4 p = rem[i];
-        #pragma unroll
-        for (int k = 0; k < PLANE_CHUNK; ++k) {
-            const float4 c = sc[k];
-            cnt[k] += (fabsf(s3d_plane_eval(c.x, c.y, c.z, c.w, p.x, p.y, p.z)) < tau) ? 1 : 0;
+    int c_lo = 0, c_hi = 0;
+    for (int base = blockIdx.x * PLANE_BLOCK + threadIdx.x - lane; base < n_rem; base += gridDim.x * PLANE_BLOCK) {      // warp-uniform
+        const int i = base + lane;
+        const bool in = i < n_rem;
+        float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (in) p = rem[i];
+        #pragma unroll 16
+        for (int k = 0; k < 32; ++k) {
+            const float4 a = sc[k], b = sc[k + 32];
+            const unsigned ba = __ballot_sync(0xffffffffu, in && fabsf(s3d_plane_eval(a.x, a.y, a.z, a.w, p.x, p.y, p.z)) < tau);
+            const unsigned bb = __ballot_sync(0xffffffffu, in && fabsf(s3d_plane_eval(b.x, b.y, b.z, b.w, p.x, p.y, p.z)) < tau);
+            if (lane == k) { c_lo += __popc(ba); c_hi += __popc(bb); }
         }
     }
-    // counts: warp shuffle -> shared-memory atomics -> ONE global atomic per candidate and CTA (integers: deterministic)
-    #pragma unroll
-    for (int k = 0; k < PLANE_CHUNK; ++k) {
-        int v = warp_sum_i(cnt[k]);
-        if ((threadIdx.x & 31) == 0 && v) atomicAdd(&s_cnt[k], (uint32_t)v);
-    }
+    if (c_lo) atomicAdd(&s_cnt[lane], (uint32_t)c_lo);
+    if (c_hi) atomicAdd(&s_cnt[lane + 32], (uint32_t)c_hi);
     __syncthreads();
     if (threadIdx.x < PLANE_CHUNK && s_cnt[threadIdx.x] && c0 + threadIdx.x < n_cand) atomicAdd(&counts[c0 + threadIdx.x], s_cnt[threadIdx.x]);
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) is_last = (atomicAdd(&st->ticket_eval, 1u) == gridDim.x * gridDim.y - 1);
     __syncthreads();
-    if (!is_last || threadIdx.x != 0) return;
+    if (!is_last) return;
     __threadfence();
+    // ---- replay of the sequential adaptive RANSAC loop over the pre-evaluated candidates
+    __shared__ int s_count[PLANE_MAX_CAND];
+    __shared__ double s_k[PLANE_MAX_CAND];
+    {
+        const double log_prob = log(1.0 - probability);
+        const double one_over = n_rem > 0 ? 1.0 / (double)n_rem : 0.0;
+        const double eps = 2.220446049250313e-16;
+        for (int c = threadIdx.x; c < n_cand; c += PLANE_BLOCK) {
+            const int cc = valid[c] ? (int)__ldcg(&counts[c]) : -1;                 // -1: invalid sample (skipped, iterations unchanged)
+            s_count[c] = cc;
+            double w = cc * one_over;
+            double p_no = 1.0 - w * w * w;
+            if (p_no < eps) p_no = eps;
+            if (p_no > 1.0 - eps) p_no = 1.0 - eps;
+            s_k[c] = log_prob / log(p_no);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    int iterations = 0, best = -1, best_count = -2147483647;
+    double k = 1.0;
+    for (int c = 0; c < n_cand && iterations < k; ++c) {
+        const int cc = s_count[c];
+        if (cc < 0) continue;
+        if (cc > best_count) { best_count = cc; best = c; k = s_k[c]; }
+        ++iterations;
+        if (iterations > max_iterations) break;
+    }
     st->ticket_eval = 0u;
-    plane_select(coefs, valid, counts, n_cand, n_rem, max_iterations, probability, st);
+    st->best_count = best >= 0 ? best_count : 0; st->iterations = iterations;
+    if (best < 0 || best_count == 0) { st->stopped = 1; st->active = 0; }          // reference :376-379
+    else { st->ransac = coefs[best]; st->refined = coefs[best]; }
 }
 
 // PCA refit over the inliers of the RANSAC model (SampleConsensusModelPlane::optimizeModelCoefficients): nine
@@ -408,7 +416,7 @@ extern "C" int s3d_segment_planes(s3d_ctx *ctx, s3d_cloud *cloud, const s3d_plan
     plane_init_kernel<<<g_wide, 256, 0, st>>>(cloud->d_pts, n, rem, cloud->d_labels, cloud->d_nrm, state);
     S3D_LAUNCHED(ctx);
     // worst-case grids (the first round scans all n points); kernels of rounds the device loop has left return at once
-    const dim3 ge(std::max(1, std::min(ctx->sm_count * 2, (n + PLANE_BLOCK - 1) / PLANE_BLOCK)), (n_cand + PLANE_CHUNK - 1) / PLANE_CHUNK);
+    const dim3 ge(std::max(1, std::min(ctx->sm_count * 4, (n + PLANE_BLOCK - 1) / PLANE_BLOCK)), (n_cand + PLANE_CHUNK - 1) / PLANE_CHUNK);
     const int nb = std::max(1, (n + S3D_COMPACT_BLOCK - 1) / S3D_COMPACT_BLOCK);
     for (int round = 0; round < prm->max_planes; ++round) {
         plane_hyp_kernel<<<1, PLANE_MAX_CAND, 0, st>>>(rem, n, prm->plane_percent, prm->max_planes, prm->seed, round, n_cand, coefs, valid, counts, state);

@@ -173,6 +173,9 @@ def _make_dataset(tmp_path, poses, cam, scene_of=None, extra_yaml=""):
 def _run_slam(tmp_path, loops):
     subprocess.run(["make", "-C", HOST, "-s"], check=True, env={**os.environ, "CXX": "g++", "CC": "gcc"})
     r = subprocess.run([os.path.join(HOST, "bin", "run_SLAM"), str(loops)], cwd=tmp_path, capture_output=True, text=True, timeout=600)
+    if os.environ.get("S3D_TEST_LOGDIR"):               # developer aid: keep the shell's output of every run
+        with open(os.path.join(os.environ["S3D_TEST_LOGDIR"], tmp_path.name + ".log"), "w") as f:
+            f.write(r.stdout + "\n--- stderr ---\n" + r.stderr)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     return r.stdout
 
