@@ -616,7 +616,8 @@ static_assert(TS_CAP * 16 >= 29 * 33 * 8, "the warp tile also carries the transp
 
 struct PersistArgs {
     const PairDesc *descs; PairState *states;
-    long long *partials;         // [2][groups][group_ctas][S3D_ROW]: (hi, lo) partial sums, double buffered by barrier parity
+    long long *gacc;             // [3][groups][S3D_ROW]: the group's (hi, lo) sums of an iteration, added with integer atomics (any order
+                                 // gives the same bits); three buffers by barrier epoch: one being added to, one being read, one being zeroed
     unsigned *barriers;          // [groups], zero at launch, monotonic
     // per-query state between iterations (49 bytes per query are read by the streaming pass):
     float4 *cq;                  // its correspondence (x,y,z, original target index; -1: none)
@@ -729,6 +730,22 @@ __global__ void __launch_bounds__(TS_BLOCK, 1) icp_persist_kernel(const PersistA
         const int cta_chunks = (cta_units + 3) >> 2;
         __syncthreads();
 
+        // stage PS_STAGE chunks of per-query state (49 B per query) into the warp's tile: every load in flight at once, no registers
+#define PS_STAGE_ROUND(c0_) do {                                                                                                      \
+            _Pragma("unroll") for (int s_ = 0; s_ < (int)PS_STAGE; ++s_) {                                                            \
+                const int m_ = 4 * ((c0_) + s_ * TS_WARPS) + (lane >> 3);                                                             \
+                const int i_ = ((rank + a.group_ctas * m_) << 3) + (lane & 7);                                                        \
+                if (m_ < cta_units && i_ < d.n_src) {                                                                                 \
+                    const uint32_t dst_ = sbuf + PS_CHUNK_BYTES * (uint32_t)s_ + 16u * (uint32_t)lane;                                \
+                    ts_cp_async16_s(dst_, &d.src[i_]);                                                                                \
+                    ts_cp_async16_s(dst_ + 512u, &my_cq[i_]);                                                                         \
+                    ts_cp_async16_s(dst_ + 1024u, &my_cn[i_]);                                                                        \
+                    if ((lane & 7) == 0)                                                                                              \
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sbuf + PS_CHUNK_BYTES * (uint32_t)s_ + 1536u + (uint32_t)lane), "l"(my_fl + i_) : "memory"); \
+                }                                                                                                                     \
+            }                                                                                                                         \
+        } while (0)
+
         for (int it = 0; it < a.iterations; ++it) {
             if (st.status != 0) break;            // failed pairs stop; every CTA of the group sees the same state
             const float *T = st.Tf;               // the pose is read from shared memory where it is used
@@ -768,19 +785,7 @@ __global__ void __launch_bounds__(TS_BLOCK, 1) icp_persist_kernel(const PersistA
             if (it > 0) {
                 int since = 0;
                 for (int c0 = warp; c0 < cta_chunks; c0 += TS_WARPS * PS_STAGE) {
-                    #pragma unroll
-                    for (int s = 0; s < PS_STAGE; ++s) {
-                        const int m = 4 * (c0 + s * TS_WARPS) + (lane >> 3);
-                        const int i = ((rank + a.group_ctas * m) << 3) + (lane & 7);
-                        if (m < cta_units && i < d.n_src) {
-                            const uint32_t dst = sbuf + PS_CHUNK_BYTES * (uint32_t)s + 16u * (uint32_t)lane;
-                            ts_cp_async16_s(dst, &d.src[i]);
-                            ts_cp_async16_s(dst + 512u, &my_cq[i]);
-                            ts_cp_async16_s(dst + 1024u, &my_cn[i]);
-                            if ((lane & 7) == 0)
-                                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sbuf + PS_CHUNK_BYTES * (uint32_t)s + 1536u + (uint32_t)lane), "l"(my_fl + i) : "memory");
-                        }
-                    }
+                    if (c0 != warp) PS_STAGE_ROUND(c0);       // (the first round was issued before the previous iteration's barrier)
                     ts_cp_async_wait_all();
                     __syncwarp();
                     #pragma unroll 1
@@ -860,110 +865,132 @@ __global__ void __launch_bounds__(TS_BLOCK, 1) icp_persist_kernel(const PersistA
             PHASE(8);
 
             // ---------------------------------------------------------------- pass 2: search what is pending
+            // Warps take items (item_octets octets, one per 8 lanes) from the CTA's list.  Two-deep software pipeline: while item n is
+            // searched, the point and old correspondence of item n+1 and the list entry of item n+2 are already on their way.
             {
                 const int n_items = it == 0 ? cta_units : pend_count;
-                const uint32_t spre = sbuf;       // (the tile is also the staging area of the item's 2 x 32 float4)
-                for (;;) {
-                    int e0 = 0;
-                    if (lane == 0) e0 = atomicAdd(&pend_next, a.item_octets);
-                    e0 = __shfl_sync(full, e0, 0);
-                    if (e0 >= n_items) break;
-                    const int e = e0 + (lane >> 3);
-                    uint32_t ent = 0u;
-                    if (e < n_items && lane < 8 * a.item_octets) ent = it == 0 ? (((uint32_t)e << 8) | 0xffu) : __ldcg(&my_pend[e]);
-                    const int m = (int)(ent >> 8);
-                    const int i = ((rank + a.group_ctas * m) << 3) + (lane & 7);
-                    const bool pending = ((ent >> (lane & 7)) & 1u) && i < d.n_src;
+                if (n_items > 0) {
+                    auto take = [&]() -> int {
+                        int e0 = 0;
+                        if (lane == 0) e0 = atomicAdd(&pend_next, a.item_octets);
+                        return __shfl_sync(full, e0, 0) + (lane >> 3);
+                    };
+                    auto entry = [&](int e) -> uint32_t {
+                        if (e >= n_items || lane >= 8 * a.item_octets) return 0u;
+                        return it == 0 ? (((uint32_t)e << 8) | 0xffu) : __ldcg(&my_pend[e]);
+                    };
+                    int e_cur = take();
+                    uint32_t ent_cur = entry(e_cur);
+                    int e_nxt = take();
+                    uint32_t ent_nxt = entry(e_nxt);
                     float4 p = make_float4(0.f, 0.f, 0.f, 0.f), q = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
-                    if (pending) {
-                        p = d.src[i];
-                        if (it > 0) q = __ldcg(&my_cq[i]);
+                    {
+                        const int i = ((rank + a.group_ctas * (int)(ent_cur >> 8)) << 3) + (lane & 7);
+                        if (((ent_cur >> (lane & 7)) & 1u) && i < d.n_src) { p = d.src[i]; if (it > 0) q = __ldcg(&my_cq[i]); }
                     }
-                    (void)spre;
-                    float3 x = make_float3(0.f, 0.f, 0.f);
-                    float r = a.first_cells * cell;
-                    if (pending) {
-                        x = s3d_xform(T, p.x, p.y, p.z);
-                        if (__float_as_int(q.w) >= 0) {
-                            // The old correspondence is a real target point, so its distance bounds the ball.  After a small move it is
-                            // also tight; after a big pose update (first iterations) the point slid along the surface and one cell
-                            // is the better first guess (tile_search verifies and widens when needed).
-                            const float dq = sqrtf(s3d_dist2(x.x, x.y, x.z, q.x, q.y, q.z));
-                            const float3 xo = s3d_xform(st.Tf_prev, p.x, p.y, p.z);
-                            const float step_mv = sqrtf(s3d_dist2(x.x, x.y, x.z, xo.x, xo.y, xo.z));
-                            r = dq * 1.00001f + slack;
-                            if (step_mv > 0.25f * cell) r = fminf(r, a.hint_cells * cell + slack);
+                    while (__shfl_sync(full, e_cur, 0) < n_items) {
+                        // next item's state and the entry after it: in flight during this item's search
+                        float4 pn = make_float4(0.f, 0.f, 0.f, 0.f), qn = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
+                        {
+                            const int in_ = ((rank + a.group_ctas * (int)(ent_nxt >> 8)) << 3) + (lane & 7);
+                            if (((ent_nxt >> (lane & 7)) & 1u) && in_ < d.n_src) { pn = d.src[in_]; if (it > 0) qn = __ldcg(&my_cq[in_]); }
                         }
-                    }
-                    // first iteration: the nearest point of the decimated target (level 0) bounds the fine search (level 1)
-                    TileOut b;
-                    for (int level = (it == 0 && have_coarse) ? 0 : 1; level < 2; ++level) {
-                        STAT(level ? 0 : 6, pending);
+                        const int e_n2 = take();
+                        const uint32_t ent_n2 = entry(e_n2);
+
+                        const int m = (int)(ent_cur >> 8);
+                        const int i = ((rank + a.group_ctas * m) << 3) + (lane & 7);
+                        const bool pending = ((ent_cur >> (lane & 7)) & 1u) && i < d.n_src;
+                        float3 x = make_float3(0.f, 0.f, 0.f);
+                        float r = a.first_cells * cell;
+                        if (pending) {
+                            x = s3d_xform(T, p.x, p.y, p.z);
+                            if (__float_as_int(q.w) >= 0) {
+                                // The old correspondence is a real target point, so its distance bounds the ball.  After a small move it is
+                                // also tight; after a big pose update (first iterations) the point slid along the surface and one cell
+                                // is the better first guess (tile_search verifies and widens when needed).
+                                const float dq = sqrtf(s3d_dist2(x.x, x.y, x.z, q.x, q.y, q.z));
+                                const float3 xo = s3d_xform(st.Tf_prev, p.x, p.y, p.z);
+                                const float step_mv = sqrtf(s3d_dist2(x.x, x.y, x.z, xo.x, xo.y, xo.z));
+                                r = dq * 1.00001f + slack;
+                                if (step_mv > 0.25f * cell) r = fminf(r, a.hint_cells * cell + slack);
+                            }
+                        }
+                        // first iteration: the nearest point of the decimated target (level 0) bounds the fine search (level 1)
+                        TileOut b;
+                        for (int level = (it == 0 && have_coarse) ? 0 : 1; level < 2; ++level) {
+                            STAT(level ? 0 : 6, pending);
 #ifdef TS_USE_TMA
-                        b = tile_search(&cfg[level], x.x, x.y, x.z, level ? r : ccell, pending, buf, lane, level == 1 && it >= 4, bar_w, &parity TS_TM_PASS);
+                            b = tile_search(&cfg[level], x.x, x.y, x.z, level ? r : ccell, pending, buf, lane, level == 1 && it >= 4, bar_w, &parity TS_TM_PASS);
 #else
-                        b = tile_search(&cfg[level], x.x, x.y, x.z, level ? r : ccell, pending, buf, lane, level == 1 && it >= 4 TS_TM_PASS);
+                            b = tile_search(&cfg[level], x.x, x.y, x.z, level ? r : ccell, pending, buf, lane, level == 1 && it >= 4 TS_TM_PASS);
 #endif
-                        if (level == 0 && pending && b.bd < INFINITY) r = sqrtf(b.bd) * 1.00001f + slack;
+                            if (level == 0 && pending && b.bd < INFINITY) r = sqrtf(b.bd) * 1.00001f + slack;
+                        }
+                        if (pending) {
+                            float4 qw = b.bq;
+                            const float d2q = b.bd;
+                            if (!(b.bd < INFINITY)) qw.w = __int_as_float(-1);      // nothing within reach
+                            float4 nv = make_float4(0.f, 0.f, 0.f, 1.f);
+                            if (EST == S3D_ESTIMATOR_POINT_TO_PLANE && __float_as_int(qw.w) >= 0) nv = __ldg(&d.tgt_nrm[__float_as_int(qw.w)]);
+                            const bool tie = b.lb3 > 0.f;
+                            const unsigned f = (unsigned)(it & 63) | (tie ? PS_FLAG_TIE : 0u) | (nv.w != 0.f ? PS_FLAG_NRM : 0u);
+                            my_cq[i] = qw;
+                            my_cn[i] = make_float4(nv.x, nv.y, nv.z, tie ? b.lb3 : b.lb);
+                            my_fl[i] = (uint8_t)f;
+                            if (tie) my_cq2[i] = b.q2;                             // near tie: keep the runner-up too
+                            const bool ok = (__float_as_int(qw.w) >= 0) && (d2q <= a.max_d2) && (nv.w != 0.f);
+                            if (ok) { accumulate_fx<EST>(acc, M, x.x, x.y, x.z, qw, nv, d2q); ++cnt; }
+                            if (last && a.nn_out) a.nn_out[i] = ok ? __float_as_int(qw.w) : -1;
+                        }
+                        PS_HAND_OVER();
+                        e_cur = e_nxt; ent_cur = ent_nxt; p = pn; q = qn;
+                        e_nxt = e_n2; ent_nxt = ent_n2;
                     }
-                    if (pending) {
-                        q = b.bq;
-                        const float d2q = b.bd;
-                        if (!(b.bd < INFINITY)) q.w = __int_as_float(-1);      // nothing within reach
-                        float4 nv = make_float4(0.f, 0.f, 0.f, 1.f);
-                        if (EST == S3D_ESTIMATOR_POINT_TO_PLANE && __float_as_int(q.w) >= 0) nv = __ldg(&d.tgt_nrm[__float_as_int(q.w)]);
-                        const bool tie = b.lb3 > 0.f;
-                        const unsigned f = (unsigned)(it & 63) | (tie ? PS_FLAG_TIE : 0u) | (nv.w != 0.f ? PS_FLAG_NRM : 0u);
-                        my_cq[i] = q;
-                        my_cn[i] = make_float4(nv.x, nv.y, nv.z, tie ? b.lb3 : b.lb);
-                        my_fl[i] = (uint8_t)f;
-                        if (tie) my_cq2[i] = b.q2;                             // near tie: keep the runner-up too
-                        const bool ok = (__float_as_int(q.w) >= 0) && (d2q <= a.max_d2) && (nv.w != 0.f);
-                        if (ok) { accumulate_fx<EST>(acc, M, x.x, x.y, x.z, q, nv, d2q); ++cnt; }
-                        if (last && a.nn_out) a.nn_out[i] = ok ? __float_as_int(q.w) : -1;
-                    }
-                    PS_HAND_OVER();
                 }
             }
             PHASE(9);
-            // ---------------------------------------------------------------- the CTA's row, group barrier, totals, solve
+            // ---------------------------------------------------------------- the group's sums, group barrier, solve
             __syncthreads();
-            long long *rows = a.partials + ((size_t)(epoch & 1u) * a.groups + group) * a.group_ctas * S3D_ROW;
+            // The per-query state of the next iteration is final (pass 2 wrote it) and does not depend on the pose: its first
+            // staging round is issued now, so that its latency is hidden behind the barrier and the solve.
+            if (!last && warp < cta_chunks) PS_STAGE_ROUND(warp);
             if (a.group_ctas > 1) {
-                if (threadIdx.x < S3D_ROW) __stcg(&rows[(size_t)rank * S3D_ROW + threadIdx.x], ctot[threadIdx.x]);
+                // the CTA's sums go to the group's accumulators (red.add.u64: integers, order free); then arrive at the barrier
+                long long *g = a.gacc + ((size_t)(epoch % 3u) * a.groups + group) * S3D_ROW;
+                if (threadIdx.x < S3D_ROW) {
+                    const long long v = ctot[threadIdx.x];
+                    if (v != 0) atomicAdd(reinterpret_cast<unsigned long long *>(&g[threadIdx.x]), (unsigned long long)v);
+                    ctot[threadIdx.x] = 0;
+                }
                 ++epoch;
                 __syncthreads();
-                if (threadIdx.x < S3D_ROW) ctot[threadIdx.x] = 0;
-                if (threadIdx.x == 0) {
-                    // release (this CTA's row, written by its other threads before the __syncthreads above) -> arrive -> wait -> acquire
-                    __threadfence();
-                    red_release_add_u32(bar, 1u);
-                    const unsigned target = epoch * (unsigned)a.group_ctas;
-                    while (ld_acquire_u32(bar) < target) { }
-                    __threadfence();
-                }
-                __syncthreads();
-                PHASE(10);
-                // every CTA adds the group's rows (integers: any order): 64 values per row, 8 rows per sweep of the 512 threads
-                {
-                    const int slot = threadIdx.x & (S3D_ROW - 1), part = threadIdx.x / S3D_ROW;
-                    long long v = 0;
-                    for (int c = part; c < a.group_ctas; c += 4 * (TS_BLOCK / S3D_ROW)) {
-                        long long w0 = 0, w1 = 0, w2 = 0, w3 = 0;
-                        const int c1 = c + (TS_BLOCK / S3D_ROW), c2 = c1 + (TS_BLOCK / S3D_ROW), c3 = c2 + (TS_BLOCK / S3D_ROW);
-                        w0 = __ldcg(&rows[(size_t)c * S3D_ROW + slot]);
-                        if (c1 < a.group_ctas) w1 = __ldcg(&rows[(size_t)c1 * S3D_ROW + slot]);
-                        if (c2 < a.group_ctas) w2 = __ldcg(&rows[(size_t)c2 * S3D_ROW + slot]);
-                        if (c3 < a.group_ctas) w3 = __ldcg(&rows[(size_t)c3 * S3D_ROW + slot]);
-                        v += (w0 + w1) + (w2 + w3);
+                if (warp == 0) {
+                    if (lane == 0) {
+                        // release (the CTA's atomics, issued by other threads before the __syncthreads above) -> arrive -> wait -> acquire
+                        __threadfence();
+                        red_release_add_u32(bar, 1u);
+                        const unsigned target = epoch * (unsigned)a.group_ctas;
+                        while (ld_acquire_u32(bar) < target) { }
+                        __threadfence();
                     }
-                    if (v != 0) smem_add_i64(&ctot[slot], v);
+                    __syncwarp();
+                    PHASE(10);
+                    const long long hi = __ldcg(&g[lane]), lo = __ldcg(&g[32 + lane]);
+                    total[lane] = lane < 29 ? fx_total<EST>(hi, lo, lane, fxs.scale) : 0.0;
+                    // the buffer read two epochs ago is free: every CTA is past the barrier that followed its reads.  It is added to
+                    // again only after the NEXT barrier, which this CTA (rank 0) reaches after these stores.
+                    if (rank == 0) {
+                        long long *gz = a.gacc + ((size_t)((epoch + 1u) % 3u) * a.groups + group) * S3D_ROW;
+                        __stcg(&gz[lane], 0ll); __stcg(&gz[32 + lane], 0ll);
+                    }
+                    __syncwarp();
                 }
-                __syncthreads();
+            } else if (warp == 0) {
+                total[lane] = lane < 29 ? fx_total<EST>(ctot[lane], ctot[32 + lane], lane, fxs.scale) : 0.0;
+                __syncwarp();
+                ctot[lane] = 0; ctot[32 + lane] = 0;
             }
-            if (threadIdx.x < 32) total[threadIdx.x] = threadIdx.x < 29 ? fx_total<EST>(ctot[threadIdx.x], ctot[32 + threadIdx.x], threadIdx.x, fxs.scale) : 0.0;
-            __syncthreads();
-            if (threadIdx.x < S3D_ROW) ctot[threadIdx.x] = 0;
             PHASE(11);
             if (threadIdx.x == 0) {
                 solve_and_update<EST>(total, &st, a.min_corr, a.pivot_eps);
@@ -975,6 +1002,8 @@ __global__ void __launch_bounds__(TS_BLOCK, 1) icp_persist_kernel(const PersistA
             __syncthreads();
             PHASE(12);
         }
+        ts_cp_async_wait_all();                   // a staging round issued ahead of an iteration that did not run (failed pair)
+        __syncwarp();
         if (rank == 0 && threadIdx.x == 0) a.states[pair] = st;
     }
 }
@@ -1083,7 +1112,7 @@ int s3d_register_issue(s3d_ctx *ctx, const s3d_cloud *const *src, const s3d_clou
         const int useful = std::max(1, (n_max + 32 * chunks_per_cta - 1) / (32 * chunks_per_cta));
         p_group_ctas = std::max(1, std::min(useful, p_res / std::min(n_pairs, p_res)));
         p_groups = std::max(1, std::min(n_pairs, p_res / p_group_ctas));
-        ctas = 2 * p_group_ctas;                      // partial rows are double buffered
+        ctas = 3;                                     // d_partials doubles as the groups' accumulators: 3 epochs x groups (<= pairs) rows
     }
     int rc = ensure_batch(ctx, n_pairs, ctas);
     if (rc) return rc;
@@ -1180,8 +1209,9 @@ int s3d_register_issue(s3d_ctx *ctx, const s3d_cloud *const *src, const s3d_clou
     int iter_launches = 0;
     if (persist && prm->max_iterations > 0) {
         S3D_CUDA(ctx, cudaMemsetAsync(ctx->d_barriers, 0, sizeof(unsigned) * p_groups, ctx->stream));
+        S3D_CUDA(ctx, cudaMemsetAsync(ctx->d_partials, 0, sizeof(long long) * S3D_ROW * 3 * (size_t)p_groups, ctx->stream));
         PersistArgs pa;
-        pa.descs = ctx->d_desc; pa.states = ctx->d_state; pa.partials = ctx->d_partials; pa.barriers = ctx->d_barriers;
+        pa.descs = ctx->d_desc; pa.states = ctx->d_state; pa.gacc = ctx->d_partials; pa.barriers = ctx->d_barriers;
         pa.cq = ctx->d_cq; pa.cn = ctx->d_cn; pa.cq2 = ctx->d_cq2; pa.flags = ctx->d_flags; pa.pend = ctx->d_pend;
         pa.nn_stride = nn_stride8; pa.pend_stride = pend_stride;
         pa.n_pairs = n_pairs; pa.groups = p_groups; pa.group_ctas = p_group_ctas; pa.iterations = prm->max_iterations;

@@ -461,6 +461,9 @@ bool GraphicEnd::check(int frame1, int frame2)
     cout << YELLOW << "checking " << frame1 << ", " << frame2 << RESET << endl;                     // :889
     RESULT_OF_MULTIPNP result = multiPnP(_keyframes[frame1].planes, _keyframes[frame2].planes, true, _keyframes[frame1].frame_index,
                                          _loop_closure_inliers);
+    // the search index this registration built on key frame `frame2` is not kept (only the current key frame stays a target)
+    if (!_keyframes[frame2].planes.empty() && _keyframes[frame2].planes[0].cloud != (_currKF.planes.empty() ? 0 : _currKF.planes[0].cloud))
+        s3d_cloud_drop_index(_ctx, const_cast<s3d_cloud *>(_keyframes[frame2].planes[0].cloud));
     if (result.T.isIdentity()) return false;
     if (result.norm > _loop_closure_error) return false;
     if (result.inliers < _loop_closure_inliers) return false;

@@ -10,7 +10,8 @@ struct Isometry3d {
     Isometry3d() { setIdentity(); }
     static Isometry3d Identity() { return Isometry3d(); }
     void setIdentity() { std::memset(m, 0, sizeof(m)); m[0] = m[5] = m[10] = m[15] = 1.0; }
-    bool isIdentity() const { Isometry3d I; return std::memcmp(m, I.m, sizeof(m)) == 0; }   // T.matrix() == Identity
+    // T.matrix() == Identity, compared by VALUE like Eigen does: the inverse of the identity carries -0.0 in its translation
+    bool isIdentity() const { for (int i = 0; i < 16; ++i) if (m[i] != ((i % 5 == 0) ? 1.0 : 0.0)) return false; return true; }
     double &operator()(int r, int c) { return m[4 * r + c]; }
     double operator()(int r, int c) const { return m[4 * r + c]; }
     Isometry3d operator*(const Isometry3d &o) const

@@ -48,6 +48,7 @@ int main(int argc, char **argv)
     Isometry3d I = T * T.inverse();
     for (int i = 0; i < 16; ++i) REQUIRE(std::fabs(I.m[i] - Isometry3d().m[i]) < 1e-14);
     REQUIRE(!T.isIdentity());
+    REQUIRE(Isometry3d().inverse().isIdentity());          // -0.0 in the inverse's translation is still the identity (reference :173 compares values)
     double q[4]; T.quaternion(q);
     REQUIRE(std::fabs(q[2] - std::sin(a / 2)) < 1e-14 && std::fabs(q[3] - std::cos(a / 2)) < 1e-14 && std::fabs(q[0]) < 1e-15);
     // --- g2o text output

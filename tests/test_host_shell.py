@@ -237,8 +237,8 @@ def test_run_slam_loop_closure_and_save_output(tmp_path, ctx):
 
 @pytest.mark.gpu
 def test_run_slam_lost_recovery(tmp_path):
-    """Frames in which the camera has turned away and sees only the floor cannot be registered (one plane: rank-deficient
-    point-to-plane system, status DEGENERATE -> T == Identity, the reference's failure convention).  With lost_frames: 1 the
+    """Frames in which the camera has turned away and sees only a far strip of floor cannot be registered (no correspondence
+    within icp_max_corr_dist: status FEW -> T == Identity, the reference's failure convention).  With lost_frames: 1 the
     second such frame triggers lostRecovery() (reference src/GraphicEnd.cpp:764-838): a key frame without an edge to its
     predecessor, a line `kf_id frame_index` in lost.txt (:775-777), a sweep over all earlier key frames."""
     cam = synth.Camera().scaled(0.25)
