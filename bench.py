@@ -311,9 +311,25 @@ def main():
     h2d = int(pin[0][0].numel() * 4 + pin[0][1].numel() * 4)
     d2h = int(rec_bytes + 3 * 24 + 3 * (64 + 4))
 
+    # ---- plane extraction (A2): 16 N bytes per evaluation pass over the CUDA-event time of plane_eval_kernel --------
+    planes_roofline = None
+    if world == 1:
+        cp = ctx.upload(host[0]["tgt"])
+        for _ in range(3):
+            cp.segment_planes(plane_prm)
+        ev, tot, pts = [], [], 0
+        for _ in range(10):
+            cp.segment_planes(plane_prm)
+            tmp = ctx.last_plane_timing()
+            ev.append(tmp["eval_ms"]); tot.append(tmp["total_ms"]); pts = tmp["points_scanned"] * tmp["eval_passes_per_round"]
+        cp.free()
+        planes_roofline = {"kernel": "plane_eval_kernel (64 RANSAC candidates per pass over the remaining points)", "bound": "hbm",
+                           "algorithmic_bytes": pts * 16, "eval_us": float(np.median(ev)) * 1e3, "extraction_device_us": float(np.median(tot)) * 1e3,
+                           "achieved": pts * 16 / (float(np.median(ev)) * 1e-3) / 1e9, "unit": "GB/s", "passes": int(tmp["rounds"] * tmp["eval_passes_per_round"])}
+
     # ---- the bandwidth-bound regime of the same kernel: late iterations of a batch whose working set exceeds L2 ----------
-    # (every query keeps its correspondence: an iteration is the two streaming passes over source, correspondence,
-    # search state and normal).  time per late iteration = (t(40 iterations) - t(10 iterations)) / 30.
+    # (every query keeps its correspondence: an iteration is ONE streaming pass over source, correspondence, normal + bound
+    # and a flag byte: 49 B per query).  time per late iteration = (t(40 iterations) - t(10 iterations)) / 30.
     batch_regime = None
     if world == 1 and not args.no_batch_regime and args.pool >= 8:
         nb = min(args.pool, 16)
@@ -331,8 +347,8 @@ def main():
         t10, t40 = batch_ms(10), batch_ms(40)
         per_it_s = (t40 - t10) / 30.0 * 1e-3
         batch_regime = {"pairs": nb, "t10_ms": t10, "t40_ms": t40, "late_iteration_us": per_it_s * 1e6,
-                        "algorithmic_GBps": nb * B_ALG / per_it_s / 1e9, "read_GBps": nb * N_PTS * 96 / per_it_s / 1e9,
-                        "bytes_read_per_query": 96}
+                        "algorithmic_GBps": nb * B_ALG / per_it_s / 1e9, "read_GBps": nb * N_PTS * 49 / per_it_s / 1e9,
+                        "bytes_read_per_query": 49}
 
     # ---- config 4 (BASELINE.json configs[3]): 512*N/8 independent pairs block-partitioned over the N ranks, 10 iterations,
     # ONE s3d_register_batch_gather per step and rank: the shard goes through the persistent kernel as one batch, the pose
@@ -444,6 +460,10 @@ def main():
                 "gathered_records": config4["pairs_total"], "record_bytes": rec_bytes, "gpu_launches": int(cnt[1].item()),
                 "roofline_frac_algorithmic": B_ALG * config4["pairs_per_gpu"] * config4["iterations"] * config4["steps"] / (float(tmax2[2].item()) * 1e-3) / 1e9 / peak,
             }
+        if planes_roofline:
+            planes_roofline["peak"] = peak
+            planes_roofline["frac"] = planes_roofline["achieved"] / peak
+            out["roofline_planes"] = planes_roofline
         if batch_regime:
             batch_regime["frac_algorithmic"] = batch_regime["algorithmic_GBps"] / peak
             batch_regime["frac_read"] = batch_regime["read_GBps"] / peak

@@ -25,6 +25,16 @@ __device__ __forceinline__ float3 s3d_xform(const float *__restrict__ T, float x
     return o;
 }
 
+// the same map with the pose held as three float4 rows (identical operations, identical bits)
+__device__ __forceinline__ float3 s3d_xform4(const float4 r0, const float4 r1, const float4 r2, float x, float y, float z)
+{
+    float3 o;
+    o.x = __fmaf_rn(r0.z, z, __fmaf_rn(r0.y, y, __fmaf_rn(r0.x, x, r0.w)));
+    o.y = __fmaf_rn(r1.z, z, __fmaf_rn(r1.y, y, __fmaf_rn(r1.x, x, r1.w)));
+    o.z = __fmaf_rn(r2.z, z, __fmaf_rn(r2.y, y, __fmaf_rn(r2.x, x, r2.w)));
+    return o;
+}
+
 __device__ __forceinline__ float s3d_dist2(float px, float py, float pz, float qx, float qy, float qz)
 {
     float dx = __fsub_rn(px, qx), dy = __fsub_rn(py, qy), dz = __fsub_rn(pz, qz);

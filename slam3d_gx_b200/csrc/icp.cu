@@ -670,7 +670,7 @@ __global__ void __launch_bounds__(TS_BLOCK, 1) icp_persist_kernel(const PersistA
     extern __shared__ __align__(16) unsigned char ts_smem[];
     float4 *tiles = reinterpret_cast<float4 *>(ts_smem);          // TS_WARPS tiles of TS_CAP candidates
     __shared__ PairState st;                                      // this CTA's copy of the pair state (all CTAs of a group agree bit for bit)
-    __shared__ float hist[PS_HIST][12];                           // float poses of the last PS_HIST iterations (ring)
+    __shared__ float4 hist[PS_HIST][3];                           // float poses (three rows) of the last PS_HIST iterations (ring)
     __shared__ long long ctot[S3D_ROW];                           // the CTA's (hi, lo) sums of this iteration, then the group's totals
     __shared__ double total[S3D_NACC];                            // the pair's 29 sums as doubles, input of the solve
     __shared__ FxScale fxs;                                       // resolution of this iteration's sums (from the pose and the data bounds)
@@ -716,7 +716,7 @@ __global__ void __launch_bounds__(TS_BLOCK, 1) icp_persist_kernel(const PersistA
         }
         if (threadIdx.x < S3D_ROW) ctot[threadIdx.x] = 0;
         __syncthreads();
-        if (threadIdx.x < 12) hist[0][threadIdx.x] = st.Tf[threadIdx.x];
+        if (threadIdx.x < 3) hist[0][threadIdx.x] = make_float4(st.Tf[4 * threadIdx.x], st.Tf[4 * threadIdx.x + 1], st.Tf[4 * threadIdx.x + 2], st.Tf[4 * threadIdx.x + 3]);
         const float cell = cfg[1].gp.cell, slack = cfg[1].slack, ccell = cfg[0].gp.cell;
         float4 *my_cq = a.cq + (size_t)pair * a.nn_stride;
         float4 *my_cn = a.cn + (size_t)pair * a.nn_stride;
@@ -753,6 +753,9 @@ __global__ void __launch_bounds__(TS_BLOCK, 1) icp_persist_kernel(const PersistA
             const unsigned long long mbits = fxs.mbits;
             const double M = __longlong_as_double((long long)mbits);
             PHASE_T0();
+#if defined(S3D_PHASES)
+            long long tm[5] = {0, 0, 0, 0, 0};
+#endif
 
             // 29 wrapping int64 accumulators per thread.  hand_over(): unbias, add the 32 lanes through the warp's tile
             // (transposed: lane k adds slot k of the 32 lanes), split into (hi, lo), add to the CTA's sums (smem atomics).
@@ -801,12 +804,14 @@ __global__ void __launch_bounds__(TS_BLOCK, 1) icp_persist_kernel(const PersistA
                             float4 q = ts_lds128(sl + 512u), nv = ts_lds128(sl + 1024u);
                             unsigned f;
                             asm volatile("ld.shared.u8 %0, [%1];" : "=r"(f) : "r"(sbuf + PS_CHUNK_BYTES * (uint32_t)s + 1536u + (uint32_t)lane));
-                            const float3 x = s3d_xform(T, p.x, p.y, p.z);
+                            const float4 *Tn = hist[it & (PS_HIST - 1)];
+                            const float3 x = s3d_xform4(Tn[0], Tn[1], Tn[2], p.x, p.y, p.z);
                             pending = true;
                             if (__float_as_int(q.w) >= 0) {
                                 // the query was at xs when it was last searched; every other target point was >= lb away from there
                                 const int its = (int)(f & 63u);
-                                const float3 xs = s3d_xform(hist[its], p.x, p.y, p.z);
+                                const float4 *Ts = hist[its];
+                                const float3 xs = s3d_xform4(Ts[0], Ts[1], Ts[2], p.x, p.y, p.z);
                                 float d2q = s3d_dist2(x.x, x.y, x.z, q.x, q.y, q.z);
                                 const float moved = sqrtf(s3d_dist2(x.x, x.y, x.z, xs.x, xs.y, xs.z)) * 1.000002f + 5e-8f;
                                 const float lb = nv.w;
@@ -865,88 +870,68 @@ __global__ void __launch_bounds__(TS_BLOCK, 1) icp_persist_kernel(const PersistA
             PHASE(8);
 
             // ---------------------------------------------------------------- pass 2: search what is pending
-            // Warps take items (item_octets octets, one per 8 lanes) from the CTA's list.  Two-deep software pipeline: while item n is
-            // searched, the point and old correspondence of item n+1 and the list entry of item n+2 are already on their way.
+            // Warps take items (item_octets octets, one per 8 lanes) from the CTA's list until it is empty.
             {
                 const int n_items = it == 0 ? cta_units : pend_count;
-                if (n_items > 0) {
-                    auto take = [&]() -> int {
-                        int e0 = 0;
-                        if (lane == 0) e0 = atomicAdd(&pend_next, a.item_octets);
-                        return __shfl_sync(full, e0, 0) + (lane >> 3);
-                    };
-                    auto entry = [&](int e) -> uint32_t {
-                        if (e >= n_items || lane >= 8 * a.item_octets) return 0u;
-                        return it == 0 ? (((uint32_t)e << 8) | 0xffu) : __ldcg(&my_pend[e]);
-                    };
-                    int e_cur = take();
-                    uint32_t ent_cur = entry(e_cur);
-                    int e_nxt = take();
-                    uint32_t ent_nxt = entry(e_nxt);
+                while (n_items > 0) {
+                    int e0 = 0;
+                    if (lane == 0) e0 = atomicAdd(&pend_next, a.item_octets);
+                    e0 = __shfl_sync(full, e0, 0);
+                    if (e0 >= n_items) break;
+                    const int e = e0 + (lane >> 3);
+                    uint32_t ent = 0u;
+                    if (e < n_items && lane < 8 * a.item_octets) ent = it == 0 ? (((uint32_t)e << 8) | 0xffu) : __ldcg(&my_pend[e]);
+                    const int m = (int)(ent >> 8);
+                    const int i = ((rank + a.group_ctas * m) << 3) + (lane & 7);
+                    const bool pending = ((ent >> (lane & 7)) & 1u) && i < d.n_src;
                     float4 p = make_float4(0.f, 0.f, 0.f, 0.f), q = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
-                    {
-                        const int i = ((rank + a.group_ctas * (int)(ent_cur >> 8)) << 3) + (lane & 7);
-                        if (((ent_cur >> (lane & 7)) & 1u) && i < d.n_src) { p = d.src[i]; if (it > 0) q = __ldcg(&my_cq[i]); }
+                    if (pending) {
+                        p = d.src[i];
+                        if (it > 0) q = __ldcg(&my_cq[i]);
                     }
-                    while (__shfl_sync(full, e_cur, 0) < n_items) {
-                        // next item's state and the entry after it: in flight during this item's search
-                        float4 pn = make_float4(0.f, 0.f, 0.f, 0.f), qn = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
-                        {
-                            const int in_ = ((rank + a.group_ctas * (int)(ent_nxt >> 8)) << 3) + (lane & 7);
-                            if (((ent_nxt >> (lane & 7)) & 1u) && in_ < d.n_src) { pn = d.src[in_]; if (it > 0) qn = __ldcg(&my_cq[in_]); }
+                    float3 x = make_float3(0.f, 0.f, 0.f);
+                    float r = a.first_cells * cell;
+                    if (pending) {
+                        x = s3d_xform(T, p.x, p.y, p.z);
+                        if (__float_as_int(q.w) >= 0) {
+                            // The old correspondence is a real target point, so its distance bounds the ball.  After a small move it is
+                            // also tight; after a big pose update (first iterations) the point slid along the surface and one cell
+                            // is the better first guess (tile_search verifies and widens when needed).
+                            const float dq = sqrtf(s3d_dist2(x.x, x.y, x.z, q.x, q.y, q.z));
+                            const float3 xo = s3d_xform(st.Tf_prev, p.x, p.y, p.z);
+                            const float step_mv = sqrtf(s3d_dist2(x.x, x.y, x.z, xo.x, xo.y, xo.z));
+                            r = dq * 1.00001f + slack;
+                            if (step_mv > 0.25f * cell) r = fminf(r, a.hint_cells * cell + slack);
                         }
-                        const int e_n2 = take();
-                        const uint32_t ent_n2 = entry(e_n2);
-
-                        const int m = (int)(ent_cur >> 8);
-                        const int i = ((rank + a.group_ctas * m) << 3) + (lane & 7);
-                        const bool pending = ((ent_cur >> (lane & 7)) & 1u) && i < d.n_src;
-                        float3 x = make_float3(0.f, 0.f, 0.f);
-                        float r = a.first_cells * cell;
-                        if (pending) {
-                            x = s3d_xform(T, p.x, p.y, p.z);
-                            if (__float_as_int(q.w) >= 0) {
-                                // The old correspondence is a real target point, so its distance bounds the ball.  After a small move it is
-                                // also tight; after a big pose update (first iterations) the point slid along the surface and one cell
-                                // is the better first guess (tile_search verifies and widens when needed).
-                                const float dq = sqrtf(s3d_dist2(x.x, x.y, x.z, q.x, q.y, q.z));
-                                const float3 xo = s3d_xform(st.Tf_prev, p.x, p.y, p.z);
-                                const float step_mv = sqrtf(s3d_dist2(x.x, x.y, x.z, xo.x, xo.y, xo.z));
-                                r = dq * 1.00001f + slack;
-                                if (step_mv > 0.25f * cell) r = fminf(r, a.hint_cells * cell + slack);
-                            }
-                        }
-                        // first iteration: the nearest point of the decimated target (level 0) bounds the fine search (level 1)
-                        TileOut b;
-                        for (int level = (it == 0 && have_coarse) ? 0 : 1; level < 2; ++level) {
-                            STAT(level ? 0 : 6, pending);
+                    }
+                    // first iteration: the nearest point of the decimated target (level 0) bounds the fine search (level 1)
+                    TileOut b;
+                    for (int level = (it == 0 && have_coarse) ? 0 : 1; level < 2; ++level) {
+                        STAT(level ? 0 : 6, pending);
 #ifdef TS_USE_TMA
-                            b = tile_search(&cfg[level], x.x, x.y, x.z, level ? r : ccell, pending, buf, lane, level == 1 && it >= 4, bar_w, &parity TS_TM_PASS);
+                        b = tile_search(&cfg[level], x.x, x.y, x.z, level ? r : ccell, pending, buf, lane, level == 1 && it >= 4, bar_w, &parity TS_TM_PASS);
 #else
-                            b = tile_search(&cfg[level], x.x, x.y, x.z, level ? r : ccell, pending, buf, lane, level == 1 && it >= 4 TS_TM_PASS);
+                        b = tile_search(&cfg[level], x.x, x.y, x.z, level ? r : ccell, pending, buf, lane, level == 1 && it >= 4 TS_TM_PASS);
 #endif
-                            if (level == 0 && pending && b.bd < INFINITY) r = sqrtf(b.bd) * 1.00001f + slack;
-                        }
-                        if (pending) {
-                            float4 qw = b.bq;
-                            const float d2q = b.bd;
-                            if (!(b.bd < INFINITY)) qw.w = __int_as_float(-1);      // nothing within reach
-                            float4 nv = make_float4(0.f, 0.f, 0.f, 1.f);
-                            if (EST == S3D_ESTIMATOR_POINT_TO_PLANE && __float_as_int(qw.w) >= 0) nv = __ldg(&d.tgt_nrm[__float_as_int(qw.w)]);
-                            const bool tie = b.lb3 > 0.f;
-                            const unsigned f = (unsigned)(it & 63) | (tie ? PS_FLAG_TIE : 0u) | (nv.w != 0.f ? PS_FLAG_NRM : 0u);
-                            my_cq[i] = qw;
-                            my_cn[i] = make_float4(nv.x, nv.y, nv.z, tie ? b.lb3 : b.lb);
-                            my_fl[i] = (uint8_t)f;
-                            if (tie) my_cq2[i] = b.q2;                             // near tie: keep the runner-up too
-                            const bool ok = (__float_as_int(qw.w) >= 0) && (d2q <= a.max_d2) && (nv.w != 0.f);
-                            if (ok) { accumulate_fx<EST>(acc, M, x.x, x.y, x.z, qw, nv, d2q); ++cnt; }
-                            if (last && a.nn_out) a.nn_out[i] = ok ? __float_as_int(qw.w) : -1;
-                        }
-                        PS_HAND_OVER();
-                        e_cur = e_nxt; ent_cur = ent_nxt; p = pn; q = qn;
-                        e_nxt = e_n2; ent_nxt = ent_n2;
+                        if (level == 0 && pending && b.bd < INFINITY) r = sqrtf(b.bd) * 1.00001f + slack;
                     }
+                    if (pending) {
+                        q = b.bq;
+                        const float d2q = b.bd;
+                        if (!(b.bd < INFINITY)) q.w = __int_as_float(-1);      // nothing within reach
+                        float4 nv = make_float4(0.f, 0.f, 0.f, 1.f);
+                        if (EST == S3D_ESTIMATOR_POINT_TO_PLANE && __float_as_int(q.w) >= 0) nv = __ldg(&d.tgt_nrm[__float_as_int(q.w)]);
+                        const bool tie = b.lb3 > 0.f;
+                        const unsigned f = (unsigned)(it & 63) | (tie ? PS_FLAG_TIE : 0u) | (nv.w != 0.f ? PS_FLAG_NRM : 0u);
+                        my_cq[i] = q;
+                        my_cn[i] = make_float4(nv.x, nv.y, nv.z, tie ? b.lb3 : b.lb);
+                        my_fl[i] = (uint8_t)f;
+                        if (tie) my_cq2[i] = b.q2;                             // near tie: keep the runner-up too
+                        const bool ok = (__float_as_int(q.w) >= 0) && (d2q <= a.max_d2) && (nv.w != 0.f);
+                        if (ok) { accumulate_fx<EST>(acc, M, x.x, x.y, x.z, q, nv, d2q); ++cnt; }
+                        if (last && a.nn_out) a.nn_out[i] = ok ? __float_as_int(q.w) : -1;
+                    }
+                    PS_HAND_OVER();
                 }
             }
             PHASE(9);
@@ -968,11 +953,15 @@ __global__ void __launch_bounds__(TS_BLOCK, 1) icp_persist_kernel(const PersistA
                 if (warp == 0) {
                     if (lane == 0) {
                         // release (the CTA's atomics, issued by other threads before the __syncthreads above) -> arrive -> wait -> acquire
+#ifdef PS_BARRIER_FENCES
                         __threadfence();
+#endif
                         red_release_add_u32(bar, 1u);
                         const unsigned target = epoch * (unsigned)a.group_ctas;
                         while (ld_acquire_u32(bar) < target) { }
+#ifdef PS_BARRIER_FENCES
                         __threadfence();
+#endif
                     }
                     __syncwarp();
                     PHASE(10);
@@ -996,7 +985,7 @@ __global__ void __launch_bounds__(TS_BLOCK, 1) icp_persist_kernel(const PersistA
                 solve_and_update<EST>(total, &st, a.min_corr, a.pivot_eps);
                 fxs = s3d_fx_make(s3d_icp_bound(*d.src_absmax, *d.tgt_absmax, EST == S3D_ESTIMATOR_POINT_TO_PLANE ? d.tgt_absmax[1] : 1.0f, st.T));
                 #pragma unroll
-                for (int k = 0; k < 12; ++k) hist[(it + 1) & (PS_HIST - 1)][k] = st.Tf[k];
+                for (int k = 0; k < 3; ++k) hist[(it + 1) & (PS_HIST - 1)][k] = make_float4(st.Tf[4 * k], st.Tf[4 * k + 1], st.Tf[4 * k + 2], st.Tf[4 * k + 3]);
                 pend_count = 0; pend_next = 0;
             }
             __syncthreads();

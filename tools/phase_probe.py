@@ -1,4 +1,5 @@
-"""Scratch: per-iteration phase times of CTA 0 (S3D_PHASES build): runs k and k+10 iterations, prints the per-iteration delta."""
+"""Per-iteration phase times of CTA 0 (S3D_PHASES build, S3D_LIBRARY=...phases.so): runs k and k+10 iterations and prints the
+per-iteration delta of every phase: pass 1 (streaming), pass 2 (search), barrier (atomics + arrive + wait), totals, solve."""
 import sys, os, ctypes as C
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -14,7 +15,11 @@ def run(k):
     ctx.register(src, tgt, None, _abi.icp_params(k))
     lib.s3d_debug_stats(buf, 1)
     return np.array(list(buf), dtype=np.float64)
+prev = np.zeros(32)
+for k in (1, 2, 3, 4, 6, 10, 20, 30):
+    cur = run(k)
+    names = {8: "pass1", 9: "pass2", 10: "barrier", 11: "totals", 12: "solve"}
+    print(f"iterations {k:2d}: cumulative us " + " ".join(f"{names[i]}={cur[i] / 1965.0:8.1f}" for i in sorted(names)), flush=True)
 a, b = run(20), run(30)
 d = (b - a) / 10 / 1965.0
-print(f"late iteration (avg of 20..29), CTA 0, us: chunks(warp0)={d[8]:.2f} reduce={d[9]:.2f} barrier={d[10]:.2f} rowsum={d[11]:.2f} solve={d[12]:.2f} "
-      f"| warp loop mean={d[17]/16:.2f} | searches/iter={(b[19]-a[19])/10:.1f} search us each={(b[18]-a[18])/max(1,(b[19]-a[19]))/1965:.2f}")
+print("late iteration (avg of 20..29), CTA 0, us: " + " ".join(f"{n}={d[i]:.2f}" for i, n in ((8, "pass1"), (9, "pass2"), (10, "barrier"), (11, "totals"), (12, "solve"))))
