@@ -602,7 +602,7 @@ static_assert(TS_CAP * 16 >= 29 * 33 * 8, "the warp tile also carries the transp
 #define PS_CHUNK_BYTES 1600u                        // one staged chunk of 32 queries: point, correspondence, normal+bound (3 x 512 B), 32 flag bytes, padding
 #define PS_STAGE ((TS_CAP * 16) / PS_CHUNK_BYTES)   // chunks a warp's tile stages at a time (6)
 #ifndef PS_P1_UNROLL
-#define PS_P1_UNROLL 1
+#define PS_P1_UNROLL 1                               // chunks of the streaming pass in flight per warp (instruction-level parallelism)
 #endif
 #define PS_HIST 64                                  // poses kept (ring): a query's position at its last search is recomputed from them
 #define PS_REBASE_AGE 48                            // a kept query is re-based onto the current pose before its ring slot is reused
@@ -794,7 +794,8 @@ __global__ void __launch_bounds__(TS_BLOCK, 1) icp_persist_kernel(const PersistA
                     if (c0 != warp) PS_STAGE_ROUND(c0);       // (the first round was issued before the previous iteration's barrier)
                     ts_cp_async_wait_all();
                     __syncwarp();
-                    #pragma unroll PS_P1_UNROLL
+                    constexpr int p1_unroll = PS_P1_UNROLL;
+                    #pragma unroll p1_unroll
                     for (int s = 0; s < PS_STAGE; ++s) {
                         const int m = 4 * (c0 + s * TS_WARPS) + (lane >> 3);
                         if (4 * (c0 + s * TS_WARPS) >= cta_units) break;                                  // warp-uniform
