@@ -679,6 +679,7 @@ __global__ void __launch_bounds__(TS_BLOCK, 1) icp_persist_kernel(const PersistA
     __shared__ FxScale fxs;                                       // resolution of this iteration's sums (from the pose and the data bounds)
     __shared__ TileCfg cfg[2];                                    // search levels of the current pair: [0] decimated grid, [1] full grid
     __shared__ int pend_count, pend_next;                         // pending list of this CTA: entries appended / handed out
+    __shared__ int full_next;                                     // the next iteration skips the streaming pass (big pose update)
 #ifdef TS_USE_TMA
     __shared__ __align__(8) uint64_t tile_bar[TS_WARPS];         // one mbarrier per warp: completion of its TMA row copies
 #endif
@@ -708,7 +709,7 @@ __global__ void __launch_bounds__(TS_BLOCK, 1) icp_persist_kernel(const PersistA
         if (threadIdx.x == 0) {
             st = a.states[pair];
             fxs = s3d_fx_make(s3d_icp_bound(*d.src_absmax, *d.tgt_absmax, EST == S3D_ESTIMATOR_POINT_TO_PLANE ? d.tgt_absmax[1] : 1.0f, st.T));
-            pend_count = 0; pend_next = 0;
+            pend_count = 0; pend_next = 0; full_next = 1;
             cfg[1].gp = *d.grid; cfg[1].cell_start = d.cell_start; cfg[1].pts = d.sorted_pts;
             cfg[1].slack = a.slack_cells * cfg[1].gp.cell; cfg[1].gate_r = gate_r;
             cfg[0] = cfg[1];
@@ -788,7 +789,13 @@ __global__ void __launch_bounds__(TS_BLOCK, 1) icp_persist_kernel(const PersistA
             } while (0)
 
             // ---------------------------------------------------------------- pass 1: streaming skip test + accumulate
-            if (it > 0) {
+            // After a big pose update (the iterations right after the first) practically every query fails the skip test: when
+            // the last update can have moved a source point by more than a quarter of a cell (decided after the solve, the same
+            // in every CTA) the streaming pass is skipped and every octet goes to the search pass (searching a query that would
+            // have passed returns the same exact answer).
+            const bool full_search = it == 0 || full_next;
+            if (full_search) { ts_cp_async_wait_all(); __syncwarp(); }      // a staging round issued ahead for nothing: the tile is the search's now
+            if (!full_search) {
                 int since = 0;
                 for (int c0 = warp; c0 < cta_chunks; c0 += TS_WARPS * PS_STAGE) {
                     if (c0 != warp) PS_STAGE_ROUND(c0);       // (the first round was issued before the previous iteration's barrier)
@@ -876,7 +883,7 @@ __global__ void __launch_bounds__(TS_BLOCK, 1) icp_persist_kernel(const PersistA
             // ---------------------------------------------------------------- pass 2: search what is pending
             // Warps take items (item_octets octets, one per 8 lanes) from the CTA's list until it is empty.
             {
-                const int n_items = it == 0 ? cta_units : pend_count;
+                const int n_items = full_search ? cta_units : pend_count;
                 while (n_items > 0) {
                     int e0 = 0;
                     if (lane == 0) e0 = atomicAdd(&pend_next, a.item_octets);
@@ -884,7 +891,7 @@ __global__ void __launch_bounds__(TS_BLOCK, 1) icp_persist_kernel(const PersistA
                     if (e0 >= n_items) break;
                     const int e = e0 + (lane >> 3);
                     uint32_t ent = 0u;
-                    if (e < n_items && lane < 8 * a.item_octets) ent = it == 0 ? (((uint32_t)e << 8) | 0xffu) : __ldcg(&my_pend[e]);
+                    if (e < n_items && lane < 8 * a.item_octets) ent = full_search ? (((uint32_t)e << 8) | 0xffu) : __ldcg(&my_pend[e]);
                     const int m = (int)(ent >> 8);
                     const int i = ((rank + a.group_ctas * m) << 3) + (lane & 7);
                     const bool pending = ((ent >> (lane & 7)) & 1u) && i < d.n_src;
@@ -943,6 +950,9 @@ __global__ void __launch_bounds__(TS_BLOCK, 1) icp_persist_kernel(const PersistA
             __syncthreads();
             // The per-query state of the next iteration is final (pass 2 wrote it) and does not depend on the pose: its first
             // staging round is issued now, so that its latency is hidden behind the barrier and the solve.
+            // The per-query state of the next iteration is final (pass 2 wrote it) and does not depend on the pose: the first staging
+            // round of its streaming pass is issued now, so that its latency hides behind the barrier and the solve.  (Should the next
+            // iteration skip the streaming pass after all, the copies are simply drained.)
             if (!last && warp < cta_chunks) PS_STAGE_ROUND(warp);
             if (a.group_ctas > 1) {
                 // the CTA's sums go to the group's accumulators (red.add.u64: integers, order free); then arrive at the barrier
@@ -991,6 +1001,15 @@ __global__ void __launch_bounds__(TS_BLOCK, 1) icp_persist_kernel(const PersistA
                 #pragma unroll
                 for (int k = 0; k < 3; ++k) hist[(it + 1) & (PS_HIST - 1)][k] = make_float4(st.Tf[4 * k], st.Tf[4 * k + 1], st.Tf[4 * k + 2], st.Tf[4 * k + 3]);
                 pend_count = 0; pend_next = 0;
+                // can the update have moved a source point by more than a quarter of a cell?  |dR| * 3 P + |dt| bounds the motion
+                float dr = 0.f, dt = 0.f;
+                #pragma unroll
+                for (int r = 0; r < 3; ++r) {
+                    #pragma unroll
+                    for (int c = 0; c < 3; ++c) dr = fmaxf(dr, fabsf(st.Tf[4 * r + c] - st.Tf_prev[4 * r + c]));
+                    dt = fmaxf(dt, fabsf(st.Tf[4 * r + 3] - st.Tf_prev[4 * r + 3]));
+                }
+                full_next = (3.f * dr * (*d.src_absmax) + dt > 0.25f * cell) ? 1 : 0;
             }
             __syncthreads();
             PHASE(12);
