@@ -884,14 +884,16 @@ __global__ void __launch_bounds__(TS_BLOCK, 1) icp_persist_kernel(const PersistA
             // Warps take items (item_octets octets, one per 8 lanes) from the CTA's list until it is empty.
             {
                 const int n_items = full_search ? cta_units : pend_count;
+                // few octets left (late iterations): one per item, so that a lone search is not queued behind another one
+                const int item = n_items <= 2 * TS_WARPS ? 1 : a.item_octets;
                 while (n_items > 0) {
                     int e0 = 0;
-                    if (lane == 0) e0 = atomicAdd(&pend_next, a.item_octets);
+                    if (lane == 0) e0 = atomicAdd(&pend_next, item);
                     e0 = __shfl_sync(full, e0, 0);
                     if (e0 >= n_items) break;
                     const int e = e0 + (lane >> 3);
                     uint32_t ent = 0u;
-                    if (e < n_items && lane < 8 * a.item_octets) ent = full_search ? (((uint32_t)e << 8) | 0xffu) : __ldcg(&my_pend[e]);
+                    if (e < n_items && lane < 8 * item) ent = full_search ? (((uint32_t)e << 8) | 0xffu) : __ldcg(&my_pend[e]);
                     const int m = (int)(ent >> 8);
                     const int i = ((rank + a.group_ctas * m) << 3) + (lane & 7);
                     const bool pending = ((ent >> (lane & 7)) & 1u) && i < d.n_src;

@@ -8,12 +8,13 @@ cam = synth.Camera().scaled(0.25)
 p = synth.make_pair(0, cam=cam, quantize=True, holes=0.1)
 ctx = s3d.Context(0)
 src = ctx.upload(p["src"]); tgt = ctx.upload(p["tgt"], p["tgt_normals"])
-for mode in (_abi.SEARCH_GRID, _abi.SEARCH_GRID_LANE):
+for mode in (_abi.SEARCH_GRID, _abi.SEARCH_GRID_LANE, _abi.SEARCH_BRUTE):
     r = ctx.register(src, tgt, None, _abi.icp_params(8, search=mode, reuse_index=0))
     print("mode", mode, r["status"], r["inliers"])
 r = ctx.register(src, tgt, None, _abi.icp_params(6, max_corr_dist=0.05, estimator=_abi.ESTIMATOR_SVD))
 print("svd gate", r["status"], r["inliers"])
 res = ctx.register_batch([src] * 5, [tgt] * 5, None, _abi.icp_params(5))
+res = ctx.register_batch([src] * 160, [tgt] * 160, None, _abi.icp_params(3))      # more pairs than CTAs: one CTA per pair, groups walk the list
 print("batch", [x["status"] for x in res])
 t2 = ctx.from_depth_normals(p["tgt_depth"], cam, 3.5, 1, 0.08)
 print("planes", len(t2.segment_planes(_abi.plane_params())))
