@@ -335,14 +335,9 @@ __device__ __noinline__ TileOut tile_search(const TileCfg *cfg, float px, float 
                     cnt = __ldg(&cell_start[base + hix + 1]) - rs;
                     yz = ((uint32_t)(yi & 63) << 20) | ((uint32_t)(zi & 63) << 26);
                     if (!whole) {
-                        // row-relative index of the first point of every cell of the row inside the box: all loads first (in
-                        // flight together), then the stores
+                        // row-relative index of the first point of every cell of the row inside the box
                         const uint32_t row = mt.cs + 2u * (uint32_t)(lane * (TS_NXMAX + 2));
-                        uint32_t bnd[TS_NXMAX];
-                        #pragma unroll
-                        for (int k = 1; k < TS_NXMAX; ++k) bnd[k] = k < nx_s ? __ldg(&cell_start[base + lox + k]) : 0u;
-                        #pragma unroll
-                        for (int k = 1; k < TS_NXMAX; ++k) if (k < nx_s) ts_sts_u16(row + 2u * (uint32_t)k, bnd[k] - rs);
+                        for (int k = 1; k < nx_s; ++k) ts_sts_u16(row + 2u * (uint32_t)k, __ldg(&cell_start[base + lox + k]) - rs);
                         ts_sts_u16(row, 0u); ts_sts_u16(row + 2u * (uint32_t)nx_s, cnt);
                     }
                     STAT(2, 1);
@@ -387,7 +382,7 @@ __device__ __noinline__ TileOut tile_search(const TileCfg *cfg, float px, float 
             // this row's part of the tile: offset, points copied, first copied point (row-relative)
             {
                 const uint32_t yz = ts_lds_u32(mt.info + 4u * (uint32_t)lane) & 0xfff00000u;
-                ts_sts_u32(mt.info + 4u * (uint32_t)lane, yz | (take > 0u ? ((uint32_t)fill + excl) | (take << 10) : 0u));
+                ts_sts_u32(mt.info + 4u * (uint32_t)lane, yz | ((uint32_t)fill + excl) | (take << 10));
                 ts_sts_u16(mt.first + 2u * (uint32_t)lane, done);
             }
             rs += take; cnt -= take; done += take;
