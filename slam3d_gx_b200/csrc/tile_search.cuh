@@ -41,16 +41,6 @@
 #endif
 #define TS_GROUP 8            // queries per box: an aligned octet of lanes
 #define TS_MAX_TRIES 64
-// Per-query sub-ranges.  The rows of the group's box are gathered once, but a query only has to look at the cells of its
-// OWN ball: consecutive source points lie along a scan line, so the union box of an octet is several times longer (in x)
-// than any one ball, and comparing every query with every candidate of the union was the largest single cost of a pass.
-// For each gathered row the cell boundaries inside the box are kept (row-relative point indices, 16 bit) next to the
-// candidates; a query's lanes walk the rows of its own (y,z) range and, inside a row, the points of its own cell range.
-// The metadata lives at the end of the warp's tile: TS_META_ROWS rows (one gather round) x (TS_NXMAX + 2) boundaries.
-#define TS_NXMAX 22           // widest box (cells along x) sub-ranges are kept for; wider boxes are scanned whole
-#define TS_META_ROWS 32
-#define TS_META_BYTES (TS_META_ROWS * ((TS_NXMAX + 2) * 2 + 4 + 2) + 64)
-#define TS_CAND ((TS_CAP * 16 - TS_META_BYTES) / 16)      // candidates a tile holds beside the metadata
 
 #if defined(S3D_PHASES)
 #define TS_TM_ARG , long long *tm
@@ -139,56 +129,44 @@ __device__ __forceinline__ void tile_best_merge(TileBest &a, const float4 obq, f
     if (better) { a.bd = obd; a.bq = obq; }
 }
 
-// One lane's share of the candidates against the query (qx,qy,qz); result merged into W.
-//   whole == true : candidates sub, sub + step, ... < fill of the tile (the group's box is scanned whole)
-//   whole == false: rows sub, sub + step, ... of the current gather round; of each row only the points whose cell lies in the
-//                   query's own cell range [qx0, qx1] x [qy0, qy1] x [qz0, qz1] (relative to the box origin)
+// One lane's share of the tile: candidates sub, sub+step, ... < m against the query (qx,qy,qz); result merged into W.
 // EXCL: the candidate whose original index is `excl` is left out (second pass that looks for the runner-up).
-struct TileMeta {             // views into the metadata region of a warp's tile (shared-memory addresses)
-    uint32_t cs;              // uint16 cs[TS_META_ROWS][TS_NXMAX + 2]: row-relative index of the first point of every cell of the row
-    uint32_t info;            // uint32 info[TS_META_ROWS]: tile offset (10 bits) | points copied (10) | y offset (6) | z offset (6)
-    uint32_t first;           // uint16 first[TS_META_ROWS]: row-relative index of the first point of the row that is in the tile
-};
-__device__ __forceinline__ uint32_t ts_lds_u16(uint32_t saddr) { uint32_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(saddr)); return v; }
-__device__ __forceinline__ uint32_t ts_lds_u32(uint32_t saddr) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr)); return v; }
-__device__ __forceinline__ void ts_sts_u16(uint32_t saddr, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(saddr), "r"(v) : "memory"); }
-__device__ __forceinline__ void ts_sts_u32(uint32_t saddr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory"); }
-
 #define TS_D2(c) (EXCL && __float_as_int((c).w) == excl ? INFINITY : s3d_dist2(qx, qy, qz, (c).x, (c).y, (c).z))
-// running nearest / runner-up over one more candidate at tile index k_ (two independent chains: 0 and 1)
-#define TS_VISIT(chain, k_) do {                                                                       \
-        const float4 c_ = ts_lds128(sbuf + 16u * (uint32_t)(k_));                                      \
-        const float d_ = TS_D2(c_);                                                                    \
-        const bool l_ = d_ < pd##chain;                                                                \
-        ps##chain = fminf(ps##chain, fmaxf(pd##chain, d_)); pd##chain = fminf(pd##chain, d_);          \
-        pk##chain = l_ ? (int)(k_) : pk##chain;                                                        \
-    } while (0)
-
 template <bool EXCL>
-__device__ __forceinline__ void tile_compare_pass(uint32_t sbuf, const TileMeta mt, bool whole, int fill, int nrows, int sub, int step,
-                                                  float qx, float qy, float qz, int qx0, int qx1, int qy0, int qy1, int qz0, int qz1,
-                                                  TileBest &W, int excl)
+__device__ __forceinline__ void tile_compare_pass(uint32_t sbuf, int m, int sub, int step,
+                                                  float qx, float qy, float qz, TileBest &W, int excl)
 {
+    // two independent running minima (even / odd visits) halve the dependent chain
     float pd0 = INFINITY, ps0 = INFINITY, pd1 = INFINITY, ps1 = INFINITY;
     int pk0 = -1, pk1 = -1;
-    if (whole) {
-        int k = sub;
-        for (; k + step < fill; k += 2 * step) { TS_VISIT(0, k); TS_VISIT(1, k + step); }
-        if (k < fill) TS_VISIT(0, k);
-    } else {
-        for (int t = sub; t < nrows; t += step) {
-            const uint32_t info = ts_lds_u32(mt.info + 4u * (uint32_t)t);
-            const int n = (int)((info >> 10) & 1023u), yi = (int)((info >> 20) & 63u), zi = (int)(info >> 26);
-            if (n == 0 || yi < qy0 || yi > qy1 || zi < qz0 || zi > qz1) continue;
-            const uint32_t row = mt.cs + 2u * (uint32_t)(t * (TS_NXMAX + 2));
-            const int first = (int)ts_lds_u16(mt.first + 2u * (uint32_t)t);
-            int a = (int)ts_lds_u16(row + 2u * (uint32_t)qx0), b = (int)ts_lds_u16(row + 2u * (uint32_t)(qx1 + 1));
-            a = max(a, first); b = min(b, first + n);
-            int k = (int)(info & 1023u) + (a - first);
-            const int ke = (int)(info & 1023u) + (b - first);
-            for (; k + 1 < ke; k += 2) { TS_VISIT(0, k); TS_VISIT(1, k + 1); }
-            if (k < ke) TS_VISIT(0, k);
-        }
+    int k = sub;
+    for (; k + 3 * step < m; k += 4 * step) {          // four candidates per turn, two per chain
+        const float4 a = ts_lds128(sbuf + 16u * (uint32_t)k), b = ts_lds128(sbuf + 16u * (uint32_t)(k + step));
+        const float4 c = ts_lds128(sbuf + 16u * (uint32_t)(k + 2 * step)), e = ts_lds128(sbuf + 16u * (uint32_t)(k + 3 * step));
+        const float da = TS_D2(a), db = TS_D2(b);
+        const float dc = TS_D2(c), de = TS_D2(e);
+        bool la = da < pd0, lbb = db < pd1;
+        ps0 = fminf(ps0, fmaxf(pd0, da)); ps1 = fminf(ps1, fmaxf(pd1, db));
+        pd0 = fminf(pd0, da); pd1 = fminf(pd1, db);
+        pk0 = la ? k : pk0; pk1 = lbb ? k + step : pk1;
+        la = dc < pd0; lbb = de < pd1;
+        ps0 = fminf(ps0, fmaxf(pd0, dc)); ps1 = fminf(ps1, fmaxf(pd1, de));
+        pd0 = fminf(pd0, dc); pd1 = fminf(pd1, de);
+        pk0 = la ? k + 2 * step : pk0; pk1 = lbb ? k + 3 * step : pk1;
+    }
+    for (; k + step < m; k += 2 * step) {
+        const float4 a = ts_lds128(sbuf + 16u * (uint32_t)k), b = ts_lds128(sbuf + 16u * (uint32_t)(k + step));
+        const float da = TS_D2(a), db = TS_D2(b);
+        const bool la = da < pd0, lbb = db < pd1;
+        ps0 = fminf(ps0, fmaxf(pd0, da)); ps1 = fminf(ps1, fmaxf(pd1, db));
+        pd0 = fminf(pd0, da); pd1 = fminf(pd1, db);
+        pk0 = la ? k : pk0; pk1 = lbb ? k + step : pk1;
+    }
+    if (k < m) {
+        const float4 a = ts_lds128(sbuf + 16u * (uint32_t)k);
+        const float da = TS_D2(a);
+        const bool la = da < pd0;
+        ps0 = fminf(ps0, fmaxf(pd0, da)); pd0 = fminf(pd0, da); pk0 = la ? k : pk0;
     }
     // combine the two chains: nearest, runner-up, and whether the minimum is attained more than once
     const float pd = fminf(pd0, pd1);
@@ -198,20 +176,11 @@ __device__ __forceinline__ void tile_compare_pass(uint32_t sbuf, const TileMeta 
     if (ps == pd) {
         // equal distances: the lowest original index wins (rare; rescan this lane's share)
         int bi = INT_MAX;
-#define TS_RESCAN(k_) do { const float4 q_ = ts_lds128(sbuf + 16u * (uint32_t)(k_)); const float d2_ = TS_D2(q_); const int qi_ = __float_as_int(q_.w); \
-                           if (d2_ == pd && qi_ < bi) { bi = qi_; pk = (int)(k_); } } while (0)
-        if (whole) { for (int kk = sub; kk < fill; kk += step) TS_RESCAN(kk); }
-        else {
-            for (int t = sub; t < nrows; t += step) {
-                const uint32_t info = ts_lds_u32(mt.info + 4u * (uint32_t)t);
-                const int n = (int)((info >> 10) & 1023u), yi = (int)((info >> 20) & 63u), zi = (int)(info >> 26);
-                if (n == 0 || yi < qy0 || yi > qy1 || zi < qz0 || zi > qz1) continue;
-                const uint32_t row = mt.cs + 2u * (uint32_t)(t * (TS_NXMAX + 2));
-                const int first = (int)ts_lds_u16(mt.first + 2u * (uint32_t)t);
-                int a = (int)ts_lds_u16(row + 2u * (uint32_t)qx0), b = (int)ts_lds_u16(row + 2u * (uint32_t)(qx1 + 1));
-                a = max(a, first); b = min(b, first + n);
-                for (int kk = (int)(info & 1023u) + (a - first); kk < (int)(info & 1023u) + (b - first); ++kk) TS_RESCAN(kk);
-            }
+        for (int kk = sub; kk < m; kk += step) {
+            const float4 q = ts_lds128(sbuf + 16u * (uint32_t)kk);
+            const float d2 = TS_D2(q);
+            const int qi = __float_as_int(q.w);
+            if (d2 == pd && qi < bi) { bi = qi; pk = kk; }
         }
     }
     tile_best_merge(W, ts_lds128(sbuf + 16u * (uint32_t)pk), pd, ps);
@@ -276,7 +245,7 @@ __device__ __noinline__ TileOut tile_search(const TileCfg *cfg, float px, float 
         const bool inbox = ingrp && r <= thr;
         const unsigned inmask = __ballot_sync(full, inbox);
         const int nin = __popc(inmask);
-        // ---- the box: union of the balls of the group; every query also keeps its own cell box ----
+        // ---- the box: union of the balls of the group ----
         int lox = INT_MAX, loy = INT_MAX, loz = INT_MAX, hix = INT_MIN, hiy = INT_MIN, hiz = INT_MIN;
         if (inbox) {
             const float Rc = r * gp.inv_cell * 1.00001f + GRID_MARGIN;
@@ -284,67 +253,39 @@ __device__ __noinline__ TileOut tile_search(const TileCfg *cfg, float px, float 
             loy = min(max(__float2int_rd(fy - Rc), 0), gp.ny - 1); hiy = min(max(__float2int_rd(fy + Rc), 0), gp.ny - 1);
             loz = min(max(__float2int_rd(fz - Rc), 0), gp.nz - 1); hiz = min(max(__float2int_rd(fz + Rc), 0), gp.nz - 1);
         }
-        int olox = lox, ohix = hix, oloy = loy, ohiy = hiy, oloz = loz, ohiz = hiz;       // this lane's own box (valid if inbox)
         lox = __reduce_min_sync(full, lox); loy = __reduce_min_sync(full, loy); loz = __reduce_min_sync(full, loz);
         hix = __reduce_max_sync(full, hix); hiy = __reduce_max_sync(full, hiy); hiz = __reduce_max_sync(full, hiz);
-        if (tries >= TS_MAX_TRIES) {          // safety net: whole grid
-            lox = loy = loz = 0; hix = gp.nx - 1; hiy = gp.ny - 1; hiz = gp.nz - 1;
-            olox = oloy = oloz = 0; ohix = hix; ohiy = hiy; ohiz = hiz;
-        }
-        const int nx_s = hix - lox + 1, ny_s = hiy - loy + 1, nz_s = hiz - loz + 1;
+        if (tries >= TS_MAX_TRIES) { lox = loy = loz = 0; hix = gp.nx - 1; hiy = gp.ny - 1; hiz = gp.nz - 1; }   // safety net: whole grid
+        const int ny_s = hiy - loy + 1, nz_s = hiz - loz + 1;
         const int rows = gp.n_points > 0 ? ny_s * nz_s : 0;
-        // per-query sub-ranges only pay (and only fit their metadata) for several queries in a box of moderate size
-        bool whole = nin <= 1 || nx_s > TS_NXMAX || ny_s > 64 || nz_s > 64;
         // ---- work split: NS query slots (power of two >= nin), 32/NS lanes per slot ----
         const int lgNS = nin > 1 ? 32 - __clz(nin - 1) : 0;             // NS = 1 << lgNS
         const int NS = 1 << lgNS, step = 32 >> lgNS, slot = lane & (NS - 1), sub = lane >> lgNS;
         const int src = (slot < nin) ? (int)__fns(inmask, 0, slot + 1) : 0;
         const float qx = __shfl_sync(full, px, src), qy = __shfl_sync(full, py, src), qz = __shfl_sync(full, pz, src);
-        // the slot's query's own box, relative to the group's box (6 small numbers in two shuffles)
-        const int own_a = (olox - lox) | ((ohix - lox) << 8) | ((oloy - loy) << 16) | ((ohiy - loy) << 24);
-        const int own_b = (oloz - loz) | ((ohiz - loz) << 8);
-        const int sa = __shfl_sync(full, whole ? 0 : own_a, src), sb = __shfl_sync(full, whole ? 0 : own_b, src);
-        const int qx0 = sa & 255, qx1 = (sa >> 8) & 255, qy0 = (sa >> 16) & 255, qy1 = (sa >> 24) & 255, qz0 = sb & 255, qz1 = (sb >> 8) & 255;
         const bool work = slot < nin;
         TileBest W; tile_best_init(W);
-        TileMeta mt;
-        mt.cs = sbuf + 16u * (uint32_t)TS_CAND;
-        mt.info = mt.cs + 2u * (uint32_t)(TS_META_ROWS * (TS_NXMAX + 2));
-        mt.first = mt.info + 4u * (uint32_t)TS_META_ROWS;
         STAT(5, lane == 0);
         TS_CNT(27, rows); TS_CNT(28, 1); TS_CNT(29, nin);
         TS_T(0);
-        // ---- gather the rows into the tile by TMA, 32 rows per round (one per lane), compare after every round ----
-        // Two cell-start loads give a row's point range (with sub-ranges: one load per cell boundary of the row), one bulk
-        // copy moves it.  What does not fit into the tile stays with its lane for the next turn (`carry`): rows of any length
-        // go through.
-        int fill = 0, t0 = 0, nfills = 0, last_fill = 0, last_rows = 0;
-        uint32_t rs = 0u, cnt = 0u, done = 0u;
+        // ---- gather the rows into the tile by TMA, compare whenever it is full ----
+        // 32 rows per round (one per lane): two cell-start loads give the row's point range, one bulk copy moves it.
+        // What does not fit into the tile stays with its lane for the next turn (`carry`): rows of any length go through.
+        int fill = 0, t0 = 0, nfills = 0, last_fill = 0;
+        uint32_t rs = 0u, cnt = 0u;
         bool carry = false;
         while (carry || t0 < rows) {
             if (!carry) {
                 const int t = t0 + lane;
-                rs = 0u; cnt = 0u; done = 0u;
-                uint32_t yz = 0u;
+                rs = 0u; cnt = 0u;
                 if (t < rows) {
                     // t / ny_s without an integer division (t < 2^22, exact in float with the half-step offset)
                     const int zi = __float2int_rz(__fdividef((float)t + 0.5f, (float)ny_s));
-                    const int yi = t - zi * ny_s;
-                    const size_t base = ((size_t)(loz + zi) * gp.ny + (loy + yi)) * gp.nx;
+                    const size_t base = ((size_t)(loz + zi) * gp.ny + (loy + (t - zi * ny_s))) * gp.nx;
                     rs = __ldg(&cell_start[base + lox]);
                     cnt = __ldg(&cell_start[base + hix + 1]) - rs;
-                    yz = ((uint32_t)(yi & 63) << 20) | ((uint32_t)(zi & 63) << 26);
-                    if (!whole) {
-                        // row-relative index of the first point of every cell of the row inside the box
-                        const uint32_t row = mt.cs + 2u * (uint32_t)(lane * (TS_NXMAX + 2));
-                        for (int k = 1; k < nx_s; ++k) ts_sts_u16(row + 2u * (uint32_t)k, __ldg(&cell_start[base + lox + k]) - rs);
-                        ts_sts_u16(row, 0u); ts_sts_u16(row + 2u * (uint32_t)nx_s, cnt);
-                    }
                     STAT(2, 1);
                 }
-                // a row too long for 16-bit boundaries: this pass scans whole (every candidate set stays a superset)
-                if (__any_sync(full, cnt > 65535u)) whole = true;
-                ts_sts_u32(mt.info + 4u * (uint32_t)lane, yz);         // (offset and count are filled in below)
                 t0 += 32;
             }
             TS_T(1);
@@ -355,7 +296,7 @@ __device__ __noinline__ TileOut tile_search(const TileCfg *cfg, float px, float 
                 if (lane >= o) incl += v;
             }
             const uint32_t total = __shfl_sync(full, incl, 31), excl = incl - cnt;
-            const uint32_t room = (uint32_t)(TS_CAND - fill);
+            const uint32_t room = (uint32_t)(TS_CAP - fill);
             uint32_t take = cnt;
             if (total > room) take = excl >= room ? 0u : min(cnt, room - excl);
             const uint32_t moved_pts = min(total, room);
@@ -379,27 +320,21 @@ __device__ __noinline__ TileOut tile_search(const TileCfg *cfg, float px, float 
                 }
             }
 #endif
-            // this row's part of the tile: offset, points copied, first copied point (row-relative)
-            {
-                const uint32_t yz = ts_lds_u32(mt.info + 4u * (uint32_t)lane) & 0xfff00000u;
-                ts_sts_u32(mt.info + 4u * (uint32_t)lane, yz | ((uint32_t)fill + excl) | (take << 10));
-                ts_sts_u16(mt.first + 2u * (uint32_t)lane, done);
-            }
-            rs += take; cnt -= take; done += take;
+            rs += take; cnt -= take;
             TS_T(2);
             carry = total > room;
             fill += (int)moved_pts;
-            if (fill > 0) {
+            if ((carry || t0 >= rows) && fill > 0) {
 #ifdef TS_USE_TMA
                 if (lane == 0) ts_mbar_arrive(bar);
                 ts_mbar_wait(bar, parity);
                 parity ^= 1u;
 #else
                 ts_cp_async_wait_all();
+                __syncwarp();
 #endif
-                __syncwarp();                                         // candidates and metadata of every lane are in place
-                if (work) tile_compare_pass<false>(sbuf, mt, whole, fill, 32, sub, step, qx, qy, qz, qx0, qx1, qy0, qy1, qz0, qz1, W, -1);
-                ++nfills; last_fill = fill; last_rows = 32;
+                if (work) tile_compare_pass<false>(sbuf, fill, sub, step, qx, qy, qz, W, -1);
+                ++nfills; last_fill = fill;
                 STAT(3, work ? fill / step : 0);
                 __syncwarp();
                 TS_CNT(26, fill);
@@ -407,7 +342,6 @@ __device__ __noinline__ TileOut tile_search(const TileCfg *cfg, float px, float 
                 TS_T(3);
             }
         }
-        (void)last_rows;
         // ---- merge the lanes of each slot, hand the result back to the query's lane ----
         for (int o = NS; o < 32; o <<= 1) {
             const float4 obq = make_float4(__shfl_xor_sync(full, W.bq.x, o), __shfl_xor_sync(full, W.bq.y, o),
@@ -420,19 +354,18 @@ __device__ __noinline__ TileOut tile_search(const TileCfg *cfg, float px, float 
         R.bq = make_float4(__shfl_sync(full, W.bq.x, myslot), __shfl_sync(full, W.bq.y, myslot),
                            __shfl_sync(full, W.bq.z, myslot), __shfl_sync(full, W.bq.w, myslot));
         R.bd = __shfl_sync(full, W.bd, myslot); R.sd = __shfl_sync(full, W.sd, myslot);
-        // ---- verify: every target point the query was not compared with lies outside its own cell box, i.e. at least `margin`
-        // away (distance to the nearest face of that box that is not a face of the whole grid) ----
+        // ---- verify: everything outside the box is at least `margin` away ----
         float mc = INFINITY;
-        if (olox > 0) mc = fminf(mc, fx - (float)olox);
-        if (ohix < gp.nx - 1) mc = fminf(mc, (float)(ohix + 1) - fx);
-        if (oloy > 0) mc = fminf(mc, fy - (float)oloy);
-        if (ohiy < gp.ny - 1) mc = fminf(mc, (float)(ohiy + 1) - fy);
-        if (oloz > 0) mc = fminf(mc, fz - (float)oloz);
-        if (ohiz < gp.nz - 1) mc = fminf(mc, (float)(ohiz + 1) - fz);
+        if (lox > 0) mc = fminf(mc, fx - (float)lox);
+        if (hix < gp.nx - 1) mc = fminf(mc, (float)(hix + 1) - fx);
+        if (loy > 0) mc = fminf(mc, fy - (float)loy);
+        if (hiy < gp.ny - 1) mc = fminf(mc, (float)(hiy + 1) - fy);
+        if (loz > 0) mc = fminf(mc, fz - (float)loz);
+        if (hiz < gp.nz - 1) mc = fminf(mc, (float)(hiz + 1) - fz);
         const float margin = fmaxf((mc - GRID_MARGIN) * gp.cell * 0.99999f, 0.f);     // INFINITY when the box is the whole grid
         if (inbox) {
-            const bool done_q = (R.bd <= margin * margin) || (margin >= gate_r) || !(mc < INFINITY);
-            if (done_q) {
+            const bool done = (R.bd <= margin * margin) || (margin >= gate_r) || !(mc < INFINITY);
+            if (done) {
                 B = R;
                 lbound = fmaxf(fminf(sqrtf(R.sd), margin) * 0.999998f - 5e-8f, 0.f);
                 todo = false;
@@ -454,7 +387,7 @@ __device__ __noinline__ TileOut tile_search(const TileCfg *cfg, float px, float 
             if (__any_sync(full, tie)) {
                 TileBest W2; tile_best_init(W2);
                 const int excl = __float_as_int(W.bq.w);           // the slot's winner (all lanes of a slot hold it)
-                if (work) tile_compare_pass<true>(sbuf, mt, whole, last_fill, 32, sub, step, qx, qy, qz, qx0, qx1, qy0, qy1, qz0, qz1, W2, excl);
+                if (work) tile_compare_pass<true>(sbuf, last_fill, sub, step, qx, qy, qz, W2, excl);
                 for (int o = NS; o < 32; o <<= 1) {
                     const float4 obq = make_float4(__shfl_xor_sync(full, W2.bq.x, o), __shfl_xor_sync(full, W2.bq.y, o),
                                                    __shfl_xor_sync(full, W2.bq.z, o), __shfl_xor_sync(full, W2.bq.w, o));
