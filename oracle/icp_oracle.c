@@ -331,11 +331,8 @@ int oracle_icp(const float *src, int n, const float *tgt, const float *tgt_nrm, 
             orc_xform(Tf, src[4 * i], src[4 * i + 1], src[4 * i + 2], xp + 3 * i);
             kd_query(tree, xp + 3 * i, &nn[i], &nd[i]);
         }
-        /* order-independent sums (oracle_common.h): 26-bit fixed-point factors, exact integer products, exact integer sums;
-         * the sum of squared distances keeps the fma rounding to 2^-g */
-        const double X = orc_pose_bound(absP, T);
-        const orc_fx fx = orc_fx_make(orc_icp_bound(X, absQ));
-        const orc_fxq fq = orc_fxq_make(X, absQ, est == S3D_ESTIMATOR_POINT_TO_PLANE ? absN : 1.0f, prm->max_corr_dist > 0 ? prm->max_corr_dist : INFINITY);
+        /* order-independent fixed-point sums (oracle_common.h): every product rounded once to 2^-g, integers added exactly */
+        const orc_fx fx = orc_fx_make(orc_icp_bound(absP, absQ, est == S3D_ESTIMATOR_POINT_TO_PLANE ? absN : 1.0f, T));
         __int128 SA[6][6], Sg[6], Sp[3], Sq[3], Spq[3][3], Sd2 = 0;
         memset(SA, 0, sizeof(SA)); memset(Sg, 0, sizeof(Sg)); memset(Sp, 0, sizeof(Sp)); memset(Sq, 0, sizeof(Sq)); memset(Spq, 0, sizeof(Spq));
         int cnt = 0;
@@ -355,32 +352,20 @@ int oracle_icp(const float *src, int n, const float *tgt, const float *tgt_nrm, 
                 J[3] = nv[0]; J[4] = nv[1]; J[5] = nv[2];
                 float ex = q[0] - p[0], ey = q[1] - p[1], ez = q[2] - p[2];
                 float r = fmaf(nv[2], ez, fmaf(nv[1], ey, nv[0] * ex));
-                int64_t qj[6];
-                for (int a = 0; a < 6; ++a) qj[a] = orc_fxq_q(J[a], a < 3 ? fq.fa : fq.fn);
-                const int64_t qr = orc_fxq_q(r, fq.fr);
                 for (int a = 0; a < 6; ++a) {
-                    for (int b = a; b < 6; ++b) SA[a][b] += qj[a] * qj[b];
-                    Sg[a] += qj[a] * qr;
+                    for (int b = a; b < 6; ++b) SA[a][b] += orc_fx_term(&fx, J[a], J[b]);
+                    Sg[a] += orc_fx_term(&fx, J[a], r);
                 }
             } else {
-                int64_t qp[3], qq[3];
-                for (int a = 0; a < 3; ++a) { qp[a] = orc_fxq_q(p[a], fq.fc); qq[a] = orc_fxq_q(q[a], fq.fc); }
                 for (int a = 0; a < 3; ++a) {
-                    Sp[a] += qp[a]; Sq[a] += qq[a];
-                    for (int b = 0; b < 3; ++b) Spq[a][b] += qp[a] * qq[b];
+                    Sp[a] += orc_fx_term(&fx, p[a], 1.0f); Sq[a] += orc_fx_term(&fx, q[a], 1.0f);
+                    for (int b = 0; b < 3; ++b) Spq[a][b] += orc_fx_term(&fx, p[a], q[b]);
                 }
             }
         }
         double A[6][6]; double g[6]; double sp[3], sq[3], spq[3][3];
-        for (int a = 0; a < 6; ++a) {
-            const int ea = a < 3 ? fq.sa : fq.sn;
-            for (int b = 0; b < 6; ++b) A[a][b] = orc_fxq_value(SA[a][b], ea + (b < 3 ? fq.sa : fq.sn));
-            g[a] = orc_fxq_value(Sg[a], ea + fq.sr);
-        }
-        for (int a = 0; a < 3; ++a) {
-            sp[a] = orc_fxq_value(Sp[a], fq.sc); sq[a] = orc_fxq_value(Sq[a], fq.sc);
-            for (int b = 0; b < 3; ++b) spq[a][b] = orc_fxq_value(Spq[a][b], 2 * fq.sc);
-        }
+        for (int a = 0; a < 6; ++a) { for (int b = 0; b < 6; ++b) A[a][b] = orc_fx_value(&fx, SA[a][b]); g[a] = orc_fx_value(&fx, Sg[a]); }
+        for (int a = 0; a < 3; ++a) { sp[a] = orc_fx_value(&fx, Sp[a]); sq[a] = orc_fx_value(&fx, Sq[a]); for (int b = 0; b < 3; ++b) spq[a][b] = orc_fx_value(&fx, Spq[a][b]); }
         const double sum_d2 = orc_fx_value(&fx, Sd2);
         res->inliers = cnt;
         res->fitness = cnt ? sum_d2 / (double)cnt : 0.0;

@@ -173,76 +173,23 @@ static inline float orc_absmax3(const float *rows, int n, int need_w)
     }
     return m;
 }
-/* Bound on the coordinates of a transformed source point: |x_c| <= sum_k |R_ck| P + |t_c| for source coordinates <= P and
- * the pose T (row-major 3x4, double); strict operations, identical bits on both sides. */
-static inline double orc_pose_bound(float P, const double *T12)
+/* bound on every product of one ICP iteration: source coordinates <= P, target coordinates <= Q, normal components <= Nn
+ * (1 for the SVD estimator), pose T (row-major 3x4, double).  |x| <= 3 Rm P + tm =: X; A = max(X, Q, 1), N = max(Nn, 1);
+ * |J| <= 2 N A, |r| <= 6 N A, d^2 <= 12 A^2  =>  every product <= 12 N^2 A^2 < B = 16 N^2 A^2. */
+static inline double orc_icp_bound(float P, float Q, float Nn, const double *T12)
 {
-    double X = 0.0;
+    double Rm = 0.0, tm = 0.0;
     for (int r = 0; r < 3; ++r) {
-        double a = ((fabs(T12[4 * r]) + fabs(T12[4 * r + 1])) + fabs(T12[4 * r + 2])) * (double)P + fabs(T12[4 * r + 3]);
-        if (a > X) X = a;
+        for (int c = 0; c < 3; ++c) { double a = fabs(T12[4 * r + c]); if (a > Rm) Rm = a; }
+        double a = fabs(T12[4 * r + 3]); if (a > tm) tm = a;
     }
-    if (!(X < 1e150)) X = 1e150;             /* also catches NaN */
-    return X;
-}
-/* bound on the squared correspondence distance (the one sum of an ICP iteration that keeps the fma rounding above):
- * |x - q| <= sqrt(3) (X + Q)  =>  d^2 <= 3 (X + Q)^2 < B = 4 (X + Q + 1)^2 */
-static inline double orc_icp_bound(double X, float Q)
-{
-    double s = (X + (double)Q) + 1.0;
-    double B = 4.0 * (s * s);
+    double A = 3.0 * Rm * (double)P + tm;
+    if ((double)Q > A) A = (double)Q;
+    if (!(A > 1.0)) A = 1.0;                 /* also catches NaN */
+    double N = (double)Nn > 1.0 ? (double)Nn : 1.0;
+    double B = 16.0 * (N * N) * (A * A);
     if (!(B < 1e300)) B = 1e300;
     return B;
-}
-
-/* ------------------------------------------------------------------------------------------------
- * The normal-equation sums of an ICP iteration: 26-bit fixed-point factors, exact integer products.
- *
- * The factors of the 27 (point-to-plane) or 15 (Kabsch) sums of products -- J = (x cross n, n), r = n.(q - x), or the
- * coordinates of x and q -- are float32 values.  Each factor is rounded ONCE to a 26-bit fixed-point integer,
- * rint(v * 2^s), with one power-of-two scale per factor class chosen from data bounds (order independent: maxima of
- * absolute values and the current pose):
- *     class a  J[0..2] = x cross n     |.| <= 2 N X            class n  J[3..5] = n     |.| <= N
- *     class r  r = n.(q - x)           |.| <= 3 N (X + Q), or sqrt(3) N gate when a correspondence gate is set
- *     class c  coordinates of x and q  |.| <= max(X, Q)                                         (Kabsch sums)
- * with N the largest normal component, X = orc_pose_bound, Q the largest target coordinate; s = 26 - E, 2^E > bound.
- * The resolution 2^-s is of the order of the float32 resolution of the factor itself (its inputs are float32
- * coordinates of magnitude up to X): 2.4e-7 for J[0..2] in a 5 m scene, 1.5e-8 for the normal.  The products of the
- * integers are exact (52 bits) and are added exactly, so the sums are independent of the order of the additions, and
- * one 32x32+64-bit integer multiply-add per term is all the GPU spends.  Converted once:
- * value = (double)(S >> 32) * 2^32 + (double)(S & 0xffffffff), times 2^-(s1 + s2).
- * ---------------------------------------------------------------------------------------------- */
-typedef struct { int sa, sn, sr, sc; float fa, fn, fr, fc; } orc_fxq;
-
-static inline int orc_exp_above(double B)          /* E with 2^(E-1) <= B < 2^E  (B finite, > 0) */
-{
-    return (int)((orc_dbits(B) >> 52) & 0x7ff) - 1022;
-}
-static inline float orc_pow2f(int e)               /* 2^e as float, -126 <= e <= 127 */
-{
-    uint32_t u = (uint32_t)(e + 127) << 23; float f; memcpy(&f, &u, 4); return f;
-}
-static inline int orc_clamp_scale(int s) { return s < -100 ? -100 : (s > 100 ? 100 : s); }
-/* gate: correspondence gate in metres or INFINITY */
-static inline orc_fxq orc_fxq_make(double X, float Q, float Nn, float gate)
-{
-    orc_fxq f;
-    const double N = (double)Nn > 1e-30 ? (double)Nn : 1e-30;
-    double ba = (2.0 * N) * X * 1.0001 + 1e-30;
-    double bn = N * 1.0001;
-    double br = (3.0 * N) * (X + (double)Q) * 1.0001 + 1e-30;
-    if ((double)gate < 1e30) { double bg = (1.7320508075688772 * N) * (double)gate * 1.0001 + 1e-30; if (bg < br) br = bg; }
-    double bc = (X > (double)Q ? X : (double)Q) * 1.0001 + 1e-30;
-    f.sa = orc_clamp_scale(26 - orc_exp_above(ba)); f.sn = orc_clamp_scale(26 - orc_exp_above(bn));
-    f.sr = orc_clamp_scale(26 - orc_exp_above(br)); f.sc = orc_clamp_scale(26 - orc_exp_above(bc));
-    f.fa = orc_pow2f(f.sa); f.fn = orc_pow2f(f.sn); f.fr = orc_pow2f(f.sr); f.fc = orc_pow2f(f.sc);
-    return f;
-}
-static inline int32_t orc_fxq_q(float v, float factor) { return (int32_t)lrintf(v * factor); }     /* round to nearest even */
-static inline double orc_fxq_value(__int128 S, int s_sum)
-{
-    const int64_t H = (int64_t)(S >> 32), L = (int64_t)(S & (__int128)0xffffffff);
-    return ((double)H * 4294967296.0 + (double)L) * orc_bitsd((uint64_t)(1023 - s_sum) << 52);
 }
 /* plane refit: sums of x, y, z and their products over points with |coordinate| <= A */
 static inline double orc_pca_bound(float A)

@@ -212,54 +212,23 @@ __device__ __forceinline__ double s3d_fx_value(long long hi, long long lo, doubl
 {
     return __dmul_rn(__dadd_rn(__dmul_rn(__ll2double_rn(hi), 4294967296.0), __ll2double_rn(lo)), scale);
 }
-// bound on the coordinates of a transformed source point (orc_pose_bound): strict operations, identical bits on both sides
-__device__ __forceinline__ double s3d_pose_bound(float P, const double *T12)
+// bound on every product of one ICP iteration (orc_icp_bound): strict operations, identical bits on both sides
+__device__ __forceinline__ double s3d_icp_bound(float P, float Q, float Nn, const double *T12)
 {
-    double X = 0.0;
+    double Rm = 0.0, tm = 0.0;
     #pragma unroll
     for (int r = 0; r < 3; ++r) {
-        const double a = __dadd_rn(__dmul_rn(__dadd_rn(__dadd_rn(fabs(T12[4 * r]), fabs(T12[4 * r + 1])), fabs(T12[4 * r + 2])), (double)P), fabs(T12[4 * r + 3]));
-        if (a > X) X = a;
+        #pragma unroll
+        for (int c = 0; c < 3; ++c) { const double a = fabs(T12[4 * r + c]); if (a > Rm) Rm = a; }
+        const double a = fabs(T12[4 * r + 3]); if (a > tm) tm = a;
     }
-    if (!(X < 1e150)) X = 1e150;
-    return X;
-}
-// bound on the squared correspondence distance (orc_icp_bound)
-__device__ __forceinline__ double s3d_icp_bound(double X, float Q)
-{
-    const double s = __dadd_rn(__dadd_rn(X, (double)Q), 1.0);
-    double B = __dmul_rn(4.0, __dmul_rn(s, s));
+    double A = __dadd_rn(__dmul_rn(__dmul_rn(3.0, Rm), (double)P), tm);
+    if ((double)Q > A) A = (double)Q;
+    if (!(A > 1.0)) A = 1.0;
+    const double N = (double)Nn > 1.0 ? (double)Nn : 1.0;
+    double B = __dmul_rn(__dmul_rn(16.0, __dmul_rn(N, N)), __dmul_rn(A, A));
     if (!(B < 1e300)) B = 1e300;
     return B;
-}
-// 26-bit fixed-point factors of the normal-equation sums (contract: oracle/oracle_common.h, orc_fxq): one power-of-two scale per
-// factor class (a: x cross n, n: normal, r: residual, c: coordinates), from data bounds; products and sums are exact integers.
-struct FxQ { int sa, sn, sr, sc; float fa, fn, fr, fc; };
-__device__ __forceinline__ int s3d_exp_above(double B) { return (int)(((unsigned long long)__double_as_longlong(B) >> 52) & 0x7ff) - 1022; }
-__device__ __forceinline__ int s3d_clamp_scale(int s) { return s < -100 ? -100 : (s > 100 ? 100 : s); }
-__device__ __forceinline__ float s3d_pow2f(int e) { return __uint_as_float((unsigned)(e + 127) << 23); }
-__device__ __forceinline__ FxQ s3d_fxq_make(double X, float Q, float Nn, float gate)
-{
-    FxQ f;
-    const double N = (double)Nn > 1e-30 ? (double)Nn : 1e-30;
-    const double ba = __dadd_rn(__dmul_rn(__dmul_rn(__dmul_rn(2.0, N), X), 1.0001), 1e-30);
-    const double bn = __dmul_rn(N, 1.0001);
-    double br = __dadd_rn(__dmul_rn(__dmul_rn(__dmul_rn(3.0, N), __dadd_rn(X, (double)Q)), 1.0001), 1e-30);
-    if ((double)gate < 1e30) {
-        const double bg = __dadd_rn(__dmul_rn(__dmul_rn(__dmul_rn(1.7320508075688772, N), (double)gate), 1.0001), 1e-30);
-        if (bg < br) br = bg;
-    }
-    const double bc = __dadd_rn(__dmul_rn(X > (double)Q ? X : (double)Q, 1.0001), 1e-30);
-    f.sa = s3d_clamp_scale(26 - s3d_exp_above(ba)); f.sn = s3d_clamp_scale(26 - s3d_exp_above(bn));
-    f.sr = s3d_clamp_scale(26 - s3d_exp_above(br)); f.sc = s3d_clamp_scale(26 - s3d_exp_above(bc));
-    f.fa = s3d_pow2f(f.sa); f.fn = s3d_pow2f(f.sn); f.fr = s3d_pow2f(f.sr); f.fc = s3d_pow2f(f.sc);
-    return f;
-}
-// (hi, lo) total of a sum of integer products -> double, scaled by 2^-s_sum
-__device__ __forceinline__ double s3d_fxq_value(long long hi, long long lo, int s_sum)
-{
-    return __dmul_rn(__dadd_rn(__dmul_rn(__ll2double_rn(hi), 4294967296.0), __ll2double_rn(lo)),
-                     __longlong_as_double((long long)((unsigned long long)(1023 - s_sum) << 52)));
 }
 __device__ __forceinline__ double s3d_pca_bound(float A)
 {

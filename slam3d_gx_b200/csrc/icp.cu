@@ -280,15 +280,13 @@ __device__ __noinline__ void solve_and_update(const double *acc, PairState *st, 
 // ------------------------------------------------------------------------------------------------
 // the fused iteration kernel
 // ------------------------------------------------------------------------------------------------
-// One accepted correspondence into the order-independent sums (common.cuh; contract in oracle/oracle_common.h): J and r in
-// float32 with the oracle's expressions (identical bits), each rounded once to a 26-bit fixed-point integer with its class's
-// power-of-two scale; the products are exact integers and go into 64-bit accumulators with ONE integer multiply-add each
-// (IMAD.WIDE).  The sum of squared distances keeps the fma rounding (raw bits of fma(d2, 1, M), unbiased at hand-over).
-// The caller counts the terms (S3D_ACC_COUNT is not touched here).
-#define S3D_FX_SEGMENT 30      // queries per thread between hand-overs: 30 * 32 lanes * 2^52 < 2^63
-struct IcpScales { FxQ q; FxScale d2; };
+// One accepted correspondence into the order-independent sums (common.cuh; contract in oracle/oracle_common.h): J and r
+// in float32 with the oracle's expressions (identical bits), every product exact in double, rounded once to 2^-g by
+// fma(a, b, M), the raw bits added into wrapping int64 accumulators.  The caller counts the terms (S3D_ACC_COUNT is not
+// touched here) and removes count * bits(M) when it hands the partial sums on (fx_unbias).
+#define S3D_FX_SEGMENT 240     // queries per thread between hand-overs: 240 * 32 lanes * 2^49 < 2^63
 template <int EST>
-__device__ __forceinline__ void accumulate_fx(long long *acc, const FxQ &fq, double M, float px, float py, float pz, float4 q, float4 nv, float d2)
+__device__ __forceinline__ void accumulate_fx(long long *acc, double M, float px, float py, float pz, float4 q, float4 nv, float d2)
 {
     if (EST == S3D_ESTIMATOR_POINT_TO_PLANE) {
         float J[6];
@@ -298,74 +296,44 @@ __device__ __forceinline__ void accumulate_fx(long long *acc, const FxQ &fq, dou
         J[3] = nv.x; J[4] = nv.y; J[5] = nv.z;
         float ex = __fsub_rn(q.x, px), ey = __fsub_rn(q.y, py), ez = __fsub_rn(q.z, pz);
         float r = __fmaf_rn(nv.z, ez, __fmaf_rn(nv.y, ey, __fmul_rn(nv.x, ex)));
-        int qj[6];
+        double Jd[6];
         #pragma unroll
-        for (int a = 0; a < 6; ++a) qj[a] = __float2int_rn(__fmul_rn(J[a], a < 3 ? fq.fa : fq.fn));
-        const int qr = __float2int_rn(__fmul_rn(r, fq.fr));
+        for (int a = 0; a < 6; ++a) Jd[a] = (double)J[a];
+        const double rd = (double)r;
         int k = 0;
         #pragma unroll
         for (int a = 0; a < 6; ++a) {
             #pragma unroll
-            for (int b = a; b < 6; ++b) { acc[k] += (long long)qj[a] * (long long)qj[b]; ++k; }
+            for (int b = a; b < 6; ++b) { acc[k] += s3d_fx_bits(Jd[a], Jd[b], M); ++k; }
         }
         #pragma unroll
-        for (int a = 0; a < 6; ++a) acc[21 + a] += (long long)qj[a] * (long long)qr;
+        for (int a = 0; a < 6; ++a) acc[21 + a] += s3d_fx_bits(Jd[a], rd, M);
     } else {
-        int qp[3], qq[3];
-        qp[0] = __float2int_rn(__fmul_rn(px, fq.fc)); qp[1] = __float2int_rn(__fmul_rn(py, fq.fc)); qp[2] = __float2int_rn(__fmul_rn(pz, fq.fc));
-        qq[0] = __float2int_rn(__fmul_rn(q.x, fq.fc)); qq[1] = __float2int_rn(__fmul_rn(q.y, fq.fc)); qq[2] = __float2int_rn(__fmul_rn(q.z, fq.fc));
+        const double p[3] = {(double)px, (double)py, (double)pz}, qq[3] = {(double)q.x, (double)q.y, (double)q.z};
         #pragma unroll
         for (int a = 0; a < 3; ++a) {
-            acc[a] += (long long)qp[a]; acc[3 + a] += (long long)qq[a];
+            acc[a] += s3d_fx_bits(p[a], 1.0, M); acc[3 + a] += s3d_fx_bits(qq[a], 1.0, M);
             #pragma unroll
-            for (int b = 0; b < 3; ++b) acc[6 + 3 * a + b] += (long long)qp[a] * (long long)qq[b];
+            for (int b = 0; b < 3; ++b) acc[6 + 3 * a + b] += s3d_fx_bits(p[a], qq[b], M);
         }
     }
     acc[S3D_ACC_SUMD2] += s3d_fx_bits((double)d2, 1.0, M);
 }
-// slots that carry sums for this estimator (the others stay 0)
+// slots that carry fixed-point sums for this estimator (the others stay 0)
 template <int EST> __device__ __forceinline__ bool fx_slot_used(int k)
 {
     return k == S3D_ACC_SUMD2 || k < (EST == S3D_ESTIMATOR_POINT_TO_PLANE ? 27 : 15);
 }
-// raw accumulator of `cnt` terms -> the true partial sum (only the sum of squared distances is biased)
+// raw accumulator of `cnt` terms -> the true partial sum (an integer number of 2^-g units)
 template <int EST> __device__ __forceinline__ long long fx_unbias(long long raw, int k, int cnt, unsigned long long mbits)
 {
-    if (k == S3D_ACC_SUMD2) return raw - (long long)((unsigned long long)cnt * mbits);
-    return fx_slot_used<EST>(k) ? raw : 0ll;
+    return fx_slot_used<EST>(k) ? raw - (long long)((unsigned long long)cnt * mbits) : 0ll;
 }
-// sum of the scale exponents of slot k's two factors
-template <int EST> __device__ __forceinline__ int fx_slot_exp(int k, const FxQ &fq)
-{
-    if (EST == S3D_ESTIMATOR_POINT_TO_PLANE) {
-        if (k >= 21) return ((k - 21) < 3 ? fq.sa : fq.sn) + fq.sr;
-        // k-th entry of the upper triangle of the 6x6 (row a, column b >= a)
-        int a = 0, first = 0;
-        #pragma unroll
-        for (int r = 0; r < 6; ++r) { if (k >= first && k < first + (6 - r)) a = r; first += 6 - r; }
-        int start = 0;
-        #pragma unroll
-        for (int r = 0; r < 6; ++r) if (r < a) start += 6 - r;
-        const int b = a + (k - start);
-        return (a < 3 ? fq.sa : fq.sn) + (b < 3 ? fq.sa : fq.sn);
-    }
-    return k < 6 ? fq.sc : 2 * fq.sc;
-}
-// the 29 totals (hi, lo) of a pair -> doubles for the solve (slot 27: sum of d^2, slot 28: the plain count)
-template <int EST> __device__ __forceinline__ double fx_total(long long hi, long long lo, int k, const IcpScales &sc)
+// the 29 totals (hi, lo) of a pair -> doubles for the solve (slot 28 is the plain count)
+template <int EST> __device__ __forceinline__ double fx_total(long long hi, long long lo, int k, double scale)
 {
     if (k == S3D_ACC_COUNT) return __dadd_rn(__dmul_rn(__ll2double_rn(hi), 4294967296.0), __ll2double_rn(lo));
-    if (k == S3D_ACC_SUMD2) return s3d_fx_value(hi, lo, sc.d2.scale);
-    return fx_slot_used<EST>(k) ? s3d_fxq_value(hi, lo, fx_slot_exp<EST>(k, sc.q)) : 0.0;
-}
-// the scales of one iteration of one pair, from the data bounds and the current pose (every CTA computes the same bits)
-template <int EST> __device__ __forceinline__ IcpScales icp_scales(const PairDesc &d, const double *T12, float gate)
-{
-    IcpScales sc;
-    const double X = s3d_pose_bound(*d.src_absmax, T12);
-    sc.d2 = s3d_fx_make(s3d_icp_bound(X, *d.tgt_absmax));
-    sc.q = s3d_fxq_make(X, *d.tgt_absmax, EST == S3D_ESTIMATOR_POINT_TO_PLANE ? d.tgt_absmax[1] : 1.0f, gate);
-    return sc;
+    return fx_slot_used<EST>(k) ? s3d_fx_value(hi, lo, scale) : 0.0;
 }
 
 template <int EST, int SEARCH>
@@ -516,27 +484,26 @@ template <int EST, int SEARCH>
 __global__ void __launch_bounds__(ICP_BLOCK, 2) icp_accum_kernel(const PairDesc *__restrict__ descs, PairState *__restrict__ states,
                                                                  long long *__restrict__ partials, const int32_t *__restrict__ nn_idx,
                                                                  const int32_t *__restrict__ nn_pos, int nn_stride,
-                                                                 float max_d2, float gate, int min_corr, double pivot_eps, int32_t *__restrict__ nn_out)
+                                                                 float max_d2, int min_corr, double pivot_eps, int32_t *__restrict__ nn_out)
 {
     __shared__ long long whi[ICP_BLOCK / 32][S3D_NACC], wlo[ICP_BLOCK / 32][S3D_NACC];
     __shared__ long long thi[8][S3D_NACC], tlo[8][S3D_NACC];
     __shared__ double total[S3D_NACC];
-    __shared__ IcpScales fxs;
+    __shared__ FxScale fxs;
     __shared__ bool is_last;
     const int pair = blockIdx.y;
     PairState *st = states + pair;
     if (st->status != 0) return;   // failed pairs stay failed; every CTA of the pair takes this exit together
     const PairDesc d = descs[pair];
-    if (threadIdx.x == 0) fxs = icp_scales<EST>(d, st->T, gate);
+    if (threadIdx.x == 0) fxs = s3d_fx_make(s3d_icp_bound(*d.src_absmax, *d.tgt_absmax, EST == S3D_ESTIMATOR_POINT_TO_PLANE ? d.tgt_absmax[1] : 1.0f, st->T));
     float T[12];
     #pragma unroll
     for (int k = 0; k < 12; ++k) T[k] = st->Tf[k];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (lane < 29) { whi[warp][lane] = 0; wlo[warp][lane] = 0; }
     __syncthreads();
-    const unsigned long long mbits = fxs.d2.mbits;
+    const unsigned long long mbits = fxs.mbits;
     const double M = __longlong_as_double((long long)mbits);
-    const FxQ fq = fxs.q;
     const int tid0 = blockIdx.x * ICP_BLOCK + threadIdx.x, tstride = gridDim.x * ICP_BLOCK;
     const int32_t *my_pos = nn_pos + (size_t)pair * nn_stride;
     int total_cnt = 0;
@@ -567,7 +534,7 @@ __global__ void __launch_bounds__(ICP_BLOCK, 2) icp_accum_kernel(const PairDesc 
             }
             const float bd = s3d_dist2(x.x, x.y, x.z, q.x, q.y, q.z);   // same expression as in the search: identical bits
             const bool ok = (j >= 0) && (bd <= max_d2) && (nv.w != 0.f);
-            if (ok) { accumulate_fx<EST>(acc, fq, M, x.x, x.y, x.z, q, nv, bd); ++cnt; }
+            if (ok) { accumulate_fx<EST>(acc, M, x.x, x.y, x.z, q, nv, bd); ++cnt; }
             if (nn_out) nn_out[i] = ok ? j : -1;
         }
         total_cnt += cnt;
@@ -614,7 +581,7 @@ __global__ void __launch_bounds__(ICP_BLOCK, 2) icp_accum_kernel(const PairDesc 
         long long hi = 0, lo = 0;
         #pragma unroll
         for (int p8 = 0; p8 < 8; ++p8) { hi += thi[p8][threadIdx.x]; lo += tlo[p8][threadIdx.x]; }
-        total[threadIdx.x] = threadIdx.x < 29 ? fx_total<EST>(hi, lo, threadIdx.x, fxs) : 0.0;
+        total[threadIdx.x] = threadIdx.x < 29 ? fx_total<EST>(hi, lo, threadIdx.x, fxs.scale) : 0.0;
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -665,7 +632,7 @@ struct PersistArgs {
     long long nn_stride;         // queries per pair in the per-query arrays (a multiple of 8)
     int pend_stride;
     int n_pairs, groups, group_ctas, iterations;
-    float max_d2; float gate; int min_corr; double pivot_eps;      // gate: the correspondence gate itself (max_d2 = gate^2) or INFINITY
+    float max_d2; int min_corr; double pivot_eps;
     int32_t *nn_out;             // correspondences of the last iteration (single pair) or null
     float hint_cells;            // first-guess search radius after a big pose update, in cells
     float first_cells;           // first-guess search radius of the first iteration when the decimated index is not used, in cells
@@ -709,11 +676,10 @@ __global__ void __launch_bounds__(TS_BLOCK, 1) icp_persist_kernel(const PersistA
     __shared__ float4 hist[PS_HIST][3];                           // float poses (three rows) of the last PS_HIST iterations (ring)
     __shared__ long long ctot[S3D_ROW];                           // the CTA's (hi, lo) sums of this iteration, then the group's totals
     __shared__ double total[S3D_NACC];                            // the pair's 29 sums as doubles, input of the solve
-    __shared__ IcpScales fxs;                                     // scales of this iteration's sums (from the pose and the data bounds)
+    __shared__ FxScale fxs;                                       // resolution of this iteration's sums (from the pose and the data bounds)
     __shared__ TileCfg cfg[2];                                    // search levels of the current pair: [0] decimated grid, [1] full grid
     __shared__ int pend_count, pend_next;                         // pending list of this CTA: entries appended / handed out
     __shared__ int full_next;                                     // the next iteration skips the streaming pass (big pose update)
-    __shared__ float delta[PS_HIST];                              // per ring slot: bound on how far ANY source point has moved since that pose
 #ifdef TS_USE_TMA
     __shared__ __align__(8) uint64_t tile_bar[TS_WARPS];         // one mbarrier per warp: completion of its TMA row copies
 #endif
@@ -742,7 +708,7 @@ __global__ void __launch_bounds__(TS_BLOCK, 1) icp_persist_kernel(const PersistA
         __syncthreads();
         if (threadIdx.x == 0) {
             st = a.states[pair];
-            fxs = icp_scales<EST>(d, st.T, a.gate);
+            fxs = s3d_fx_make(s3d_icp_bound(*d.src_absmax, *d.tgt_absmax, EST == S3D_ESTIMATOR_POINT_TO_PLANE ? d.tgt_absmax[1] : 1.0f, st.T));
             pend_count = 0; pend_next = 0; full_next = 1;
             cfg[1].gp = *d.grid; cfg[1].cell_start = d.cell_start; cfg[1].pts = d.sorted_pts;
             cfg[1].slack = a.slack_cells * cfg[1].gp.cell; cfg[1].gate_r = gate_r;
@@ -788,9 +754,8 @@ __global__ void __launch_bounds__(TS_BLOCK, 1) icp_persist_kernel(const PersistA
             if (st.status != 0) break;            // failed pairs stop; every CTA of the group sees the same state
             const float *T = st.Tf;               // the pose is read from shared memory where it is used
             const bool last = (it == a.iterations - 1);
-            const unsigned long long mbits = fxs.d2.mbits;
+            const unsigned long long mbits = fxs.mbits;
             const double M = __longlong_as_double((long long)mbits);
-            const FxQ fq = fxs.q;
             PHASE_T0();
 #if defined(S3D_PHASES)
             long long tm[5] = {0, 0, 0, 0, 0};
@@ -831,24 +796,6 @@ __global__ void __launch_bounds__(TS_BLOCK, 1) icp_persist_kernel(const PersistA
             const bool full_search = it == 0 || full_next;
             if (full_search) { ts_cp_async_wait_all(); __syncwarp(); }      // a staging round issued ahead for nothing: the tile is the search's now
             if (!full_search) {
-                // Cheap form of the skip test.  For ring slot j, delta[j] bounds |T_now p - T_j p| for EVERY source point
-                // (|p|_inf <= P): per coordinate (sum_k |dR_ck|) P + |dt_c|, plus the rounding of the two float evaluations.
-                // A query whose margin beats delta[its] keeps its correspondence without its old position being recomputed;
-                // the others fall back to the exact distance.  Both forms are sufficient conditions of the same inequality.
-                if (threadIdx.x < PS_HIST) {
-                    const float4 *Tn = hist[it & (PS_HIST - 1)], *Tj = hist[threadIdx.x];
-                    const float P = *d.src_absmax;
-                    float s2 = 0.f, amax = 0.f;
-                    #pragma unroll
-                    for (int c = 0; c < 3; ++c) {
-                        const float m = (fabsf(Tn[c].x - Tj[c].x) + fabsf(Tn[c].y - Tj[c].y) + fabsf(Tn[c].z - Tj[c].z)) * P + fabsf(Tn[c].w - Tj[c].w);
-                        s2 += m * m;
-                        amax = fmaxf(amax, (fabsf(Tn[c].x) + fabsf(Tn[c].y) + fabsf(Tn[c].z)) * P + fabsf(Tn[c].w));
-                        amax = fmaxf(amax, (fabsf(Tj[c].x) + fabsf(Tj[c].y) + fabsf(Tj[c].z)) * P + fabsf(Tj[c].w));
-                    }
-                    delta[threadIdx.x] = sqrtf(s2) * 1.0001f + 2e-6f * amax + 1e-7f;
-                }
-                __syncthreads();
                 int since = 0;
                 for (int c0 = warp; c0 < cta_chunks; c0 += TS_WARPS * PS_STAGE) {
                     if (c0 != warp) PS_STAGE_ROUND(c0);       // (the first round was issued before the previous iteration's barrier)
@@ -874,17 +821,13 @@ __global__ void __launch_bounds__(TS_BLOCK, 1) icp_persist_kernel(const PersistA
                             if (__float_as_int(q.w) >= 0) {
                                 // the query was at xs when it was last searched; every other target point was >= lb away from there
                                 const int its = (int)(f & 63u);
+                                const float4 *Ts = hist[its];
+                                const float3 xs = s3d_xform4(Ts[0], Ts[1], Ts[2], p.x, p.y, p.z);
                                 float d2q = s3d_dist2(x.x, x.y, x.z, q.x, q.y, q.z);
+                                const float moved = sqrtf(s3d_dist2(x.x, x.y, x.z, xs.x, xs.y, xs.z)) * 1.000002f + 5e-8f;
                                 const float lb = nv.w;
-                                float moved = delta[its];                     // bound for every source point: usually enough
-                                bool keep = !(f & PS_FLAG_TIE) && sqrtf(d2q) * 1.000002f + 2e-7f < lb - moved;
-                                if (!keep) {                                  // exact distance from the old position
-                                    const float4 *Ts = hist[its];
-                                    const float3 xs = s3d_xform4(Ts[0], Ts[1], Ts[2], p.x, p.y, p.z);
-                                    moved = fminf(moved, sqrtf(s3d_dist2(x.x, x.y, x.z, xs.x, xs.y, xs.z)) * 1.000002f + 5e-8f);
-                                }
-                                if (keep) { }
-                                else if (!(f & PS_FLAG_TIE)) keep = sqrtf(d2q) * 1.000002f + 2e-7f < lb - moved;      // still the exact nearest neighbour
+                                bool keep;
+                                if (!(f & PS_FLAG_TIE)) keep = sqrtf(d2q) * 1.000002f + 2e-7f < lb - moved;      // still the exact nearest neighbour
                                 else {
                                     // near tie (rare): the runner-up q2 was kept and everything else is >= lb away.  Both are evaluated;
                                     // the nearer (lower original index on equality) is the exact nearest neighbour if it beats the bound.
@@ -906,7 +849,7 @@ __global__ void __launch_bounds__(TS_BLOCK, 1) icp_persist_kernel(const PersistA
                                     pending = false;
                                     STAT(1, 1);
                                     const bool ok = (d2q <= a.max_d2) && (f & PS_FLAG_NRM);
-                                    if (ok) { accumulate_fx<EST>(acc, fq, M, x.x, x.y, x.z, q, nv, d2q); ++cnt; }
+                                    if (ok) { accumulate_fx<EST>(acc, M, x.x, x.y, x.z, q, nv, d2q); ++cnt; }
                                     if (last && a.nn_out) a.nn_out[i] = ok ? __float_as_int(q.w) : -1;
                                     if (((it - its) & 63) >= PS_REBASE_AGE) {
                                         // re-base onto the current pose before the ring slot is reused: everything else is at least
@@ -998,7 +941,7 @@ __global__ void __launch_bounds__(TS_BLOCK, 1) icp_persist_kernel(const PersistA
                         my_fl[i] = (uint8_t)f;
                         if (tie) my_cq2[i] = b.q2;                             // near tie: keep the runner-up too
                         const bool ok = (__float_as_int(q.w) >= 0) && (d2q <= a.max_d2) && (nv.w != 0.f);
-                        if (ok) { accumulate_fx<EST>(acc, fq, M, x.x, x.y, x.z, q, nv, d2q); ++cnt; }
+                        if (ok) { accumulate_fx<EST>(acc, M, x.x, x.y, x.z, q, nv, d2q); ++cnt; }
                         if (last && a.nn_out) a.nn_out[i] = ok ? __float_as_int(q.w) : -1;
                     }
                     PS_HAND_OVER();
@@ -1039,7 +982,7 @@ __global__ void __launch_bounds__(TS_BLOCK, 1) icp_persist_kernel(const PersistA
                     __syncwarp();
                     PHASE(10);
                     const long long hi = __ldcg(&g[lane]), lo = __ldcg(&g[32 + lane]);
-                    total[lane] = lane < 29 ? fx_total<EST>(hi, lo, lane, fxs) : 0.0;
+                    total[lane] = lane < 29 ? fx_total<EST>(hi, lo, lane, fxs.scale) : 0.0;
                     // the buffer read two epochs ago is free: every CTA is past the barrier that followed its reads.  It is added to
                     // again only after the NEXT barrier, which this CTA (rank 0) reaches after these stores.
                     if (rank == 0) {
@@ -1049,14 +992,14 @@ __global__ void __launch_bounds__(TS_BLOCK, 1) icp_persist_kernel(const PersistA
                     __syncwarp();
                 }
             } else if (warp == 0) {
-                total[lane] = lane < 29 ? fx_total<EST>(ctot[lane], ctot[32 + lane], lane, fxs) : 0.0;
+                total[lane] = lane < 29 ? fx_total<EST>(ctot[lane], ctot[32 + lane], lane, fxs.scale) : 0.0;
                 __syncwarp();
                 ctot[lane] = 0; ctot[32 + lane] = 0;
             }
             PHASE(11);
             if (threadIdx.x == 0) {
                 solve_and_update<EST>(total, &st, a.min_corr, a.pivot_eps);
-                fxs = icp_scales<EST>(d, st.T, a.gate);
+                fxs = s3d_fx_make(s3d_icp_bound(*d.src_absmax, *d.tgt_absmax, EST == S3D_ESTIMATOR_POINT_TO_PLANE ? d.tgt_absmax[1] : 1.0f, st.T));
                 #pragma unroll
                 for (int k = 0; k < 3; ++k) hist[(it + 1) & (PS_HIST - 1)][k] = make_float4(st.Tf[4 * k], st.Tf[4 * k + 1], st.Tf[4 * k + 2], st.Tf[4 * k + 3]);
                 pend_count = 0; pend_next = 0;
@@ -1125,14 +1068,14 @@ static int ensure_batch(s3d_ctx *ctx, int n_pairs, int ctas)
 
 // one iteration of the per-iteration-launch modes: [grid search kernel] + accumulate/solve kernel
 template <int EST, int SEARCH>
-static int launch_iter(s3d_ctx *ctx, dim3 grid, int nn_stride, int use_seed, float max_d2, float gate, int min_corr, double pivot_eps, int32_t *nn_out)
+static int launch_iter(s3d_ctx *ctx, dim3 grid, int nn_stride, int use_seed, float max_d2, int min_corr, double pivot_eps, int32_t *nn_out)
 {
     if (SEARCH == S3D_SEARCH_GRID) {
         icp_iter_kernel<EST, SEARCH><<<grid, ICP_BLOCK, 0, ctx->stream>>>(ctx->d_desc, ctx->d_state, ctx->d_nn_pos, ctx->d_nn_d2, nn_stride, use_seed, max_d2);
         S3D_LAUNCHED(ctx);
     }
     icp_accum_kernel<EST, SEARCH><<<grid, ICP_BLOCK, 0, ctx->stream>>>(ctx->d_desc, ctx->d_state, ctx->d_partials, ctx->d_nn_idx, ctx->d_nn_pos,
-                                                                       nn_stride, max_d2, gate, min_corr, pivot_eps, nn_out);
+                                                                       nn_stride, max_d2, min_corr, pivot_eps, nn_out);
     S3D_LAUNCHED(ctx);
     return S3D_OK;
 }
@@ -1274,7 +1217,6 @@ int s3d_register_issue(s3d_ctx *ctx, const s3d_cloud *const *src, const s3d_clou
     S3D_CUDA(ctx, cudaMemcpyAsync(ctx->d_state, ctx->h_state, sizeof(PairState) * n_pairs, cudaMemcpyHostToDevice, ctx->stream));
 
     const float max_d2 = prm->max_corr_dist > 0.f ? prm->max_corr_dist * prm->max_corr_dist : INFINITY;
-    const float gate = prm->max_corr_dist > 0.f ? prm->max_corr_dist : INFINITY;
     const int min_corr = prm->min_correspondences > 0 ? prm->min_correspondences : 3;
     const double pivot_eps = prm->pivot_eps > 0 ? prm->pivot_eps : 1e-9;
     const dim3 grid(ctas, n_pairs);
@@ -1287,7 +1229,7 @@ int s3d_register_issue(s3d_ctx *ctx, const s3d_cloud *const *src, const s3d_clou
         pa.cq = ctx->d_cq; pa.cn = ctx->d_cn; pa.cq2 = ctx->d_cq2; pa.flags = ctx->d_flags; pa.pend = ctx->d_pend;
         pa.nn_stride = nn_stride8; pa.pend_stride = pend_stride;
         pa.n_pairs = n_pairs; pa.groups = p_groups; pa.group_ctas = p_group_ctas; pa.iterations = prm->max_iterations;
-        pa.max_d2 = max_d2; pa.gate = gate; pa.min_corr = min_corr; pa.pivot_eps = pivot_eps; pa.nn_out = nn_out;
+        pa.max_d2 = max_d2; pa.min_corr = min_corr; pa.pivot_eps = pivot_eps; pa.nn_out = nn_out;
         { static const char *e = getenv("S3D_HINT_CELLS"); pa.hint_cells = e ? (float)atof(e) : 1.0f; }
         { static const char *e = getenv("S3D_FIRST_CELLS"); pa.first_cells = e ? (float)atof(e) : 1.5f; }
         { static const char *e = getenv("S3D_USE_COARSE"); pa.use_coarse = e ? atoi(e) : 1; }
@@ -1309,12 +1251,12 @@ int s3d_register_issue(s3d_ctx *ctx, const s3d_cloud *const *src, const s3d_clou
             }
             nn_brute_tma_kernel<<<g2, ICP_BLOCK, smem, ctx->stream>>>(ctx->d_desc, ctx->d_state, ctx->d_nn_idx, ctx->d_nn_d2, n_max);
             S3D_LAUNCHED(ctx); ++iter_launches;
-            rc = plane ? launch_iter<S3D_ESTIMATOR_POINT_TO_PLANE, S3D_SEARCH_BRUTE>(ctx, grid, n_max, 0, max_d2, gate, min_corr, pivot_eps, no)
-                       : launch_iter<S3D_ESTIMATOR_SVD, S3D_SEARCH_BRUTE>(ctx, grid, n_max, 0, max_d2, gate, min_corr, pivot_eps, no);
+            rc = plane ? launch_iter<S3D_ESTIMATOR_POINT_TO_PLANE, S3D_SEARCH_BRUTE>(ctx, grid, n_max, 0, max_d2, min_corr, pivot_eps, no)
+                       : launch_iter<S3D_ESTIMATOR_SVD, S3D_SEARCH_BRUTE>(ctx, grid, n_max, 0, max_d2, min_corr, pivot_eps, no);
             ++iter_launches;
         } else {
-            rc = plane ? launch_iter<S3D_ESTIMATOR_POINT_TO_PLANE, S3D_SEARCH_GRID>(ctx, grid, n_max, it > 0, max_d2, gate, min_corr, pivot_eps, no)
-                       : launch_iter<S3D_ESTIMATOR_SVD, S3D_SEARCH_GRID>(ctx, grid, n_max, it > 0, max_d2, gate, min_corr, pivot_eps, no);
+            rc = plane ? launch_iter<S3D_ESTIMATOR_POINT_TO_PLANE, S3D_SEARCH_GRID>(ctx, grid, n_max, it > 0, max_d2, min_corr, pivot_eps, no)
+                       : launch_iter<S3D_ESTIMATOR_SVD, S3D_SEARCH_GRID>(ctx, grid, n_max, it > 0, max_d2, min_corr, pivot_eps, no);
             iter_launches += 2;
         }
         if (rc) return rc;
