@@ -680,7 +680,6 @@ __global__ void __launch_bounds__(TS_BLOCK, 1) icp_persist_kernel(const PersistA
     __shared__ TileCfg cfg[2];                                    // search levels of the current pair: [0] decimated grid, [1] full grid
     __shared__ int pend_count, pend_next;                         // pending list of this CTA: entries appended / handed out
     __shared__ int full_next;                                     // the next iteration skips the streaming pass (big pose update)
-    __shared__ float delta[PS_HIST];                              // per ring slot: bound on how far ANY source point has moved since that pose
 #ifdef TS_USE_TMA
     __shared__ __align__(8) uint64_t tile_bar[TS_WARPS];         // one mbarrier per warp: completion of its TMA row copies
 #endif
@@ -797,24 +796,6 @@ __global__ void __launch_bounds__(TS_BLOCK, 1) icp_persist_kernel(const PersistA
             const bool full_search = it == 0 || full_next;
             if (full_search) { ts_cp_async_wait_all(); __syncwarp(); }      // a staging round issued ahead for nothing: the tile is the search's now
             if (!full_search) {
-                // Cheap form of the skip test.  For ring slot j, delta[j] bounds |T_now p - T_j p| for EVERY source point
-                // (|p|_inf <= P): per coordinate (sum_k |dR_ck|) P + |dt_c|, plus the rounding of the two float evaluations.
-                // A query whose margin beats delta[its] keeps its correspondence without its old position being recomputed;
-                // the others fall back to the exact distance.  Both forms are sufficient conditions of the same inequality.
-                if (threadIdx.x < PS_HIST) {
-                    const float4 *Tn = hist[it & (PS_HIST - 1)], *Tj = hist[threadIdx.x];
-                    const float P = *d.src_absmax;
-                    float s2 = 0.f, amax = 0.f;
-                    #pragma unroll
-                    for (int c = 0; c < 3; ++c) {
-                        const float m = (fabsf(Tn[c].x - Tj[c].x) + fabsf(Tn[c].y - Tj[c].y) + fabsf(Tn[c].z - Tj[c].z)) * P + fabsf(Tn[c].w - Tj[c].w);
-                        s2 += m * m;
-                        amax = fmaxf(amax, (fabsf(Tn[c].x) + fabsf(Tn[c].y) + fabsf(Tn[c].z)) * P + fabsf(Tn[c].w));
-                        amax = fmaxf(amax, (fabsf(Tj[c].x) + fabsf(Tj[c].y) + fabsf(Tj[c].z)) * P + fabsf(Tj[c].w));
-                    }
-                    delta[threadIdx.x] = sqrtf(s2) * 1.0001f + 2e-6f * amax + 1e-7f;
-                }
-                __syncthreads();
                 int since = 0;
                 for (int c0 = warp; c0 < cta_chunks; c0 += TS_WARPS * PS_STAGE) {
                     if (c0 != warp) PS_STAGE_ROUND(c0);       // (the first round was issued before the previous iteration's barrier)
@@ -840,17 +821,13 @@ __global__ void __launch_bounds__(TS_BLOCK, 1) icp_persist_kernel(const PersistA
                             if (__float_as_int(q.w) >= 0) {
                                 // the query was at xs when it was last searched; every other target point was >= lb away from there
                                 const int its = (int)(f & 63u);
+                                const float4 *Ts = hist[its];
+                                const float3 xs = s3d_xform4(Ts[0], Ts[1], Ts[2], p.x, p.y, p.z);
                                 float d2q = s3d_dist2(x.x, x.y, x.z, q.x, q.y, q.z);
+                                const float moved = sqrtf(s3d_dist2(x.x, x.y, x.z, xs.x, xs.y, xs.z)) * 1.000002f + 5e-8f;
                                 const float lb = nv.w;
-                                float moved = delta[its];                     // bound for every source point: usually enough
-                                bool keep = !(f & PS_FLAG_TIE) && sqrtf(d2q) * 1.000002f + 2e-7f < lb - moved;
-                                if (!keep) {                                  // exact distance from the old position
-                                    const float4 *Ts = hist[its];
-                                    const float3 xs = s3d_xform4(Ts[0], Ts[1], Ts[2], p.x, p.y, p.z);
-                                    moved = fminf(moved, sqrtf(s3d_dist2(x.x, x.y, x.z, xs.x, xs.y, xs.z)) * 1.000002f + 5e-8f);
-                                }
-                                if (keep) { }
-                                else if (!(f & PS_FLAG_TIE)) keep = sqrtf(d2q) * 1.000002f + 2e-7f < lb - moved;      // still the exact nearest neighbour
+                                bool keep;
+                                if (!(f & PS_FLAG_TIE)) keep = sqrtf(d2q) * 1.000002f + 2e-7f < lb - moved;      // still the exact nearest neighbour
                                 else {
                                     // near tie (rare): the runner-up q2 was kept and everything else is >= lb away.  Both are evaluated;
                                     // the nearer (lower original index on equality) is the exact nearest neighbour if it beats the bound.
