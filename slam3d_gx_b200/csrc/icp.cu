@@ -651,7 +651,6 @@ __device__ __forceinline__ void red_release_add_u32(unsigned *p, unsigned v)
 {
     asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-__device__ __forceinline__ void smem_add_i64(long long *p, long long v) { atomicAdd(reinterpret_cast<unsigned long long *>(p), (unsigned long long)v); }
 
 // How an iteration runs (one group of CTAs per pair; octet u = 8 consecutive source points belongs to CTA u mod group_ctas):
 //   pass 1  streaming: every warp walks its share of the CTA's octets once, 49 bytes per query (point, correspondence, normal + bound,
@@ -674,7 +673,9 @@ __global__ void __launch_bounds__(TS_BLOCK, 1) icp_persist_kernel(const PersistA
     float4 *tiles = reinterpret_cast<float4 *>(ts_smem);          // TS_WARPS tiles of TS_CAP candidates
     __shared__ PairState st;                                      // this CTA's copy of the pair state (all CTAs of a group agree bit for bit)
     __shared__ float4 hist[PS_HIST][3];                           // float poses (three rows) of the last PS_HIST iterations (ring)
-    __shared__ long long ctot[S3D_ROW];                           // the CTA's (hi, lo) sums of this iteration, then the group's totals
+    __shared__ long long wrow[TS_WARPS][S3D_ROW];                 // every warp's own (hi, lo) sums of this iteration (no 64-bit shared atomics:
+                                                                  // they are compare-and-swap loops and 16 warps meet on the same 58 words)
+    __shared__ long long ctot[S3D_ROW];                           // the CTA's (hi, lo) sums of this iteration
     __shared__ double total[S3D_NACC];                            // the pair's 29 sums as doubles, input of the solve
     __shared__ FxScale fxs;                                       // resolution of this iteration's sums (from the pose and the data bounds)
     __shared__ TileCfg cfg[2];                                    // search levels of the current pair: [0] decimated grid, [1] full grid
@@ -767,6 +768,8 @@ __global__ void __launch_bounds__(TS_BLOCK, 1) icp_persist_kernel(const PersistA
             #pragma unroll
             for (int k = 0; k < 29; ++k) acc[k] = 0;
             int cnt = 0;
+            wrow[warp][lane] = 0; wrow[warp][32 + lane] = 0;
+            __syncwarp();
 #define PS_HAND_OVER() do {                                                                                               \
                 long long *tr_ = reinterpret_cast<long long *>(buf);          /* 29 x 33 int64 <= TS_CAP float4 */          \
                 __syncwarp();                                                                                             \
@@ -779,8 +782,8 @@ __global__ void __launch_bounds__(TS_BLOCK, 1) icp_persist_kernel(const PersistA
                     if (v_ != 0) {                                                                                        \
                         long long hi_, lo_; s3d_fx_split(v_, hi_, lo_);                                                   \
                         if (lane == 28) { hi_ = 0; lo_ = v_; }                                                            \
-                        if (hi_ != 0) smem_add_i64(&ctot[lane], hi_);                                                     \
-                        smem_add_i64(&ctot[32 + lane], lo_);                                                              \
+                        wrow[warp][lane] += hi_;                                                                          \
+                        wrow[warp][32 + lane] += lo_;                                                                     \
                     }                                                                                                     \
                 }                                                                                                         \
                 __syncwarp();                                                                                             \
@@ -950,6 +953,12 @@ __global__ void __launch_bounds__(TS_BLOCK, 1) icp_persist_kernel(const PersistA
             PHASE(9);
             // ---------------------------------------------------------------- the group's sums, group barrier, solve
             __syncthreads();
+            if (threadIdx.x < S3D_ROW) {
+                long long v = 0;
+                #pragma unroll
+                for (int w = 0; w < TS_WARPS; ++w) v += wrow[w][threadIdx.x];
+                ctot[threadIdx.x] = v;
+            }
             // The per-query state of the next iteration is final (pass 2 wrote it) and does not depend on the pose: its first
             // staging round is issued now, so that its latency is hidden behind the barrier and the solve.
             // The per-query state of the next iteration is final (pass 2 wrote it) and does not depend on the pose: the first staging
@@ -991,10 +1000,10 @@ __global__ void __launch_bounds__(TS_BLOCK, 1) icp_persist_kernel(const PersistA
                     }
                     __syncwarp();
                 }
-            } else if (warp == 0) {
-                total[lane] = lane < 29 ? fx_total<EST>(ctot[lane], ctot[32 + lane], lane, fxs.scale) : 0.0;
+            } else {
+                __syncthreads();                  // (the 64 sums were written by two warps)
+                if (warp == 0) total[lane] = lane < 29 ? fx_total<EST>(ctot[lane], ctot[32 + lane], lane, fxs.scale) : 0.0;
                 __syncwarp();
-                ctot[lane] = 0; ctot[32 + lane] = 0;
             }
             PHASE(11);
             if (threadIdx.x == 0) {
