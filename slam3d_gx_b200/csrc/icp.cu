@@ -801,7 +801,11 @@ __global__ void __launch_bounds__(TS_BLOCK, 1) icp_persist_kernel(const PersistA
             if (!full_search) {
                 int since = 0;
                 for (int c0 = warp; c0 < cta_chunks; c0 += TS_WARPS * PS_STAGE) {
+#ifndef PS_NO_PREFETCH
                     if (c0 != warp) PS_STAGE_ROUND(c0);       // (the first round was issued before the previous iteration's barrier)
+#else
+                    PS_STAGE_ROUND(c0);
+#endif
                     ts_cp_async_wait_all();
                     __syncwarp();
                     constexpr int p1_unroll = PS_P1_UNROLL;
@@ -964,7 +968,9 @@ __global__ void __launch_bounds__(TS_BLOCK, 1) icp_persist_kernel(const PersistA
             // The per-query state of the next iteration is final (pass 2 wrote it) and does not depend on the pose: the first staging
             // round of its streaming pass is issued now, so that its latency hides behind the barrier and the solve.  (Should the next
             // iteration skip the streaming pass after all, the copies are simply drained.)
+#ifndef PS_NO_PREFETCH
             if (!last && warp < cta_chunks) PS_STAGE_ROUND(warp);
+#endif
             if (a.group_ctas > 1) {
                 // the CTA's sums go to the group's accumulators (red.add.u64: integers, order free); then arrive at the barrier
                 long long *g = a.gacc + ((size_t)(epoch % 3u) * a.groups + group) * S3D_ROW;

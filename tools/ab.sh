@@ -23,7 +23,7 @@ print("  batch16 late_iteration_us %.1f  t10 %.2f ms" % ((t40 - t10) / 30 * 1e3,
 PY
 }
 for rep in 1; do
-  for lib in "" _f60890e _c5437e4 _0e3cbc8 _0cdaf40; do
+  for lib in "" _nopf _fences _f60890e; do
     echo "== rep $rep lib '$lib'"
     if [ -z "$lib" ]; then lone X=1; batch X=1; else lone S3D_LIBRARY=$PWD/slam3d_gx_b200/libslam3d_b200$lib.so; batch S3D_LIBRARY=$PWD/slam3d_gx_b200/libslam3d_b200$lib.so; fi
   done
