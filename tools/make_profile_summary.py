@@ -5,7 +5,7 @@ tag, launches, rep = sys.argv[1:4]
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 out_dir = os.path.join(ROOT, "profiles")
 os.makedirs(out_dir, exist_ok=True)
-CMD = "python bench.py --steps 2 --warmup 3 --pool 2 --no-cpu-baseline"
+CMD = "python bench.py --steps 2 --warmup 3 --pool 2 --no-cpu-baseline --no-config4 --no-batch-regime"
 
 rows = [r for r in csv.reader(open(launches)) if len(r) > 5]
 hdr = rows[0]; ki, vi = hdr.index("Kernel Name"), hdr.index("Metric Value")
@@ -52,8 +52,8 @@ with open(os.path.join(out_dir, f"{tag}_icp_persist_full_summary.txt"), "w") as 
     f.write("units: " + " | ".join(rr[1][h.index(w)] if w in h else "?" for w in want) + "\n")
     f.write(f"\nDRAM bytes (read+write) per launch: mean {sum(dram)/len(dram):.0f}, max {max(dram):.0f}; algorithmic bytes per launch "
             f"30 x 14745600 = 442368000.\n")
-    f.write("ncu flushes the caches before every replay: the DRAM bytes are the cold first touch of the ~45 MB working set (source, cell-sorted "
-            "target + normals, touched part of the cell array, per-query state); iterations 2..30 of the launch run out of L2.\n")
+    f.write("ncu flushes the caches before every replay: the DRAM bytes are the cold first touch of the ~40 MB working set (source, cell-sorted "
+            "target + normals, touched part of the cell array, 49 B of per-query state); iterations 2..30 of the launch run out of L2.\n")
     src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
     rows2 = list(csv.reader(io.StringIO(src)))
     # the source page repeats the header per kernel; take the first kernel
