@@ -62,7 +62,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "20", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
@@ -81,7 +81,7 @@ class ClockSampler:
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = sorted({names[i] for r in self.rows if len(r) > 8 for i in range(4) if r[5 + i].lower().startswith("active")})
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+                "reasons": reasons, "samples": len(sm), "window": "warm-up + timed steps (same workload), nvidia-smi every 20 ms"}
 
 
 def config_dict(world, pool):
@@ -135,8 +135,8 @@ def run_reference(args, rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=48)
-    ap.add_argument("--warmup", type=int, default=16)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=40)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--pool", type=int, default=POOL)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -151,7 +151,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
 
     if args.impl == "reference":
-        if args.steps == 48 and args.warmup == 16:      # defaults sized for the GPU arm; keep the CPU arm bounded
+        if args.steps == 200 and args.warmup == 40:     # defaults sized for the GPU arm; keep the CPU arm bounded
             args.steps, args.warmup = 4, 1
         run_reference(args, rank)
         return
@@ -221,6 +221,11 @@ def main():
 
     for k in range(args.pool):      # prime every pair once (first-use device allocations of its index), untimed
         step(k)
+    # clocks / throttle reasons: nvidia-smi sampled every 20 ms from the warm-up steps (the same workload) to the end of the timed region
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)            # nvidia-smi needs a moment to start; its first rows then fall into the warm-up
     for i in range(W):
         step(i)
     finish_gathers()
@@ -229,9 +234,6 @@ def main():
         dist.barrier()
     torch.cuda.synchronize()
 
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     launches0 = ctx.launch_count
     iter_ms, index_ms, iter_launches = 0.0, 0.0, 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -315,11 +317,12 @@ def main():
     planes_roofline = None
     if world == 1:
         cp = ctx.upload(host[0]["tgt"])
+        timed_prm = _abi.plane_params(timed=True)        # per-pass events (the default call replays a CUDA graph and times only the whole)
         for _ in range(3):
-            cp.segment_planes(plane_prm)
+            cp.segment_planes(timed_prm)
         ev, tot, pts = [], [], 0
         for _ in range(10):
-            cp.segment_planes(plane_prm)
+            cp.segment_planes(timed_prm)
             tmp = ctx.last_plane_timing()
             ev.append(tmp["eval_ms"]); tot.append(tmp["total_ms"]); pts = tmp["points_scanned"] * tmp["eval_passes_per_round"]
         cp.free()

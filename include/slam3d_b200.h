@@ -94,7 +94,8 @@ typedef struct s3d_plane_params {
     int32_t  max_planes;         /* 3     (GraphicEnd.cpp:424) */
     int32_t  max_iterations;     /* 50    PCL SACSegmentation max_iterations_ */
     float    probability;        /* 0.99  PCL probability_ */
-    int32_t  reserved;
+    int32_t  reserved;           /* bit 0: time every evaluation pass with its own CUDA events (s3d_last_plane_timing.eval_ms);
+                                    otherwise the launches are replayed from a CUDA graph and only total_ms is measured */
     uint64_t seed;               /* hypothesis stream seed (PCL: mt19937 seeded 12345) */
 } s3d_plane_params;
 

@@ -54,9 +54,9 @@ def icp_params(max_iterations=10, max_corr_dist=0.0, estimator=ESTIMATOR_POINT_T
 
 
 def plane_params(distance_threshold=0.08, plane_percent=0.2, max_planes=3, max_iterations=50,
-                 probability=0.99, seed=12345) -> PlaneParams:
-    """Defaults: reference parameters.yaml:41-47 and PCL-1.7 SACSegmentation."""
-    return PlaneParams(distance_threshold, plane_percent, max_planes, max_iterations, probability, 0, seed)
+                 probability=0.99, seed=12345, timed=False) -> PlaneParams:
+    """Defaults: reference parameters.yaml:41-47 and PCL-1.7 SACSegmentation.  timed: per-pass CUDA events instead of the graph replay."""
+    return PlaneParams(distance_threshold, plane_percent, max_planes, max_iterations, probability, 1 if timed else 0, seed)
 
 
 def camera_c(cam) -> CameraC:

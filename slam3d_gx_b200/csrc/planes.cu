@@ -15,6 +15,7 @@
 // read-back at the end returns the planes.  The PCA sums are order-independent fixed-point sums and the
 // refit runs in strict double (common.cuh), so coefficients and labels equal the oracle's bit for bit.
 #include <cstring>
+#include <cstdlib>
 #include <algorithm>
 #include "context.h"
 #include "common.cuh"
@@ -412,27 +413,65 @@ extern "C" int s3d_segment_planes(s3d_ctx *ctx, s3d_cloud *cloud, const s3d_plan
         for (int k = 0; k < 2; ++k) S3D_CUDA(ctx, cudaEventCreate(&ctx->ev_plane[k]));
         for (int k = 0; k < 2 * S3D_MAX_PLANES; ++k) S3D_CUDA(ctx, cudaEventCreate(&ctx->ev_eval[k]));
     }
-    cudaEventRecord(ctx->ev_plane[0], st);
-    plane_init_kernel<<<g_wide, 256, 0, st>>>(cloud->d_pts, n, rem, cloud->d_labels, cloud->d_nrm, state);
-    S3D_LAUNCHED(ctx);
     // worst-case grids (the first round scans all n points); kernels of rounds the device loop has left return at once
     const dim3 ge(std::max(1, std::min(ctx->sm_count * 4, (n + PLANE_BLOCK - 1) / PLANE_BLOCK)), (n_cand + PLANE_CHUNK - 1) / PLANE_CHUNK);
     const int nb = std::max(1, (n + S3D_COMPACT_BLOCK - 1) / S3D_COMPACT_BLOCK);
-    for (int round = 0; round < prm->max_planes; ++round) {
-        plane_hyp_kernel<<<1, PLANE_MAX_CAND, 0, st>>>(rem, n, prm->plane_percent, prm->max_planes, prm->seed, round, n_cand, coefs, valid, counts, state);
+    const bool timed = (prm->reserved & 1) != 0;         // time every evaluation pass with its own events (s3d_last_plane_timing.eval_ms)
+    // the whole extraction: 1 + 5 * max_planes launches whose arguments are all known here
+    auto launches = [&](bool with_events) -> int {
+        float4 *ra = rem, *rb = rem2;
+        plane_init_kernel<<<g_wide, 256, 0, st>>>(cloud->d_pts, n, ra, cloud->d_labels, cloud->d_nrm, state);
         S3D_LAUNCHED(ctx);
-        cudaEventRecord(ctx->ev_eval[2 * round], st);
-        plane_eval_kernel<<<ge, PLANE_BLOCK, 0, st>>>(rem, coefs, valid, n_cand, tau, counts, prm->max_iterations, (double)prm->probability, state);
-        S3D_LAUNCHED(ctx);
-        cudaEventRecord(ctx->ev_eval[2 * round + 1], st);
-        plane_refit_kernel<<<ctx->sm_count, PLANE_BLOCK, 0, st>>>(rem, tau, cloud->d_absmax, state, partials);   // one CTA per SM: the kernel is mostly its reduction
-        S3D_LAUNCHED(ctx);
-        plane_count_kernel<<<nb, S3D_COMPACT_BLOCK, 0, st>>>(rem, tau, state, blk);
-        S3D_LAUNCHED(ctx);
-        plane_write_kernel<<<nb, S3D_COMPACT_BLOCK, 0, st>>>(rem, rem2, tau, blk, cloud->d_labels, cloud->d_nrm, state);
-        S3D_LAUNCHED(ctx);
-        std::swap(rem, rem2);
+        for (int round = 0; round < prm->max_planes; ++round) {
+            plane_hyp_kernel<<<1, PLANE_MAX_CAND, 0, st>>>(ra, n, prm->plane_percent, prm->max_planes, prm->seed, round, n_cand, coefs, valid, counts, state);
+            S3D_LAUNCHED(ctx);
+            if (with_events) cudaEventRecord(ctx->ev_eval[2 * round], st);
+            plane_eval_kernel<<<ge, PLANE_BLOCK, 0, st>>>(ra, coefs, valid, n_cand, tau, counts, prm->max_iterations, (double)prm->probability, state);
+            S3D_LAUNCHED(ctx);
+            if (with_events) cudaEventRecord(ctx->ev_eval[2 * round + 1], st);
+            plane_refit_kernel<<<ctx->sm_count, PLANE_BLOCK, 0, st>>>(ra, tau, cloud->d_absmax, state, partials);   // one CTA per SM: the kernel is mostly its reduction
+            S3D_LAUNCHED(ctx);
+            plane_count_kernel<<<nb, S3D_COMPACT_BLOCK, 0, st>>>(ra, tau, state, blk);
+            S3D_LAUNCHED(ctx);
+            plane_write_kernel<<<nb, S3D_COMPACT_BLOCK, 0, st>>>(ra, rb, tau, blk, cloud->d_labels, cloud->d_nrm, state);
+            S3D_LAUNCHED(ctx);
+            std::swap(ra, rb);
+        }
+        return S3D_OK;
+    };
+    cudaEventRecord(ctx->ev_plane[0], st);
+    bool done = false;
+    static const bool use_graph = []() { const char *e = getenv("S3D_PLANE_GRAPH"); return !e || atoi(e) != 0; }();
+    if (use_graph && !timed) {
+        // The launches are bound by the host's launch rate (16 small kernels): the sequence is captured once into a CUDA graph keyed
+        // by every buffer and parameter it touches (the ctx pool hands the next frame's cloud the same buffers) and replayed.
+        const void *ptrs[] = {cloud->d_pts, cloud->d_labels, cloud->d_nrm, cloud->d_absmax, ctx->d_seg, (const void *)st, (const void *)"planes"};
+        uint64_t key = 0xcbf29ce484222325ull;
+        auto mix = [&](const void *p_, size_t nb_) { const unsigned char *b = (const unsigned char *)p_; for (size_t i = 0; i < nb_; ++i) { key ^= b[i]; key *= 0x100000001b3ull; } };
+        mix(ptrs, sizeof(ptrs)); mix(&n, sizeof(n)); mix(prm, sizeof(*prm));
+        auto it = ctx->graphs.find(key);
+        if (it == ctx->graphs.end()) {
+            if (ctx->graphs.size() > 256) { for (auto &kv : ctx->graphs) cudaGraphExecDestroy(kv.second); ctx->graphs.clear(); }
+            cudaGraph_t graph = nullptr; cudaGraphExec_t exec = nullptr;
+            const int64_t l0 = ctx->launches;
+            if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+                const int rc = launches(false);
+                const cudaError_t e = cudaStreamEndCapture(st, &graph);
+                ctx->launches = l0;                              // captured, not launched
+                if (rc == S3D_OK && e == cudaSuccess && graph && cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess) {
+                    it = ctx->graphs.emplace(key, exec).first;
+                    ctx->graph_nodes[key] = 1 + 5 * prm->max_planes;
+                }
+                if (graph) cudaGraphDestroy(graph);
+                cudaGetLastError();
+            }
+        }
+        if (it != ctx->graphs.end() && cudaGraphLaunch(it->second, st) == cudaSuccess) {
+            ctx->launches += ctx->graph_nodes[key];
+            done = true;
+        }
     }
+    if (!done) { const int rc = launches(timed); if (rc) return rc; }
     cudaEventRecord(ctx->ev_plane[1], st);
     S3D_CUDA(ctx, cudaMemcpyAsync(hb, state, sizeof(PlaneState), cudaMemcpyDeviceToHost, st));
     S3D_CUDA(ctx, cudaStreamSynchronize(st));
@@ -447,7 +486,7 @@ extern "C" int s3d_segment_planes(s3d_ctx *ctx, s3d_cloud *cloud, const s3d_plan
     for (int k = 0; k < S3D_MAX_PLANES; ++k) if (hb->rem_at_round[k] > 0) { ctx->plane_timing.rounds++; ctx->plane_timing.points_scanned += hb->rem_at_round[k]; }
     ctx->plane_timing.eval_passes_per_round = (int)ge.y;
     ctx->plane_timing.eval_ms = 0.f;
-    for (int k = 0; k < ctx->plane_timing.rounds && k < prm->max_planes; ++k) {
+    for (int k = 0; timed && k < ctx->plane_timing.rounds && k < prm->max_planes; ++k) {
         float e = 0.f;
         cudaEventElapsedTime(&e, ctx->ev_eval[2 * k], ctx->ev_eval[2 * k + 1]);
         ctx->plane_timing.eval_ms += e;

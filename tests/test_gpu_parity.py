@@ -353,7 +353,7 @@ def test_plane_segmentation_parity(ctx, small_cam, kw):
 
 def test_plane_segmentation_full_size_and_icp_with_segmented_normals(ctx, full_pair):
     p = full_pair
-    prm = _abi.plane_params()
+    prm = _abi.plane_params(timed=True)        # per-pass events (the default call replays the launches from a CUDA graph)
     tgt = ctx.upload(p["tgt"])
     planes = tgt.segment_planes(prm)
     got = tgt.download(xyz=False, normals=True, labels=True)
@@ -373,6 +373,14 @@ def test_plane_segmentation_full_size_and_icp_with_segmented_normals(ctx, full_p
     assert np.array_equal(r["T"], oi["T"]) and r["inliers"] == oi["inliers"]
     tm = ctx.last_plane_timing()
     assert tm["rounds"] == 3 and tm["eval_passes_per_round"] == 1 and 307200 < tm["points_scanned"] < 3 * 307200 and 0 < tm["eval_ms"] <= tm["total_ms"]
+    # the graph replay (default parameters) gives the same planes and labels, twice (capture, then replay)
+    t2 = ctx.upload(p["tgt"])
+    for _ in range(2):
+        again = t2.segment_planes(_abi.plane_params())
+        assert [a["inliers"] for a in again] == [a["inliers"] for a in planes] and all(np.array_equal(a["coef"], b["coef"]) for a, b in zip(again, planes))
+        assert np.array_equal(t2.download(xyz=False, labels=True)["labels"], got["labels"])
+        assert ctx.last_plane_timing()["eval_ms"] == 0.0 and ctx.last_plane_timing()["total_ms"] > 0.0
+    t2.free()
     src.free(); tgt.free()
 
 

@@ -6,11 +6,11 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import slam3d_gx_b200 as s3d
 from slam3d_gx_b200 import synth, _abi
 
-reps = int(sys.argv[1]) if len(sys.argv) > 1 else 10
+reps = int(sys.argv[1]) if len(sys.argv) > 1 and sys.argv[1].isdigit() else 10
 ctx = s3d.Context(0)
 p = synth.make_pair(0)
 c = ctx.upload(p["tgt"])
-prm = _abi.plane_params()
+prm = _abi.plane_params(timed="timed" in sys.argv)
 for _ in range(3):
     planes = c.segment_planes(prm)
 ts, ev, tot = [], [], []
@@ -23,4 +23,4 @@ for _ in range(reps):
 tm = ctx.last_plane_timing()
 print(json.dumps({"planes": len(planes), "wall_ms_median": float(np.median(ts)), "device_total_ms_median": float(np.median(tot)),
                   "eval_ms_median": float(np.median(ev)), "rounds": tm["rounds"], "points_scanned": tm["points_scanned"],
-                  "eval_GBps": tm["points_scanned"] * 16 * tm["eval_passes_per_round"] / (float(np.median(ev)) * 1e-3) / 1e9}))
+                  "eval_GBps": tm["points_scanned"] * 16 * tm["eval_passes_per_round"] / max(float(np.median(ev)), 1e-9) / 1e-3 / 1e9}))
