@@ -291,7 +291,7 @@ def main():
 
     # one continuous pipeline: warm-up steps (which also let the index build capture its few launch graphs, one per recurring
     # set of pool buffers) run straight into the timed steps; every timed step issues exactly one upload (of its successor)
-    e2e_steps = max(4, min(args.steps, 16))
+    e2e_steps = max(4, min(args.steps, 64))
     e2e_warm = 8
     nxt = e2e_upload(0)
     t0 = None
