@@ -222,10 +222,9 @@ def main():
     for k in range(args.pool):      # prime every pair once (first-use device allocations of its index), untimed
         step(k)
     # clocks / throttle reasons: nvidia-smi sampled every 20 ms from the warm-up steps (the same workload) to the end of the timed region
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-        time.sleep(0.25)            # nvidia-smi needs a moment to start; its first rows then fall into the warm-up
+    sampler = ClockSampler(local_rank)          # every rank samples its own GPU
+    sampler.start()
+    time.sleep(0.25)                # nvidia-smi needs a moment to start; its first rows then fall into the warm-up
     for i in range(W):
         step(i)
     finish_gathers()
@@ -252,7 +251,7 @@ def main():
     torch.cuda.synchronize()
     elapsed_ms = e0.elapsed_time(e1)
     launches = ctx.launch_count - launches0
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop()
     assert last.status == 0, "registration failed inside the timed region"
 
     # ---- e2e: host buffers through the C ABI (upload + plane extraction + registration + read-back) ------
@@ -380,6 +379,8 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
         c4_l0 = ctx.launch_count
+        c4_sampler = ClockSampler(local_rank)
+        c4_sampler.start()
         c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         c0.record(stream)
         c4_dev_ms = 0.0
@@ -393,11 +394,12 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
         c4_ms = c0.elapsed_time(c1)
+        c4_clocks = c4_sampler.stop()
         ok = [allr[r * n_slot + k].status for r in range(world) for k in range(len(sharding.partition(n_total, world, r)))]
         assert len(ok) == n_total and all(st == 0 for st in ok), "config 4: a pair failed or a record is missing"
         # every rank holds every record: pair 0's pose as rank 0 computed it must be what this rank received
         config4 = {"ms": c4_ms, "dev_ms": c4_dev_ms, "launches": ctx.launch_count - c4_l0, "steps": c4_steps, "pairs_total": n_total,
-                   "pairs_per_gpu": per_rank, "iterations": C4_ITERS, "T0": [allr[0].T[k] for k in range(12)]}
+                   "pairs_per_gpu": per_rank, "iterations": C4_ITERS, "T0": [allr[0].T[k] for k in range(12)], "clocks": c4_clocks}
 
     # ---- max over ranks --------------------------------------------------------------------------------
     t = torch.tensor([elapsed_ms, e2e_s * 1e3, iter_ms, config4["ms"] if config4 else 0.0], dtype=torch.float64, device="cuda")
@@ -414,7 +416,14 @@ def main():
             t0ref = t0c.clone()
             dist.broadcast(t0ref, src=0)
             assert torch.equal(t0c, t0ref), "config 4: gathered records differ between ranks"
-    elapsed_rank_ms = elapsed_ms
+    per_rank = [{"rank": rank, "elapsed_ms": elapsed_ms, "sm_mhz": clocks.get("sm_mhz"), "reasons": clocks.get("reasons"),
+                 "config4_ms": config4["ms"] if config4 else None, "config4_device_ms": config4["dev_ms"] if config4 else None,
+                 "config4_sm_mhz": config4["clocks"].get("sm_mhz") if config4 else None,
+                 "config4_reasons": config4["clocks"].get("reasons") if config4 else None}]
+    if world > 1:
+        gathered = [None] * world
+        dist.all_gather_object(gathered, per_rank[0])
+        per_rank = gathered
     elapsed_ms, e2e_ms, iter_ms_max, c4_ms_max = [float(x) for x in t.tolist()]
     total_launches = int(cnt[0].item())
 
@@ -449,6 +458,7 @@ def main():
                          "note": "achieved = algorithmic bytes (16N+32M per iteration, SURVEY.md 8d) / measured kernel time; the single-pair working set (~45 MB) is L2 resident, so the kernel is bound by search issue slots and per-iteration barrier latency, not by HBM"},
             "breakdown_ms_per_step": {"index_build": index_ms / args.steps, "iterations": iter_ms / args.steps},
             "elapsed_ms_ranks": {"min": float(tmin[0].item()), "max": float(tmax2[0].item())},
+            "per_rank": per_rank,
         }
         if config4:
             c4_its = config4["pairs_total"] * config4["iterations"] * config4["steps"] / (c4_ms_max * 1e-3)
