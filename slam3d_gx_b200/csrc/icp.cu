@@ -807,6 +807,7 @@ __global__ void __launch_bounds__(TS_BLOCK, 1) icp_persist_kernel(const PersistA
                     PS_STAGE_ROUND(c0);
 #endif
                     ts_cp_async_wait_all();
+                    if (c0 == warp) PHASE(13);
                     __syncwarp();
                     constexpr int p1_unroll = PS_P1_UNROLL;
                     #pragma unroll p1_unroll
@@ -881,7 +882,9 @@ __global__ void __launch_bounds__(TS_BLOCK, 1) icp_persist_kernel(const PersistA
                     since += PS_STAGE;
                     if (since >= S3D_FX_SEGMENT - PS_STAGE) { PS_HAND_OVER(); since = 0; }      // warp-uniform
                 }
+                PHASE(14);
                 PS_HAND_OVER();
+                PHASE(15);
                 __threadfence_block();
                 __syncthreads();                  // the pending list is complete
             }

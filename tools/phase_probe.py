@@ -22,4 +22,4 @@ for k in (1, 2, 3, 4, 6, 10, 20, 30):
     print(f"iterations {k:2d}: cumulative us " + " ".join(f"{names[i]}={cur[i] / 1965.0:8.1f}" for i in sorted(names)), flush=True)
 a, b = run(20), run(30)
 d = (b - a) / 10 / 1965.0
-print("late iteration (avg of 20..29), CTA 0, us: " + " ".join(f"{n}={d[i]:.2f}" for i, n in ((8, "pass1"), (9, "pass2"), (10, "barrier"), (11, "totals"), (12, "solve"))))
+print("late iteration (avg of 20..29), CTA 0, us: " + " ".join(f"{n}={d[i]:.2f}" for i, n in ((13, "p1:wait-for-staged-loads"), (14, "p1:chunks"), (15, "p1:hand-over"), (8, "p1:sync"), (9, "pass2"), (10, "barrier"), (11, "totals"), (12, "solve"))))
