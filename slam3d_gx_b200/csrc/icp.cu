@@ -894,15 +894,12 @@ __global__ void __launch_bounds__(TS_BLOCK, 1) icp_persist_kernel(const PersistA
             // Warps take items (item_octets octets, one per 8 lanes) from the CTA's list until it is empty.
             {
                 const int n_items = full_search ? cta_units : pend_count;
-                // item_octets octets per item while plenty are left; single octets for the last ones (and in late iterations, where
-                // only a few are pending at all), so that no warp is still busy with a long item while the others have run dry
+                // few octets left (late iterations): one per item, so that a lone search is not queued behind another one
+                const int item = n_items <= 2 * TS_WARPS ? 1 : a.item_octets;
                 while (n_items > 0) {
-                    int e0 = 0, item = 1;
-                    if (lane == 0) {
-                        item = (n_items - *(volatile int *)&pend_next > 3 * TS_WARPS * a.item_octets) ? a.item_octets : 1;
-                        e0 = atomicAdd(&pend_next, item);
-                    }
-                    e0 = __shfl_sync(full, e0, 0); item = __shfl_sync(full, item, 0);
+                    int e0 = 0;
+                    if (lane == 0) e0 = atomicAdd(&pend_next, item);
+                    e0 = __shfl_sync(full, e0, 0);
                     if (e0 >= n_items) break;
                     const int e = e0 + (lane >> 3);
                     uint32_t ent = 0u;
