@@ -958,6 +958,12 @@ __global__ void __launch_bounds__(TS_BLOCK, 1) icp_persist_kernel(const PersistA
                 }
             }
             PHASE(9);
+#if defined(S3D_PHASES)
+            if (blockIdx.x == 0 && threadIdx.x == 0) {
+                #pragma unroll
+                for (int k = 0; k < 5; ++k) atomicAdd(&g_stats[21 + k], (unsigned long long)tm[k]);
+            }
+#endif
             // ---------------------------------------------------------------- the group's sums, group barrier, solve
             __syncthreads();
             if (threadIdx.x < S3D_ROW) {
