@@ -964,22 +964,67 @@ __global__ void __launch_bounds__(TS_BLOCK, 1) icp_persist_kernel(const PersistA
                 for (int k = 0; k < 5; ++k) atomicAdd(&g_stats[21 + k], (unsigned long long)tm[k]);
             }
 #endif
-            // ---------------------------------------------------------------- the group's sums, group barrier, solve
+            // ---------------------------------------------------------------- the group's sums, solve
             __syncthreads();
+            // The per-query state of the next iteration is final (pass 2 wrote it) and does not depend on the pose: the first staging
+            // round of its streaming pass is issued now, so that its latency hides behind the group sum and the solve.  (Should the next
+            // iteration skip the streaming pass after all, the copies are simply drained.)
+#ifndef PS_NO_PREFETCH
+            if (!last && warp < cta_chunks) PS_STAGE_ROUND(warp);
+#endif
+#ifndef PS_BARRIER_CLASSIC
+            // Self-validating group sums: there is no barrier.  Lane k of warp 0 owns slot k: it adds the CTA's (hi, lo) to the group's
+            // two words of the slot with ONE atomic each, and every atomic also carries +1 in bits 48.. of the word.  A word whose
+            // count has reached the number of CTAs of the group holds the complete sum: the lane polls its own two words, nothing
+            // else is waited for (no arrive counter, no release/acquire round trip between the data and a flag).  The sums are
+            // normalised per CTA (0 <= lo < 2^32, |hi| < 2^47 for up to 2^30 terms), so the count never meets the value.
+            // Three buffers by epoch: one being added to, one being read, one being zeroed (by rank 0, when it has seen epoch e
+            // complete: every CTA has then finished reading epoch e-1, whose buffer is used again at e+2; rank 0's adds of epoch
+            // e+1 are release operations, so the zeros are in place before anybody can see e+1 complete and move on to e+2).
+            if (warp == 0) {
+                long long hi = 0, lo = 0;
+                if (lane < 29) {
+                    #pragma unroll
+                    for (int w = 0; w < TS_WARPS; ++w) { hi += wrow[w][lane]; lo += wrow[w][32 + lane]; }
+                    hi += lo >> 32; lo &= 0xffffffffll;
+                }
+                if (a.group_ctas > 1) {
+                    long long *g = a.gacc + ((size_t)(epoch % 3u) * a.groups + group) * S3D_ROW;
+                    const long long one = 1ll << 48;
+                    if (lane < 29) {
+                        if (rank == 0) {
+                            asm volatile("red.release.gpu.global.add.u64 [%0], %1;" ::"l"(&g[lane]), "l"(hi + one) : "memory");
+                            asm volatile("red.release.gpu.global.add.u64 [%0], %1;" ::"l"(&g[32 + lane]), "l"(lo + one) : "memory");
+                        } else {
+                            atomicAdd(reinterpret_cast<unsigned long long *>(&g[lane]), (unsigned long long)(hi + one));
+                            atomicAdd(reinterpret_cast<unsigned long long *>(&g[32 + lane]), (unsigned long long)(lo + one));
+                        }
+                        const long long n = (long long)a.group_ctas;
+                        long long wh, wl;
+                        do {
+                            asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(wh) : "l"(&g[lane]) : "memory");
+                            asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(wl) : "l"(&g[32 + lane]) : "memory");
+                        } while (((wh + (one >> 1)) >> 48) < n || (wl >> 48) < n);
+                        hi = wh - (n << 48); lo = wl - (n << 48);
+                    }
+                    ++epoch;
+                    __syncwarp();
+                    PHASE(10);
+                    if (rank == 0) {
+                        long long *gz = a.gacc + ((size_t)((epoch + 1u) % 3u) * a.groups + group) * S3D_ROW;
+                        __stcg(&gz[lane], 0ll); __stcg(&gz[32 + lane], 0ll);
+                    }
+                }
+                total[lane] = lane < 29 ? fx_total<EST>(hi, lo, lane, fxs.scale) : 0.0;
+                __syncwarp();
+            } else if (a.group_ctas > 1) ++epoch;
+#else
             if (threadIdx.x < S3D_ROW) {
                 long long v = 0;
                 #pragma unroll
                 for (int w = 0; w < TS_WARPS; ++w) v += wrow[w][threadIdx.x];
                 ctot[threadIdx.x] = v;
             }
-            // The per-query state of the next iteration is final (pass 2 wrote it) and does not depend on the pose: its first
-            // staging round is issued now, so that its latency is hidden behind the barrier and the solve.
-            // The per-query state of the next iteration is final (pass 2 wrote it) and does not depend on the pose: the first staging
-            // round of its streaming pass is issued now, so that its latency hides behind the barrier and the solve.  (Should the next
-            // iteration skip the streaming pass after all, the copies are simply drained.)
-#ifndef PS_NO_PREFETCH
-            if (!last && warp < cta_chunks) PS_STAGE_ROUND(warp);
-#endif
             if (a.group_ctas > 1) {
                 // the CTA's sums go to the group's accumulators (red.add.u64: integers, order free); then arrive at the barrier
                 long long *g = a.gacc + ((size_t)(epoch % 3u) * a.groups + group) * S3D_ROW;
@@ -993,15 +1038,9 @@ __global__ void __launch_bounds__(TS_BLOCK, 1) icp_persist_kernel(const PersistA
                 if (warp == 0) {
                     if (lane == 0) {
                         // release (the CTA's atomics, issued by other threads before the __syncthreads above) -> arrive -> wait -> acquire
-#ifdef PS_BARRIER_FENCES
-                        __threadfence();
-#endif
                         red_release_add_u32(bar, 1u);
                         const unsigned target = epoch * (unsigned)a.group_ctas;
                         while (ld_acquire_u32(bar) < target) { }
-#ifdef PS_BARRIER_FENCES
-                        __threadfence();
-#endif
                     }
                     __syncwarp();
                     PHASE(10);
@@ -1020,6 +1059,7 @@ __global__ void __launch_bounds__(TS_BLOCK, 1) icp_persist_kernel(const PersistA
                 if (warp == 0) total[lane] = lane < 29 ? fx_total<EST>(ctot[lane], ctot[32 + lane], lane, fxs.scale) : 0.0;
                 __syncwarp();
             }
+#endif
             PHASE(11);
             if (threadIdx.x == 0) {
                 solve_and_update<EST>(total, &st, a.min_corr, a.pivot_eps);
