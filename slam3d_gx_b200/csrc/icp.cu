@@ -1188,12 +1188,12 @@ int s3d_register_issue(s3d_ctx *ctx, const s3d_cloud *const *src, const s3d_clou
         const int p_res = ctx->persist_resident[plane ? 0 : 1];
         const int chunks_per_cta = 2 * TS_WARPS;      // at least two chunks of 32 queries per warp before a pair is spread wider
         const int useful = std::max(1, (n_max + 32 * chunks_per_cta - 1) / (32 * chunks_per_cta));
-        // Up to 16 pairs: one group each, all at once.  Larger batches: fewer, larger groups that walk the batch in >= 16 rounds
-        // (4 groups for 64 pairs, 16 from 256 pairs on).  One small group per pair -- every pair at once -- made the launch as long as
-        // its most expensive pair and left 148 mod n_pairs SMs idle: 54.1 / 64.5 ms for two 64-pair shards of config 4 against
-        // 38.6 / 40.0 ms with 4 groups of 37 CTAs.  (Larger groups pay the per-iteration barrier + solve on more SMs: for 16 pairs
-        // 9-CTA groups keep a late iteration at 87 us where 49-CTA groups need 129 us.)
-        const int max_groups = n_pairs <= 16 ? n_pairs : std::max(4, std::min(16, n_pairs / 16));
+        // Up to 16 pairs: one group each, all at once.  Larger batches: 4 groups of a quarter of the chip each walk the batch in
+        // rounds.  One small group per pair -- every pair at once -- made the launch as long as its most expensive pair and left
+        // 148 mod n_pairs SMs idle: 54.1 / 64.5 ms for two 64-pair shards of config 4 against 38.6 / 40.0 ms with 4 groups of 37
+        // CTAs (128 pairs: 75.5 / 75.8 / 73.6 ms with groups of 9 / 18 / 37).  Larger groups pay the per-iteration group sum +
+        // solve on more SMs: for 16 pairs 9-CTA groups keep a late iteration at 87 us where 49-CTA groups need 129 us.
+        const int max_groups = n_pairs <= 16 ? n_pairs : 4;
         p_group_ctas = std::max(1, std::min(useful, p_res / std::min(max_groups, p_res)));
         { static const char *e = getenv("S3D_GROUP_CTAS"); const int v = e ? atoi(e) : 0; if (v > 0) p_group_ctas = std::max(1, std::min(std::min(useful, p_res), v)); }
         p_groups = std::max(1, std::min(n_pairs, p_res / p_group_ctas));
