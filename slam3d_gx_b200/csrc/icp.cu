@@ -609,6 +609,11 @@ static_assert(TS_CAP * 16 >= 29 * 33 * 8, "the warp tile also carries the transp
 #define PS_FLAG_TIE 64u
 #define PS_FLAG_NRM 128u
 
+#if defined(S3D_PHASES)
+__device__ unsigned long long g_cta_t[148 * 8];      // debug: %globaltimer at the end of the search pass of iterations 0..7, per CTA
+extern "C" int s3d_debug_cta_times(unsigned long long *out) { cudaDeviceSynchronize(); return (int)cudaMemcpyFromSymbol(out, g_cta_t, sizeof(g_cta_t)); }
+__device__ __forceinline__ unsigned long long ps_globaltimer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#endif
 #if defined(S3D_STATS) || defined(S3D_PHASES)
 #define PHASE_T0() long long ph_t = clock64()
 #define PHASE(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) { long long n_ = clock64(); atomicAdd(&g_stats[i], (unsigned long long)(n_ - ph_t)); ph_t = n_; } } while (0)
@@ -698,7 +703,9 @@ __global__ void __launch_bounds__(TS_BLOCK, 1) icp_persist_kernel(const PersistA
     }
     __syncthreads();
 #endif
+#ifdef PS_BARRIER_CLASSIC
     unsigned *bar = a.barriers + group;
+#endif
     unsigned epoch = 0;
     const float gate_r = a.max_d2 < INFINITY ? sqrtf(a.max_d2) : INFINITY;
     uint32_t *my_pend = a.pend + (size_t)blockIdx.x * a.pend_stride;
@@ -959,6 +966,8 @@ __global__ void __launch_bounds__(TS_BLOCK, 1) icp_persist_kernel(const PersistA
             }
             PHASE(9);
 #if defined(S3D_PHASES)
+            __syncthreads();
+            if (threadIdx.x == 0 && it < 8 && blockIdx.x < 148) g_cta_t[blockIdx.x * 8 + it] = ps_globaltimer();
             if (blockIdx.x == 0 && threadIdx.x == 0) {
                 #pragma unroll
                 for (int k = 0; k < 5; ++k) atomicAdd(&g_stats[21 + k], (unsigned long long)tm[k]);
