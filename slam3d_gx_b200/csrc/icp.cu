@@ -745,6 +745,7 @@ __global__ void __launch_bounds__(TS_BLOCK, 1) icp_persist_kernel(const PersistA
         // stage PS_STAGE chunks of per-query state (49 B per query) into the warp's tile: every load in flight at once, no registers
 #define PS_STAGE_ROUND(c0_) do {                                                                                                      \
             _Pragma("unroll") for (int s_ = 0; s_ < (int)PS_STAGE; ++s_) {                                                            \
+                if (4 * ((c0_) + s_ * TS_WARPS) >= cta_units) break;                               /* warp-uniform */                 \
                 const int m_ = 4 * ((c0_) + s_ * TS_WARPS) + (lane >> 3);                                                             \
                 const int i_ = ((rank + a.group_ctas * m_) << 3) + (lane & 7);                                                        \
                 if (m_ < cta_units && i_ < d.n_src) {                                                                                 \
@@ -780,18 +781,21 @@ __global__ void __launch_bounds__(TS_BLOCK, 1) icp_persist_kernel(const PersistA
 #define PS_HAND_OVER() do {                                                                                               \
                 long long *tr_ = reinterpret_cast<long long *>(buf);          /* 29 x 33 int64 <= TS_CAP float4 */          \
                 __syncwarp();                                                                                             \
-                _Pragma("unroll") for (int k = 0; k < 28; ++k) tr_[k * 33 + lane] = fx_unbias<EST>(acc[k], k, cnt, mbits); \
+                /* raw (wrapping) sums: the bias count * bits(M) of a slot is removed once, after the 32 lanes are added */ \
+                _Pragma("unroll") for (int k = 0; k < 28; ++k) tr_[k * 33 + lane] = acc[k];                               \
                 tr_[28 * 33 + lane] = (long long)cnt;                                                                     \
                 __syncwarp();                                                                                             \
+                long long v_ = 0;                                                                                         \
                 if (lane < 29) {                                                                                          \
-                    long long v_ = 0;                                                                                     \
                     _Pragma("unroll 8") for (int l = 0; l < 32; ++l) v_ += tr_[lane * 33 + l];                            \
-                    if (v_ != 0) {                                                                                        \
-                        long long hi_, lo_; s3d_fx_split(v_, hi_, lo_);                                                   \
-                        if (lane == 28) { hi_ = 0; lo_ = v_; }                                                            \
-                        wrow[warp][lane] += hi_;                                                                          \
-                        wrow[warp][32 + lane] += lo_;                                                                     \
-                    }                                                                                                     \
+                }                                                                                                         \
+                const long long cn_ = __shfl_sync(full, v_, 28);                                                          \
+                if (lane < 28) v_ = fx_slot_used<EST>(lane) ? v_ - (long long)((unsigned long long)cn_ * mbits) : 0ll;    \
+                if (lane < 29 && v_ != 0) {                                                                               \
+                    long long hi_, lo_; s3d_fx_split(v_, hi_, lo_);                                                       \
+                    if (lane == 28) { hi_ = 0; lo_ = v_; }                                                                \
+                    wrow[warp][lane] += hi_;                                                                              \
+                    wrow[warp][32 + lane] += lo_;                                                                         \
                 }                                                                                                         \
                 __syncwarp();                                                                                             \
                 _Pragma("unroll") for (int k = 0; k < 29; ++k) acc[k] = 0;                                                \
