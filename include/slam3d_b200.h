@@ -225,6 +225,18 @@ int  s3d_register_pair(s3d_ctx *ctx, const s3d_cloud *src, const s3d_cloud *tgt,
  * debugging / parity aid */
 int  s3d_last_correspondences(s3d_ctx *ctx, int32_t *idx_out, int n);
 int  s3d_last_timing(const s3d_ctx *ctx, s3d_timing *out);
+
+/* A stream of independent single-pair registrations without a host round trip per pair -- the loop over loop-closure
+ * candidates of reference src/GraphicEnd.cpp:729-761 when its results are only needed after the loop.  s3d_register_enqueue
+ * issues one registration on the context's stream and forms its result record on the device; s3d_register_drain waits for
+ * everything enqueued since the last drain and returns the records (and, when timing_out is not NULL, the device times of
+ * each) in enqueue order with ONE device-to-host copy.  At most S3D_ASYNC_DEPTH pairs may be outstanding (S3D_E_STATE
+ * beyond that: drain first).  The clouds must stay alive and unmodified until the drain.  Results are bit-identical to
+ * s3d_register_pair. */
+#define S3D_ASYNC_DEPTH 64
+int  s3d_register_enqueue(s3d_ctx *ctx, const s3d_cloud *src, const s3d_cloud *tgt, const double *guess /* 16 doubles or NULL */,
+                          const s3d_icp_params *params);
+int  s3d_register_drain(s3d_ctx *ctx, s3d_result *results_out, s3d_timing *timing_out /* may be NULL */, int capacity, int *n_out);
 void s3d_icp_params_default(s3d_icp_params *p);
 void s3d_plane_params_default(s3d_plane_params *p);
 int  s3d_last_plane_timing(const s3d_ctx *ctx, s3d_plane_timing *out);

@@ -34,8 +34,9 @@ EXPORTS = [
     "s3d_last_correspondences", "s3d_last_timing", "s3d_icp_params_default", "s3d_plane_params_default",
     "s3d_planar_keypoints", "s3d_gather_results", "s3d_cloud_passthrough_z", "s3d_cloud_voxel_grid", "s3d_cloud_transform",
     "s3d_cloud_concat", "s3d_map_fuse", "s3d_cloud_from_depth_normals", "s3d_cloud_upload_async", "s3d_cloud_wait", "s3d_host_alloc", "s3d_host_free",
-    "s3d_memory_stats", "s3d_last_plane_timing", "s3d_comm_unique_id", "s3d_comm_create", "s3d_comm_destroy", "s3d_register_batch_gather",
+    "s3d_memory_stats", "s3d_last_plane_timing", "s3d_comm_unique_id", "s3d_comm_create", "s3d_comm_destroy", "s3d_register_batch_gather", "s3d_register_enqueue", "s3d_register_drain",
 ]
+ASYNC_DEPTH = 64          # S3D_ASYNC_DEPTH
 COMM_ID_BYTES = 128
 
 
@@ -82,6 +83,8 @@ def load_library():
     lib.s3d_register_pair.argtypes = [vp, vp, vp, vp, C.POINTER(_abi.IcpParams), C.POINTER(_abi.Result)]
     lib.s3d_last_correspondences.argtypes = [vp, vp, ci]
     lib.s3d_last_timing.argtypes = [vp, C.POINTER(_abi.Timing)]
+    lib.s3d_register_enqueue.argtypes = [vp, vp, vp, vp, C.POINTER(_abi.IcpParams)]
+    lib.s3d_register_drain.argtypes = [vp, C.POINTER(_abi.Result), C.POINTER(_abi.Timing), ci, C.POINTER(ci)]
     lib.s3d_icp_params_default.argtypes = [C.POINTER(_abi.IcpParams)]
     lib.s3d_icp_params_default.restype = None
     lib.s3d_plane_params_default.argtypes = [C.POINTER(_abi.PlaneParams)]
@@ -291,6 +294,29 @@ class Context:
         if raw:
             return res
         return [_abi.result_to_dict(res[i]) for i in range(n)]
+
+    def register_enqueue(self, src, tgt, guess=None, params: _abi.IcpParams | None = None):
+        """One registration issued without waiting for it (s3d_register_enqueue); at most ASYNC_DEPTH outstanding."""
+        params = params or _abi.icp_params()
+        g = None
+        if guess is not None:
+            g = np.ascontiguousarray(guess, dtype=np.float64).reshape(16)
+        self._check(self.lib.s3d_register_enqueue(self.h, src.handle, tgt.handle, g.ctypes.data if g is not None else None, C.byref(params)))
+
+    def register_drain(self, raw: bool = False):
+        """Results (enqueue order) and device timings of everything enqueued since the last drain (s3d_register_drain)."""
+        res = (_abi.Result * ASYNC_DEPTH)()
+        tms = (_abi.Timing * ASYNC_DEPTH)()
+        n = C.c_int(0)
+        self._check(self.lib.s3d_register_drain(self.h, res, tms, ASYNC_DEPTH, C.byref(n)))
+        timings = [dict(index_ms=tms[i].index_ms, iterate_ms=tms[i].iterate_ms, iter_launches=tms[i].iter_launches,
+                        total_launches=tms[i].total_launches) for i in range(n.value)]
+        if raw:
+            out = (_abi.Result * n.value)()
+            for i in range(n.value):
+                out[i] = res[i]
+            return out, timings
+        return [_abi.result_to_dict(res[i]) for i in range(n.value)], timings
 
     # ---- multi-GPU: one shard per rank, one pose gather (SURVEY.md 8e) -------------------------------------------
     @staticmethod

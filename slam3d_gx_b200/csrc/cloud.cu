@@ -135,6 +135,11 @@ extern "C" void s3d_destroy(s3d_ctx *ctx)
     cudaFree(ctx->d_seg);
     cudaFree(ctx->d_gather_send); cudaFree(ctx->d_gather_recv);
     if (ctx->h_gather) cudaFreeHost(ctx->h_gather);
+    if (ctx->h_desc_ring) cudaFreeHost(ctx->h_desc_ring);
+    if (ctx->h_state_ring) cudaFreeHost(ctx->h_state_ring);
+    if (ctx->h_async) cudaFreeHost(ctx->h_async);
+    cudaFree(ctx->d_async);
+    for (int i = 0; i < S3D_ASYNC_DEPTH; ++i) for (int k = 0; k < 3; ++k) if (ctx->ev_ring[i][k]) cudaEventDestroy(ctx->ev_ring[i][k]);
     s3d_dev_pool_release(ctx);
     for (auto &kv : ctx->pool_live) cudaFree(kv.first);     // handles the caller never freed
     ctx->pool_live.clear();
@@ -143,6 +148,7 @@ extern "C" void s3d_destroy(s3d_ctx *ctx)
     for (int i = 0; i < 2; ++i) if (ctx->ev_plane[i]) cudaEventDestroy(ctx->ev_plane[i]);
     for (int i = 0; i < 2 * S3D_MAX_PLANES; ++i) if (ctx->ev_eval[i]) cudaEventDestroy(ctx->ev_eval[i]);
     if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); cudaEventDestroy(ctx->copy_fence); }
+    if (ctx->aux_stream) { cudaStreamSynchronize(ctx->aux_stream); cudaStreamDestroy(ctx->aux_stream); cudaEventDestroy(ctx->aux_fork); cudaEventDestroy(ctx->aux_join); }
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }

@@ -90,6 +90,8 @@ struct s3d_ctx {
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;   // uploads of the NEXT frame while the ctx stream registers the current one
     cudaEvent_t copy_fence = nullptr;     // orders the copy stream behind what the ctx stream has been given so far
+    cudaStream_t aux_stream = nullptr;    // second branch of the index build (grid.cu)
+    cudaEvent_t aux_fork = nullptr, aux_join = nullptr;
     std::string err;
     int64_t launches = 0;
     // batch scratch (grown on demand)
@@ -113,6 +115,14 @@ struct s3d_ctx {
     size_t cap_gather_send = 0, cap_gather_recv = 0, cap_gather_host = 0;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     s3d_timing timing = {0, 0, 0, 0};
+    // stream of single-pair registrations (s3d_register_enqueue / s3d_register_drain): per outstanding pair a page-locked
+    // staging slot for its descriptor + initial state, three events, and a result record formed on the device
+    PairDesc *h_desc_use = nullptr; PairState *h_state_use = nullptr; cudaEvent_t *ev_use = nullptr;   // where s3d_register_issue stages / records (null: h_desc, h_state, ev)
+    PairDesc *h_desc_ring = nullptr; PairState *h_state_ring = nullptr;
+    s3d_result *d_async = nullptr, *h_async = nullptr;
+    cudaEvent_t ev_ring[S3D_ASYNC_DEPTH][3] = {};
+    bool async_built[S3D_ASYNC_DEPTH] = {}; int async_launches[S3D_ASYNC_DEPTH] = {}; int async_total_launches[S3D_ASYNC_DEPTH] = {};
+    int async_n = 0;
     cudaEvent_t ev_plane[2] = {nullptr, nullptr};
     cudaEvent_t ev_eval[2 * S3D_MAX_PLANES] = {};       // around the evaluation pass of each RANSAC round
     s3d_plane_timing plane_timing = {0, 0, 0, 0, 0, 0};

@@ -245,10 +245,9 @@ static int grid_ensure_buffers(s3d_ctx *ctx, GridIndex &g, bool with_normals, in
 }
 
 // The launches that build (or rebuild) the index: nothing but kernel launches on ctx->stream, so the sequence can be captured.
-static int grid_launch(s3d_ctx *ctx, GridIndex &g, const float4 *d_pts, const float4 *d_nrm, int n, float cell, float scale,
+static int grid_launch(s3d_ctx *ctx, cudaStream_t st, GridIndex &g, const float4 *d_pts, const float4 *d_nrm, int n, float cell, float scale,
                        uint32_t max_cells)
 {
-    cudaStream_t st = ctx->stream;
     const int wide = ctx->sm_count * 8;
     const int scan_blocks = (int)(max_cells / SCAN_TILE) + 1;
     bbox_init_kernel<<<1, 32, 0, st>>>(g.d_bbox); S3D_LAUNCHED(ctx);
@@ -269,13 +268,26 @@ static int grid_launch(s3d_ctx *ctx, GridIndex &g, const float4 *d_pts, const fl
 
 static int build_launches(s3d_ctx *ctx, s3d_cloud *c, float cell, float scale, bool want_coarse, int nc)
 {
-    int rc = grid_launch(ctx, c->grid, c->d_pts, c->d_nrm, c->n, cell, scale, S3D_GRID_MAX_CELLS);
-    if (rc) return rc;
+    // The decimated seeding index (every S3D_COARSE_STRIDE-th point: first-iteration seeds, see icp.cu) depends on nothing the
+    // full index produces: its ten small launches run on a second stream beside the nine of the full index (fork / join by
+    // events; captured, they become two parallel branches of the graph).
     if (want_coarse) {
-        // coarse seeding index over every S3D_COARSE_STRIDE-th point (first-iteration seeds, see icp.cu)
-        decimate_kernel<<<std::min(ctx->sm_count * 8, (nc + 255) / 256), 256, 0, ctx->stream>>>(c->d_pts, nc, S3D_COARSE_STRIDE, c->d_coarse_pts);
+        if (!ctx->aux_stream) {
+            S3D_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
+            S3D_CUDA(ctx, cudaEventCreateWithFlags(&ctx->aux_fork, cudaEventDisableTiming));
+            S3D_CUDA(ctx, cudaEventCreateWithFlags(&ctx->aux_join, cudaEventDisableTiming));
+        }
+        S3D_CUDA(ctx, cudaEventRecord(ctx->aux_fork, ctx->stream));
+        S3D_CUDA(ctx, cudaStreamWaitEvent(ctx->aux_stream, ctx->aux_fork, 0));
+        decimate_kernel<<<std::min(ctx->sm_count * 8, (nc + 255) / 256), 256, 0, ctx->aux_stream>>>(c->d_pts, nc, S3D_COARSE_STRIDE, c->d_coarse_pts);
         S3D_LAUNCHED(ctx);
-        rc = grid_launch(ctx, c->coarse, c->d_coarse_pts, nullptr, nc, 0.f, scale, S3D_COARSE_MAX_CELLS);
+        int rc = grid_launch(ctx, ctx->aux_stream, c->coarse, c->d_coarse_pts, nullptr, nc, 0.f, scale, S3D_COARSE_MAX_CELLS);
+        if (rc) return rc;
+    }
+    int rc = grid_launch(ctx, ctx->stream, c->grid, c->d_pts, c->d_nrm, c->n, cell, scale, S3D_GRID_MAX_CELLS);
+    if (want_coarse) {
+        S3D_CUDA(ctx, cudaEventRecord(ctx->aux_join, ctx->aux_stream));
+        S3D_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->aux_join, 0));
     }
     return rc;
 }

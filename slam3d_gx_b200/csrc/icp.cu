@@ -1215,7 +1215,10 @@ int s3d_register_issue(s3d_ctx *ctx, const s3d_cloud *const *src, const s3d_clou
     int rc = ensure_batch(ctx, n_pairs, ctas);
     if (rc) return rc;
 
-    cudaEventRecord(ctx->ev[0], ctx->stream);
+    cudaEvent_t *evs = ctx->ev_use ? ctx->ev_use : ctx->ev;
+    PairDesc *h_desc = ctx->h_desc_use ? ctx->h_desc_use : ctx->h_desc;
+    PairState *h_state = ctx->h_state_use ? ctx->h_state_use : ctx->h_state;
+    cudaEventRecord(evs[0], ctx->stream);
     bool built = false;
     if (use_grid) {
         for (int i = 0; i < n_pairs; ++i) {
@@ -1227,7 +1230,7 @@ int s3d_register_issue(s3d_ctx *ctx, const s3d_cloud *const *src, const s3d_clou
             if (stale) { rc = s3d_grid_build(ctx, t, prm->grid_cell); if (rc) return rc; built = true; }
         }
     }
-    cudaEventRecord(ctx->ev[1], ctx->stream);
+    cudaEventRecord(evs[1], ctx->stream);
 
     if (!persist) {
         size_t need = (size_t)n_pairs * n_max;
@@ -1277,7 +1280,7 @@ int s3d_register_issue(s3d_ctx *ctx, const s3d_cloud *const *src, const s3d_clou
     } else ctx->last_nn_n = 0;
 
     for (int i = 0; i < n_pairs; ++i) {
-        PairDesc &d = ctx->h_desc[i];
+        PairDesc &d = h_desc[i];
         d.src = src[i]->d_pts; d.n_src = src[i]->n;
         d.tgt = tgt[i]->d_pts; d.tgt_nrm = tgt[i]->d_nrm; d.n_tgt = tgt[i]->n;
         d.sorted_pts = tgt[i]->grid.d_sorted_pts; d.sorted_nrm = tgt[i]->grid.d_sorted_nrm;
@@ -1291,14 +1294,14 @@ int s3d_register_issue(s3d_ctx *ctx, const s3d_cloud *const *src, const s3d_clou
         if (rc == S3D_OK) rc = s3d_cloud_absmax(ctx, tgt[i], plane);
         if (rc) return rc;
         d.src_absmax = src[i]->d_absmax; d.tgt_absmax = tgt[i]->d_absmax;
-        PairState &s = ctx->h_state[i];
+        PairState &s = h_state[i];
         memset(&s, 0, sizeof(s));
         static const double I12[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
         const double *g = guess ? guess + 16 * (size_t)i : I12;
         for (int k = 0; k < 12; ++k) { s.T[k] = g[k]; s.Tf[k] = (float)g[k]; }
     }
-    S3D_CUDA(ctx, cudaMemcpyAsync(ctx->d_desc, ctx->h_desc, sizeof(PairDesc) * n_pairs, cudaMemcpyHostToDevice, ctx->stream));
-    S3D_CUDA(ctx, cudaMemcpyAsync(ctx->d_state, ctx->h_state, sizeof(PairState) * n_pairs, cudaMemcpyHostToDevice, ctx->stream));
+    S3D_CUDA(ctx, cudaMemcpyAsync(ctx->d_desc, h_desc, sizeof(PairDesc) * n_pairs, cudaMemcpyHostToDevice, ctx->stream));
+    S3D_CUDA(ctx, cudaMemcpyAsync(ctx->d_state, h_state, sizeof(PairState) * n_pairs, cudaMemcpyHostToDevice, ctx->stream));
 
     const float max_d2 = prm->max_corr_dist > 0.f ? prm->max_corr_dist * prm->max_corr_dist : INFINITY;
     const int min_corr = prm->min_correspondences > 0 ? prm->min_correspondences : 3;
@@ -1345,7 +1348,7 @@ int s3d_register_issue(s3d_ctx *ctx, const s3d_cloud *const *src, const s3d_clou
         }
         if (rc) return rc;
     }
-    cudaEventRecord(ctx->ev[2], ctx->stream);
+    cudaEventRecord(evs[2], ctx->stream);
     *built_out = built; *iter_launches_out = iter_launches;
     ctx->timing.total_launches = (int)(ctx->launches - launches0);
     return S3D_OK;
@@ -1419,6 +1422,68 @@ extern "C" int s3d_register_batch(s3d_ctx *ctx, const s3d_cloud *const *src, con
         s3d_result_finish(&r);
     }
     s3d_register_timing(ctx, built, iter_launches);
+    return S3D_OK;
+}
+
+// ---- stream of single-pair registrations ---------------------------------------------------------------------------
+static int async_ready(s3d_ctx *ctx)
+{
+    if (ctx->d_async) return S3D_OK;
+    S3D_CUDA(ctx, cudaMallocHost(&ctx->h_desc_ring, sizeof(PairDesc) * S3D_ASYNC_DEPTH));
+    S3D_CUDA(ctx, cudaMallocHost(&ctx->h_state_ring, sizeof(PairState) * S3D_ASYNC_DEPTH));
+    S3D_CUDA(ctx, cudaMallocHost(&ctx->h_async, sizeof(s3d_result) * S3D_ASYNC_DEPTH));
+    for (int i = 0; i < S3D_ASYNC_DEPTH; ++i) for (int k = 0; k < 3; ++k) S3D_CUDA(ctx, cudaEventCreate(&ctx->ev_ring[i][k]));
+    S3D_CUDA(ctx, cudaMalloc(&ctx->d_async, sizeof(s3d_result) * S3D_ASYNC_DEPTH));
+    return S3D_OK;
+}
+
+extern "C" int s3d_register_enqueue(s3d_ctx *ctx, const s3d_cloud *src, const s3d_cloud *tgt, const double *guess, const s3d_icp_params *prm)
+{
+    if (!ctx) return S3D_E_ARG;
+    if (ctx->async_n >= S3D_ASYNC_DEPTH) return s3d_fail(ctx, S3D_E_STATE, "s3d_register_enqueue: S3D_ASYNC_DEPTH registrations outstanding, call s3d_register_drain first");
+    cudaSetDevice(ctx->device);
+    int rc = async_ready(ctx);
+    if (rc) return rc;
+    const int slot = ctx->async_n;
+    const s3d_cloud *s[1] = {src}, *t[1] = {tgt};
+    bool built = false; int iter_launches = 0;
+    // the descriptor and the initial state are staged in this slot's own page-locked memory (the copies are asynchronous),
+    // the event times go to this slot's events
+    ctx->h_desc_use = ctx->h_desc_ring + slot; ctx->h_state_use = ctx->h_state_ring + slot; ctx->ev_use = ctx->ev_ring[slot];
+    rc = s3d_register_issue(ctx, s, t, guess, 1, prm, &built, &iter_launches);
+    ctx->h_desc_use = nullptr; ctx->h_state_use = nullptr; ctx->ev_use = nullptr;
+    if (rc) return rc;
+    rc = s3d_result_pack(ctx, 1, ctx->d_async + slot, 1);       // PairState -> record, on the device, before the next pair reuses d_state
+    if (rc) return rc;
+    ctx->async_built[slot] = built; ctx->async_launches[slot] = iter_launches; ctx->async_total_launches[slot] = ctx->timing.total_launches + 1;
+    ctx->async_n = slot + 1;
+    return S3D_OK;
+}
+
+extern "C" int s3d_register_drain(s3d_ctx *ctx, s3d_result *results_out, s3d_timing *timing_out, int capacity, int *n_out)
+{
+    if (!ctx || !results_out || !n_out) return s3d_fail(ctx, S3D_E_ARG, "s3d_register_drain: bad argument");
+    const int n = ctx->async_n;
+    if (capacity < n) return s3d_fail(ctx, S3D_E_ARG, "s3d_register_drain: capacity below the number of outstanding registrations");
+    *n_out = 0;
+    if (n == 0) return S3D_OK;
+    cudaSetDevice(ctx->device);
+    S3D_CUDA(ctx, cudaMemcpyAsync(ctx->h_async, ctx->d_async, sizeof(s3d_result) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    S3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->async_n = 0;
+    for (int i = 0; i < n; ++i) {
+        results_out[i] = ctx->h_async[i];
+        s3d_result_finish(&results_out[i]);
+        float ms_index = 0.f, ms_iter = 0.f;
+        cudaEventElapsedTime(&ms_index, ctx->ev_ring[i][0], ctx->ev_ring[i][1]);
+        cudaEventElapsedTime(&ms_iter, ctx->ev_ring[i][1], ctx->ev_ring[i][2]);
+        s3d_timing tm; memset(&tm, 0, sizeof(tm));
+        tm.index_ms = ctx->async_built[i] ? ms_index : 0.f; tm.iterate_ms = ms_iter;
+        tm.iter_launches = ctx->async_launches[i]; tm.total_launches = ctx->async_total_launches[i];
+        if (timing_out) timing_out[i] = tm;
+        ctx->timing = tm;
+    }
+    *n_out = n;
     return S3D_OK;
 }
 

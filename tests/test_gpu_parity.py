@@ -134,6 +134,51 @@ def test_skip_logic_is_exact(ctx, small_pair, k):
     assert np.array_equal(nna, idx)
 
 
+def test_enqueue_drain_matches_blocking_calls(ctx, small_cam, small_pair):
+    """s3d_register_enqueue / s3d_register_drain (a stream of registrations, no host round trip per pair): records in enqueue
+    order, bit-identical to s3d_register_pair and to the oracle, per-pair device timings, S3D_E_STATE beyond the depth, a
+    failing pair in the middle keeps its slot, and an empty drain returns nothing."""
+    import slam3d_gx_b200 as s3d
+    from slam3d_gx_b200.binding import ASYNC_DEPTH
+    assert ctx.register_drain() == ([], [])
+    pairs = [small_pair] + [synth.make_pair(k, cam=small_cam) for k in (1, 2)]
+    prm = _abi.icp_params(6, reuse_index=0)
+    clouds = [(ctx.upload(p["src"]), ctx.upload(p["tgt"], p["tgt_normals"])) for p in pairs]
+    few = ctx.upload(pairs[0]["src"][:2])                       # 2 points: S3D_PAIR_FEW_CORRESPONDENCES
+    try:
+        ref = [ctx.register(cs, ct, None, prm) for cs, ct in clouds]
+        o = oracle.icp(pairs[1]["src"], pairs[1]["tgt"], pairs[1]["tgt_normals"], params=prm)
+        assert np.array_equal(ref[1]["T"], o["T"]) and ref[1]["inliers"] == o["inliers"]
+        order = [0, 1, 2, 1, 0]
+        for k in order[:2]:
+            ctx.register_enqueue(*clouds[k], None, prm)
+        ctx.register_enqueue(few, clouds[0][1], None, prm)
+        for k in order[2:]:
+            ctx.register_enqueue(*clouds[k], None, prm)
+        res, tms = ctx.register_drain()
+        assert len(res) == len(tms) == 6
+        got = res[:2] + res[3:]
+        for k, r in zip(order, got):
+            assert r["status"] == 0 and np.array_equal(r["T"], ref[k]["T"]) and r["inliers"] == ref[k]["inliers"]
+            assert r["fitness"] == ref[k]["fitness"] and r["norm"] == ref[k]["norm"] and r["iterations"] == 6
+        assert res[2]["status"] == _abi.PAIR_FEW and np.array_equal(res[2]["T"], np.eye(4))
+        assert all(t["iterate_ms"] > 0 and t["index_ms"] > 0 and t["iter_launches"] == 1 for t in tms)
+        assert ctx.register_drain() == ([], [])
+        # depth limit
+        for _ in range(ASYNC_DEPTH):
+            ctx.register_enqueue(*clouds[0], None, _abi.icp_params(1))
+        with pytest.raises(s3d.S3DError):
+            ctx.register_enqueue(*clouds[0], None, _abi.icp_params(1))
+        res, _ = ctx.register_drain()
+        assert len(res) == ASYNC_DEPTH and all(r["status"] == 0 for r in res)
+        one = ctx.register(*clouds[0], None, _abi.icp_params(1))
+        assert all(np.array_equal(r["T"], one["T"]) for r in res)
+    finally:
+        few.free()
+        for cs, ct in clouds:
+            cs.free(); ct.free()
+
+
 def test_icp_is_deterministic(ctx, small_pair):
     p = small_pair
     a, _ = _gpu_icp(ctx, p, _abi.icp_params(8))
