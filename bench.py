@@ -282,10 +282,16 @@ def main():
     plane_prm = _abi.plane_params()
     e2e_prm = _abi.icp_params(ITERS, reuse_index=0)
 
-    # Every step uploads its own two clouds from pinned host memory, extracts the target's planes, registers and reads
-    # the result back.  The upload of step i+1 is issued (s3d_cloud_upload_async, the ctx copy stream) before the compute of
-    # step i, so the copy engine works while the SMs do: one upload per step, all of them inside the timed region.
-    e2e_t = {"upload_issue": 0.0, "plane_extraction": 0.0, "register": 0.0, "index_build_dev": 0.0, "iterations_dev": 0.0, "free": 0.0}
+    # Every step uploads its own two clouds from pinned host memory, extracts the target's planes, registers, and its result
+    # record and plane list are copied back to page-locked host memory right behind it.  The step is ISSUED without waiting
+    # (s3d_segment_planes_enqueue + s3d_register_enqueue: labels, normals, index, 30 iterations and the record are formed on the
+    # device in stream order); the host collects the results of the last E2E_DRAIN steps in one go (s3d_*_drain).  The upload
+    # of step i+1 is issued (s3d_cloud_upload_async, the ctx copy stream) before the compute of step i, so the copy engine works
+    # while the SMs do: one upload per step, all of them inside the timed region.
+    E2E_DRAIN = 16
+    e2e_t = {"upload_issue": 0.0, "plane_extraction_issue": 0.0, "register_issue": 0.0, "free": 0.0, "drain": 0.0,
+             "index_build_dev": 0.0, "iterations_dev": 0.0}
+    e2e_out = {"records": 0, "planes": 0}
 
     def e2e_upload(i):
         a, b = pin[i % len(pin)]
@@ -296,16 +302,24 @@ def main():
 
     def e2e_compute(cs, ct):
         t0 = time.perf_counter()
-        planes = ct.segment_planes(plane_prm)
+        ct.segment_planes_enqueue(plane_prm)
         t1 = time.perf_counter()
-        r = ctx.register_batch([cs], [ct], None, e2e_prm, raw=True)[0]
+        ctx.register_enqueue(cs, ct, None, e2e_prm)
         t2 = time.perf_counter()
-        tm = ctx.last_timing()
-        cs.free(); ct.free()
+        cs.release(); ct.release()       # back to the context's stream-ordered pool without waiting: the next upload reuses the buffers behind this step
         t3 = time.perf_counter()
-        e2e_t["plane_extraction"] += t1 - t0; e2e_t["register"] += t2 - t1; e2e_t["free"] += t3 - t2
-        e2e_t["index_build_dev"] += tm["index_ms"] * 1e-3; e2e_t["iterations_dev"] += tm["iterate_ms"] * 1e-3
-        return r, planes
+        e2e_t["plane_extraction_issue"] += t1 - t0; e2e_t["register_issue"] += t2 - t1; e2e_t["free"] += t3 - t2
+
+    def e2e_drain():
+        t0 = time.perf_counter()
+        planes_all = ctx.planes_drain()
+        res, tms = ctx.register_drain(raw=True)
+        e2e_t["drain"] += time.perf_counter() - t0
+        assert len(planes_all) == len(res) == len(tms)
+        for pl, r, tm in zip(planes_all, res, tms):
+            assert r.status == 0 and len(pl) == 3, "e2e: a registration failed or a plane is missing"
+            e2e_t["index_build_dev"] += tm["index_ms"] * 1e-3; e2e_t["iterations_dev"] += tm["iterate_ms"] * 1e-3
+        e2e_out["records"] += len(res); e2e_out["planes"] += sum(len(pl) for pl in planes_all)
 
     # one continuous pipeline: warm-up steps (which also let the index build capture its few launch graphs, one per recurring
     # set of pool buffers) run straight into the timed steps; every timed step issues exactly one upload (of its successor)
@@ -315,21 +329,26 @@ def main():
     t0 = None
     for i in range(e2e_warm + e2e_steps):
         if i == e2e_warm:
+            e2e_drain()
             torch.cuda.synchronize()
             if world > 1:
                 dist.barrier()
             for k in e2e_t:
                 e2e_t[k] = 0.0
+            e2e_out["records"] = e2e_out["planes"] = 0
             t0 = time.perf_counter()
         cs, ct = nxt
         nxt = e2e_upload(i + 1)
-        r, planes = e2e_compute(cs, ct)
+        e2e_compute(cs, ct)
+        if i >= e2e_warm and (i - e2e_warm + 1) % E2E_DRAIN == 0:
+            e2e_drain()
+    e2e_drain()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     nxt[0].free(); nxt[1].free()
-    assert r.status == 0 and len(planes) == 3
+    assert e2e_out["records"] == e2e_steps and e2e_out["planes"] == 3 * e2e_steps
     h2d = int(pin[0][0].numel() * 4 + pin[0][1].numel() * 4)
-    d2h = int(rec_bytes + 3 * 24 + 3 * (64 + 4))
+    d2h = int(rec_bytes + 528)          # the pair's record + the final state of the plane extraction's device loop (planes, counts)
 
     # ---- plane extraction (A2): 16 N bytes per evaluation pass over the CUDA-event time of plane_eval_kernel --------
     planes_roofline = None
@@ -467,7 +486,7 @@ def main():
             "dtype": "f32", "data": "synthetic",
             "config": config_dict(world, args.pool),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": e2e_steps, "host_ms_per_step": {k: v / e2e_steps * 1e3 for k, v in e2e_t.items()}, "includes": "pinned-host upload of both clouds (step i+1's copy overlaps step i's compute), RANSAC plane extraction of the target, index build, 30 iterations, result read-back"},
+                    "steps": e2e_steps, "host_ms_per_step": {k: v / e2e_steps * 1e3 for k, v in e2e_t.items()}, "includes": "pinned-host upload of both clouds (step i+1's copy overlaps step i's compute), RANSAC plane extraction of the target, index build, 30 iterations, copy of the result record and the planes to page-locked host memory behind every step; steps are issued without waiting (s3d_segment_planes_enqueue, s3d_register_enqueue) and collected every %d steps (s3d_*_drain)" % E2E_DRAIN},
             "gpu_launches": total_launches,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

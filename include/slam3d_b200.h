@@ -187,6 +187,10 @@ int  s3d_cloud_drop_index(s3d_ctx *ctx, s3d_cloud *cloud);
  * (any pointer may be NULL).  A long run keeps only its key frames resident (reference: _keyframes, src/GraphicEnd.h:150). */
 int  s3d_memory_stats(const s3d_ctx *ctx, size_t *live_bytes, size_t *peak_live_bytes, size_t *cached_bytes);
 void s3d_cloud_free(s3d_ctx *ctx, s3d_cloud *cloud);
+/* s3d_cloud_free waits for the context's stream first.  s3d_cloud_release does not: the buffers go back to the context's pool, which
+ * is ordered by the context's stream, so work already enqueued on the cloud (s3d_register_enqueue, s3d_segment_planes_enqueue)
+ * still runs on intact data and whoever is handed the buffers next is enqueued behind it. */
+void s3d_cloud_release(s3d_ctx *ctx, s3d_cloud *cloud);
 
 /* ---- filters and map fusion (the steps either side of the registration path) ------------------ */
 /* pcl::PassThrough on "z": keeps finite points with z_min <= z <= z_max, order preserved
@@ -230,13 +234,18 @@ int  s3d_last_timing(const s3d_ctx *ctx, s3d_timing *out);
  * candidates of reference src/GraphicEnd.cpp:729-761 when its results are only needed after the loop.  s3d_register_enqueue
  * issues one registration on the context's stream and forms its result record on the device; s3d_register_drain waits for
  * everything enqueued since the last drain and returns the records (and, when timing_out is not NULL, the device times of
- * each) in enqueue order with ONE device-to-host copy.  At most S3D_ASYNC_DEPTH pairs may be outstanding (S3D_E_STATE
- * beyond that: drain first).  The clouds must stay alive and unmodified until the drain.  Results are bit-identical to
- * s3d_register_pair. */
+ * each) in enqueue order.  At most S3D_ASYNC_DEPTH pairs may be outstanding (S3D_E_STATE
+ * beyond that: drain first).  The clouds must stay unmodified until the drain.  Results are bit-identical to
+ * s3d_register_pair.  Every record is copied to page-locked host memory right behind its pair (160 bytes); the drain only waits.
+ * A cloud may be released (s3d_cloud_release, not s3d_cloud_free, which waits) once the work that uses it is enqueued.  s3d_segment_planes_enqueue / s3d_segment_planes_drain do the same for the plane extraction (labels and
+ * normals are written on the device in stream order, so a registration enqueued behind it sees them); planes_out holds
+ * S3D_MAX_PLANES planes per extraction, n_planes_out the number found by each. */
 #define S3D_ASYNC_DEPTH 64
 int  s3d_register_enqueue(s3d_ctx *ctx, const s3d_cloud *src, const s3d_cloud *tgt, const double *guess /* 16 doubles or NULL */,
                           const s3d_icp_params *params);
 int  s3d_register_drain(s3d_ctx *ctx, s3d_result *results_out, s3d_timing *timing_out /* may be NULL */, int capacity, int *n_out);
+int  s3d_segment_planes_enqueue(s3d_ctx *ctx, s3d_cloud *cloud, const s3d_plane_params *params);
+int  s3d_segment_planes_drain(s3d_ctx *ctx, s3d_plane *planes_out, int *n_planes_out, int capacity, int *n_out);
 void s3d_icp_params_default(s3d_icp_params *p);
 void s3d_plane_params_default(s3d_plane_params *p);
 int  s3d_last_plane_timing(const s3d_ctx *ctx, s3d_plane_timing *out);

@@ -34,9 +34,10 @@ EXPORTS = [
     "s3d_last_correspondences", "s3d_last_timing", "s3d_icp_params_default", "s3d_plane_params_default",
     "s3d_planar_keypoints", "s3d_gather_results", "s3d_cloud_passthrough_z", "s3d_cloud_voxel_grid", "s3d_cloud_transform",
     "s3d_cloud_concat", "s3d_map_fuse", "s3d_cloud_from_depth_normals", "s3d_cloud_upload_async", "s3d_cloud_wait", "s3d_host_alloc", "s3d_host_free",
-    "s3d_memory_stats", "s3d_last_plane_timing", "s3d_comm_unique_id", "s3d_comm_create", "s3d_comm_destroy", "s3d_register_batch_gather", "s3d_register_enqueue", "s3d_register_drain",
+    "s3d_memory_stats", "s3d_last_plane_timing", "s3d_comm_unique_id", "s3d_comm_create", "s3d_comm_destroy", "s3d_register_batch_gather", "s3d_register_enqueue", "s3d_register_drain", "s3d_segment_planes_enqueue", "s3d_segment_planes_drain", "s3d_cloud_release",
 ]
 ASYNC_DEPTH = 64          # S3D_ASYNC_DEPTH
+MAX_PLANES = 16           # S3D_MAX_PLANES
 COMM_ID_BYTES = 128
 
 
@@ -77,6 +78,8 @@ def load_library():
     lib.s3d_cloud_drop_index.argtypes = [vp, vp]
     lib.s3d_cloud_free.argtypes = [vp, vp]
     lib.s3d_cloud_free.restype = None
+    lib.s3d_cloud_release.argtypes = [vp, vp]
+    lib.s3d_cloud_release.restype = None
     lib.s3d_segment_planes.argtypes = [vp, vp, C.POINTER(_abi.PlaneParams), C.POINTER(_abi.Plane), C.POINTER(ci)]
     lib.s3d_register_batch.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), vp, ci, C.POINTER(_abi.IcpParams),
                                        C.POINTER(_abi.Result)]
@@ -85,6 +88,8 @@ def load_library():
     lib.s3d_last_timing.argtypes = [vp, C.POINTER(_abi.Timing)]
     lib.s3d_register_enqueue.argtypes = [vp, vp, vp, vp, C.POINTER(_abi.IcpParams)]
     lib.s3d_register_drain.argtypes = [vp, C.POINTER(_abi.Result), C.POINTER(_abi.Timing), ci, C.POINTER(ci)]
+    lib.s3d_segment_planes_enqueue.argtypes = [vp, vp, C.POINTER(_abi.PlaneParams)]
+    lib.s3d_segment_planes_drain.argtypes = [vp, C.POINTER(_abi.Plane), C.POINTER(ci), ci, C.POINTER(ci)]
     lib.s3d_icp_params_default.argtypes = [C.POINTER(_abi.IcpParams)]
     lib.s3d_icp_params_default.restype = None
     lib.s3d_plane_params_default.argtypes = [C.POINTER(_abi.PlaneParams)]
@@ -160,6 +165,11 @@ class Cloud:
         return [dict(coef=np.array(list(planes[i].coef), np.float32), inliers=planes[i].inliers,
                      hypotheses=planes[i].hypotheses) for i in range(k.value)]
 
+    def segment_planes_enqueue(self, params: _abi.PlaneParams | None = None):
+        """The extraction issued without waiting for it (s3d_segment_planes_enqueue); planes come back from Context.planes_drain."""
+        params = params or _abi.plane_params()
+        self.ctx._check(self.ctx.lib.s3d_segment_planes_enqueue(self.ctx.h, self.handle, C.byref(params)))
+
     def drop_index(self):
         self.ctx.lib.s3d_cloud_drop_index(self.ctx.h, self.handle)
 
@@ -185,6 +195,12 @@ class Cloud:
     def free(self):
         if self.handle is not None:
             self.ctx.lib.s3d_cloud_free(self.ctx.h, self.handle)
+            self.handle = None
+
+    def release(self):
+        """Like free() but without waiting for the context's stream (s3d_cloud_release): for clouds with work still enqueued."""
+        if self.handle is not None:
+            self.ctx.lib.s3d_cloud_release(self.ctx.h, self.handle)
             self.handle = None
 
 
@@ -302,6 +318,15 @@ class Context:
         if guess is not None:
             g = np.ascontiguousarray(guess, dtype=np.float64).reshape(16)
         self._check(self.lib.s3d_register_enqueue(self.h, src.handle, tgt.handle, g.ctypes.data if g is not None else None, C.byref(params)))
+
+    def planes_drain(self):
+        """Planes of every extraction enqueued since the last drain, in enqueue order (s3d_segment_planes_drain)."""
+        planes = (_abi.Plane * (ASYNC_DEPTH * MAX_PLANES))()
+        counts = (C.c_int * ASYNC_DEPTH)()
+        n = C.c_int(0)
+        self._check(self.lib.s3d_segment_planes_drain(self.h, planes, counts, ASYNC_DEPTH, C.byref(n)))
+        return [[dict(coef=np.array(list(planes[i * MAX_PLANES + k].coef), np.float32), inliers=planes[i * MAX_PLANES + k].inliers,
+                      hypotheses=planes[i * MAX_PLANES + k].hypotheses) for k in range(counts[i])] for i in range(n.value)]
 
     def register_drain(self, raw: bool = False):
         """Results (enqueue order) and device timings of everything enqueued since the last drain (s3d_register_drain)."""

@@ -138,6 +138,7 @@ extern "C" void s3d_destroy(s3d_ctx *ctx)
     if (ctx->h_desc_ring) cudaFreeHost(ctx->h_desc_ring);
     if (ctx->h_state_ring) cudaFreeHost(ctx->h_state_ring);
     if (ctx->h_async) cudaFreeHost(ctx->h_async);
+    if (ctx->h_planes_ring) cudaFreeHost(ctx->h_planes_ring);
     cudaFree(ctx->d_async);
     for (int i = 0; i < S3D_ASYNC_DEPTH; ++i) for (int k = 0; k < 3; ++k) if (ctx->ev_ring[i][k]) cudaEventDestroy(ctx->ev_ring[i][k]);
     s3d_dev_pool_release(ctx);
@@ -515,12 +516,16 @@ extern "C" int s3d_memory_stats(const s3d_ctx *ctx, size_t *live_bytes, size_t *
     return S3D_OK;
 }
 
-extern "C" void s3d_cloud_free(s3d_ctx *ctx, s3d_cloud *cloud)
+static void cloud_retire(s3d_ctx *ctx, s3d_cloud *cloud, bool wait)
 {
     if (!cloud) return;
-    if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
+    if (ctx) { cudaSetDevice(ctx->device); if (wait) cudaStreamSynchronize(ctx->stream); }
     if (!ctx) { delete cloud; return; }     // cannot return device memory without its context (leak rather than crash)
-    if (cloud->ready) { cudaEventSynchronize(cloud->ready); cudaEventDestroy(cloud->ready); }   // an upload may still be writing it
+    if (cloud->ready) {                     // an upload may still be writing it
+        if (wait) cudaEventSynchronize(cloud->ready);
+        else cudaStreamWaitEvent(ctx->stream, cloud->ready, 0);      // whoever gets the buffers next (ctx stream order) comes after the upload
+        cudaEventDestroy(cloud->ready);
+    }
     s3d_dev_free(ctx, cloud->d_stage);
     s3d_grid_free(ctx, cloud->grid);
     s3d_grid_free(ctx, cloud->coarse);
@@ -529,3 +534,10 @@ extern "C" void s3d_cloud_free(s3d_ctx *ctx, s3d_cloud *cloud)
     s3d_dev_free(ctx, cloud->d_absmax);
     delete cloud;
 }
+
+extern "C" void s3d_cloud_free(s3d_ctx *ctx, s3d_cloud *cloud) { cloud_retire(ctx, cloud, true); }
+
+// Without waiting: the buffers go back to the context's pool, which is ordered by the context's stream -- whatever was enqueued
+// on the cloud still runs on intact data, whoever gets the buffers next is enqueued behind it (uploads on the copy stream are
+// fenced behind the ctx stream, the index build's second stream forks from it).
+extern "C" void s3d_cloud_release(s3d_ctx *ctx, s3d_cloud *cloud) { cloud_retire(ctx, cloud, false); }

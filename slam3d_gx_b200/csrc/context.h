@@ -123,6 +123,7 @@ struct s3d_ctx {
     cudaEvent_t ev_ring[S3D_ASYNC_DEPTH][3] = {};
     bool async_built[S3D_ASYNC_DEPTH] = {}; int async_launches[S3D_ASYNC_DEPTH] = {}; int async_total_launches[S3D_ASYNC_DEPTH] = {};
     int async_n = 0;
+    void *h_planes_ring = nullptr; int planes_async_n = 0;      // s3d_segment_planes_enqueue: page-locked landing slots of the device loop's final state
     cudaEvent_t ev_plane[2] = {nullptr, nullptr};
     cudaEvent_t ev_eval[2 * S3D_MAX_PLANES] = {};       // around the evaluation pass of each RANSAC round
     s3d_plane_timing plane_timing = {0, 0, 0, 0, 0, 0};

@@ -1455,6 +1455,7 @@ extern "C" int s3d_register_enqueue(s3d_ctx *ctx, const s3d_cloud *src, const s3
     if (rc) return rc;
     rc = s3d_result_pack(ctx, 1, ctx->d_async + slot, 1);       // PairState -> record, on the device, before the next pair reuses d_state
     if (rc) return rc;
+    S3D_CUDA(ctx, cudaMemcpyAsync(ctx->h_async + slot, ctx->d_async + slot, sizeof(s3d_result), cudaMemcpyDeviceToHost, ctx->stream));   // the record goes home right behind its pair
     ctx->async_built[slot] = built; ctx->async_launches[slot] = iter_launches; ctx->async_total_launches[slot] = ctx->timing.total_launches + 1;
     ctx->async_n = slot + 1;
     return S3D_OK;
@@ -1468,7 +1469,6 @@ extern "C" int s3d_register_drain(s3d_ctx *ctx, s3d_result *results_out, s3d_tim
     *n_out = 0;
     if (n == 0) return S3D_OK;
     cudaSetDevice(ctx->device);
-    S3D_CUDA(ctx, cudaMemcpyAsync(ctx->h_async, ctx->d_async, sizeof(s3d_result) * n, cudaMemcpyDeviceToHost, ctx->stream));
     S3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->async_n = 0;
     for (int i = 0; i < n; ++i) {

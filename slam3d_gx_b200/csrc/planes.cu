@@ -41,6 +41,8 @@ struct PlaneState {
     s3d_plane planes[S3D_MAX_PLANES];
 };
 
+static_assert(sizeof(PlaneState) == 528, "bench.py counts this many bytes per extraction in e2e.d2h_bytes_per_step");
+
 __global__ void plane_init_kernel(const float4 *__restrict__ pts, int n, float4 *__restrict__ rem, int32_t *__restrict__ labels,
                                   float4 *__restrict__ nrm, PlaneState *st)
 {
@@ -367,14 +369,14 @@ extern "C" void s3d_plane_params_default(s3d_plane_params *p)
     p->probability = 0.99f; p->seed = 12345ull;
 }
 
-extern "C" int s3d_segment_planes(s3d_ctx *ctx, s3d_cloud *cloud, const s3d_plane_params *prm, s3d_plane *planes_out, int *n_planes_out)
+// Enqueues the whole extraction on the ctx stream followed by the copy of the device loop's final state to `hb` (page-locked);
+// no host synchronisation.  eval_passes_out: evaluation passes per round (timing bookkeeping of the blocking call).
+static int planes_issue(s3d_ctx *ctx, s3d_cloud *cloud, const s3d_plane_params *prm, PlaneState *hb, int *eval_passes_out, bool *timed_out)
 {
-    if (!ctx || !cloud || !prm || !planes_out || !n_planes_out) return s3d_fail(ctx, S3D_E_ARG, "s3d_segment_planes: bad argument");
     if (prm->max_planes < 0 || prm->max_planes > S3D_MAX_PLANES || prm->max_iterations < 1 ||
         prm->max_iterations + PLANE_CANDIDATES_EXTRA > PLANE_MAX_CAND || !(prm->distance_threshold > 0.f))
         return s3d_fail(ctx, S3D_E_ARG, "s3d_segment_planes: parameter out of range");
     cudaSetDevice(ctx->device);
-    *n_planes_out = 0;
     { int rc = s3d_cloud_ready(ctx, cloud); if (rc) return rc; }
     const int n = cloud->n;
     const size_t np = (size_t)(n > 0 ? n : 1);
@@ -404,8 +406,6 @@ extern "C" int s3d_segment_planes(s3d_ctx *ctx, s3d_cloud *cloud, const s3d_plan
     float4 *coefs = (float4 *)(base + o_coef); int *valid = (int *)(base + o_valid);
     uint32_t *counts = (uint32_t *)(base + o_cnt); PlaneState *state = (PlaneState *)(base + o_state);
     long long *partials = (long long *)(base + o_part); uint32_t *blk = (uint32_t *)(base + o_blk);
-    PlaneState *hb = (PlaneState *)s3d_pinned(ctx, sizeof(PlaneState));
-    if (!hb) return s3d_fail(ctx, S3D_E_CUDA, "pinned alloc");
     cudaStream_t st = ctx->stream;
     const float tau = prm->distance_threshold;
 
@@ -474,7 +474,19 @@ extern "C" int s3d_segment_planes(s3d_ctx *ctx, s3d_cloud *cloud, const s3d_plan
     if (!done) { const int rc = launches(timed); if (rc) return rc; }
     cudaEventRecord(ctx->ev_plane[1], st);
     S3D_CUDA(ctx, cudaMemcpyAsync(hb, state, sizeof(PlaneState), cudaMemcpyDeviceToHost, st));
-    S3D_CUDA(ctx, cudaStreamSynchronize(st));
+    *eval_passes_out = (int)ge.y; *timed_out = timed;
+    return S3D_OK;
+}
+
+extern "C" int s3d_segment_planes(s3d_ctx *ctx, s3d_cloud *cloud, const s3d_plane_params *prm, s3d_plane *planes_out, int *n_planes_out)
+{
+    if (!ctx || !cloud || !prm || !planes_out || !n_planes_out) return s3d_fail(ctx, S3D_E_ARG, "s3d_segment_planes: bad argument");
+    *n_planes_out = 0;
+    PlaneState *hb = (PlaneState *)s3d_pinned(ctx, sizeof(PlaneState));
+    if (!hb) return s3d_fail(ctx, S3D_E_CUDA, "pinned alloc");
+    int eval_passes = 1; bool timed = false;
+    { const int rc = planes_issue(ctx, cloud, prm, hb, &eval_passes, &timed); if (rc) return rc; }
+    S3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     const int n_planes = hb->n_planes;
     for (int k = 0; k < n_planes; ++k) planes_out[k] = hb->planes[k];
     *n_planes_out = n_planes;
@@ -484,13 +496,46 @@ extern "C" int s3d_segment_planes(s3d_ctx *ctx, s3d_cloud *cloud, const s3d_plan
     ctx->plane_timing.total_ms = ms;
     ctx->plane_timing.rounds = 0; ctx->plane_timing.points_scanned = 0;
     for (int k = 0; k < S3D_MAX_PLANES; ++k) if (hb->rem_at_round[k] > 0) { ctx->plane_timing.rounds++; ctx->plane_timing.points_scanned += hb->rem_at_round[k]; }
-    ctx->plane_timing.eval_passes_per_round = (int)ge.y;
+    ctx->plane_timing.eval_passes_per_round = eval_passes;
     ctx->plane_timing.eval_ms = 0.f;
     for (int k = 0; timed && k < ctx->plane_timing.rounds && k < prm->max_planes; ++k) {
         float e = 0.f;
         cudaEventElapsedTime(&e, ctx->ev_eval[2 * k], ctx->ev_eval[2 * k + 1]);
         ctx->plane_timing.eval_ms += e;
     }
+    return S3D_OK;
+}
+
+// ---- extraction without a host round trip (the stream counterpart of s3d_register_enqueue) -----------------------------------
+extern "C" int s3d_segment_planes_enqueue(s3d_ctx *ctx, s3d_cloud *cloud, const s3d_plane_params *prm)
+{
+    if (!ctx || !cloud || !prm) return s3d_fail(ctx, S3D_E_ARG, "s3d_segment_planes_enqueue: bad argument");
+    if (ctx->planes_async_n >= S3D_ASYNC_DEPTH) return s3d_fail(ctx, S3D_E_STATE, "s3d_segment_planes_enqueue: S3D_ASYNC_DEPTH extractions outstanding, call s3d_segment_planes_drain first");
+    cudaSetDevice(ctx->device);
+    if (!ctx->h_planes_ring) S3D_CUDA(ctx, cudaMallocHost(&ctx->h_planes_ring, sizeof(PlaneState) * S3D_ASYNC_DEPTH));
+    int eval_passes = 1; bool timed = false;
+    const int rc = planes_issue(ctx, cloud, prm, reinterpret_cast<PlaneState *>(ctx->h_planes_ring) + ctx->planes_async_n, &eval_passes, &timed);
+    if (rc) return rc;
+    ctx->planes_async_n++;
+    return S3D_OK;
+}
+
+extern "C" int s3d_segment_planes_drain(s3d_ctx *ctx, s3d_plane *planes_out, int *n_planes_out, int capacity, int *n_out)
+{
+    if (!ctx || !planes_out || !n_planes_out || !n_out) return s3d_fail(ctx, S3D_E_ARG, "s3d_segment_planes_drain: bad argument");
+    const int n = ctx->planes_async_n;
+    if (capacity < n) return s3d_fail(ctx, S3D_E_ARG, "s3d_segment_planes_drain: capacity below the number of outstanding extractions");
+    *n_out = 0;
+    if (n == 0) return S3D_OK;
+    cudaSetDevice(ctx->device);
+    S3D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->planes_async_n = 0;
+    const PlaneState *ring = reinterpret_cast<const PlaneState *>(ctx->h_planes_ring);
+    for (int i = 0; i < n; ++i) {
+        n_planes_out[i] = ring[i].n_planes;
+        for (int k = 0; k < S3D_MAX_PLANES; ++k) planes_out[(size_t)i * S3D_MAX_PLANES + k] = ring[i].planes[k];
+    }
+    *n_out = n;
     return S3D_OK;
 }
 

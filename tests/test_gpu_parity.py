@@ -429,6 +429,44 @@ def test_plane_segmentation_full_size_and_icp_with_segmented_normals(ctx, full_p
     src.free(); tgt.free()
 
 
+def test_plane_extraction_enqueue_drain(ctx, small_cam):
+    """s3d_segment_planes_enqueue / s3d_segment_planes_drain: the same planes, labels and normals as the blocking call, and a
+    registration enqueued behind the extraction sees the normals it wrote (stream order, no host round trip in between)."""
+    p = synth.make_pair(3, cam=small_cam)
+    prm = _abi.plane_params()
+    icp = _abi.icp_params(5)
+    a, b = ctx.upload(p["tgt"]), ctx.upload(p["tgt"])
+    src = ctx.upload(p["src"])
+    try:
+        ref_planes = a.segment_planes(prm)
+        ref = ctx.register(src, a, None, icp)
+        assert ctx.planes_drain() == []
+        b.segment_planes_enqueue(prm)
+        ctx.register_enqueue(src, b, None, icp)
+        b.segment_planes_enqueue(prm)                  # a second extraction of the same cloud: same answer, second slot
+        # a cloud released while its work is enqueued: the work still runs on intact data, the next uploads get its buffers behind it
+        c = ctx.upload(p["tgt"]); s2 = ctx.upload(p["src"])
+        c.segment_planes_enqueue(prm)
+        ctx.register_enqueue(s2, c, None, icp)
+        c.release(); s2.release()
+        junk = [ctx.upload(np.full_like(p["tgt"], 7.0)) for _ in range(4)]
+        got = ctx.planes_drain()
+        res, _ = ctx.register_drain()
+        for j in junk:
+            j.free()
+        assert len(got) == 3 and len(res) == 2
+        assert res[1]["status"] == 0 and np.array_equal(res[1]["T"], ref["T"]) and res[1]["inliers"] == ref["inliers"]
+        for pl in got:
+            assert len(pl) == len(ref_planes) > 0
+            for x, y in zip(pl, ref_planes):
+                assert np.array_equal(x["coef"], y["coef"]) and x["inliers"] == y["inliers"] and x["hypotheses"] == y["hypotheses"]
+        da, db = a.download(normals=True, labels=True), b.download(normals=True, labels=True)
+        assert np.array_equal(da["labels"], db["labels"]) and np.array_equal(da["normals"], db["normals"])
+        assert res[0]["status"] == 0 and np.array_equal(res[0]["T"], ref["T"]) and res[0]["inliers"] == ref["inliers"]
+    finally:
+        a.free(); b.free(); src.free()
+
+
 def test_plane_segmentation_edge_cases(ctx):
     prm = _abi.plane_params()
     c = ctx.upload(np.zeros((0, 3), np.float32))
