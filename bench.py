@@ -454,7 +454,7 @@ def main():
             t0ref = t0c.clone()
             dist.broadcast(t0ref, src=0)
             assert torch.equal(t0c, t0ref), "config 4: gathered records differ between ranks"
-    per_rank = [{"rank": rank, "elapsed_ms": elapsed_ms, "sm_mhz": clocks.get("sm_mhz"), "reasons": clocks.get("reasons"),
+    per_rank = [{"rank": rank, "elapsed_ms": elapsed_ms, "device_ms": iter_ms + index_ms, "sm_mhz": clocks.get("sm_mhz"), "reasons": clocks.get("reasons"),
                  "config4_ms": config4["ms"] if config4 else None, "config4_device_ms": config4["dev_ms"] if config4 else None,
                  "config4_sm_mhz": config4["clocks"].get("sm_mhz") if config4 else None,
                  "config4_reasons": config4["clocks"].get("reasons") if config4 else None}]
