@@ -19,5 +19,15 @@ print("batch", [x["status"] for x in res])
 t2 = ctx.from_depth_normals(p["tgt_depth"], cam, 3.5, 1, 0.08)
 print("planes", len(t2.segment_planes(_abi.plane_params())))
 v = t2.voxel_grid(0.03); z = v.passthrough_z(0.0, 3.0); print("filters", len(v), len(z))
+# the stream forms: extraction + registration enqueued behind each other, clouds released while their work is queued
+for k in range(3):
+    a = ctx.upload(p["src"]); b = ctx.upload(p["tgt"])
+    b.segment_planes_enqueue(_abi.plane_params())
+    ctx.register_enqueue(a, b, None, _abi.icp_params(4, reuse_index=0))
+    a.release(); b.release()
+pl = ctx.planes_drain(); rs, tm = ctx.register_drain()
+print("stream", [len(x) for x in pl], [x["status"] for x in rs])
+res = ctx.register_batch([src] * 20, [tgt] * 20, None, _abi.icp_params(3))      # more than 16 pairs: four groups walk the list
+print("batch20", sorted(set(x["status"] for x in res)))
 for c in (src, tgt, t2, v, z): c.free()
 ctx.close()
