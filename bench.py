@@ -275,7 +275,7 @@ def main():
 
     # ---- e2e: host buffers through the C ABI (upload + plane extraction + registration + read-back) ------
     pin = []
-    for k in range(min(4, args.pool)):
+    for k in range(args.pool):          # the same pool of pairs as the device-resident arm
         a = torch.from_numpy(host[k]["src"].copy()).pin_memory()
         b = torch.from_numpy(host[k]["tgt"].copy()).pin_memory()
         pin.append((a, b))
