@@ -469,9 +469,12 @@ def main():
         peak, peak_src = measured_peak()
         value = world * args.steps * ITERS / (elapsed_ms * 1e-3)
         e2e_value = world * e2e_steps * ITERS / (e2e_ms * 1e-3)
-        # dominant kernel: the fused correspondence + reduction + solve launch (one per iteration)
-        per_launch_s = (iter_ms * 1e-3) / max(1, iter_launches)
-        units_per_launch = (args.steps * ITERS) / max(1, iter_launches)
+        # dominant kernel: icp_persist_kernel -- ALL iterations of a registration in two back-to-back cooperative launches of its
+        # two instances (search-only for the leading full-search iterations, general for the rest); the CUDA events of every
+        # registration of the timed region bracket both, so "launch" below is that pair = one registration of ITERS iterations
+        launches_per_registration = iter_launches / max(1, args.steps)
+        per_launch_s = (iter_ms * 1e-3) / max(1, args.steps)
+        units_per_launch = float(ITERS)
         achieved = B_ALG * units_per_launch / per_launch_s / 1e9
         traffic = None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
@@ -490,10 +493,11 @@ def main():
             "gpu_launches": total_launches,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": "icp_persist_kernel<point_to_plane> (one cooperative launch = all 30 iterations)", "peak_source": peak_src,
+                         "traffic": traffic, "kernel": "icp_persist_kernel<point_to_plane> (all 30 iterations of a registration: the search-only instance for the leading full-search iterations + the general instance, back to back)", "peak_source": peak_src,
                          "algorithmic_bytes_per_iteration": B_ALG, "iterations_per_launch": units_per_launch,
+                         "cooperative_launches_per_registration": launches_per_registration,
                          "avg_launch_us": per_launch_s * 1e6,
-                         "note": "achieved = algorithmic bytes (16N+32M per iteration, SURVEY.md 8d) / measured kernel time; the single-pair working set (~45 MB) is L2 resident, so the kernel is bound by search issue slots and per-iteration barrier latency, not by HBM"},
+                         "note": "achieved = algorithmic bytes (16N+32M per iteration, SURVEY.md 8d) / measured kernel time of a registration (CUDA events around its launches, every registration of the timed region); the single-pair working set (~45 MB) is L2 resident, so the kernel is bound by search issue slots and the per-iteration group sum + solve, not by HBM"},
             "breakdown_ms_per_step": {"index_build": index_ms / args.steps, "iterations": iter_ms / args.steps},
             "elapsed_ms_ranks": {"min": float(tmin[0].item()), "max": float(tmax2[0].item())},
             "per_rank": per_rank,

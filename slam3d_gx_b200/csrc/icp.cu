@@ -671,14 +671,19 @@ __device__ __forceinline__ void red_release_add_u32(unsigned *p, unsigned v)
 //   then    the CTA's sums (integers, smem atomics) go to the group as one row, group barrier (red.release / ld.acquire), every CTA
 //           adds the rows and solves redundantly in strict double: all CTAs hold bit-identical poses, no second barrier.
 // Because the sums do not depend on the order of the additions, a query can be accumulated by whichever pass decides it.
-template <int EST>
-__global__ void __launch_bounds__(TS_BLOCK, 1) icp_persist_kernel(const PersistArgs a)
+template <int EST, int BLOCK_, int CAP_, bool SEARCH_ONLY>
+__global__ void __launch_bounds__(BLOCK_, 1) icp_persist_kernel(const PersistArgs a)
 {
+    // BLOCK_ threads, CAP_ candidates per warp tile.  SEARCH_ONLY: the instance that runs a pair's leading full-search iterations
+    // (every query searched, no streaming pass) with more, leaner warps and hands the pair over -- through its PairState and the
+    // per-query arrays -- to the general instance at the first iteration that streams.
+    constexpr int K_WARPS = BLOCK_ / 32, K_CAP = CAP_, K_STAGE = (CAP_ * 16) / (int)PS_CHUNK_BYTES;
+    static_assert(CAP_ * 16 >= 29 * 33 * 8, "the warp tile also carries the transposed 29 x 33 int64 reduction");
     extern __shared__ __align__(16) unsigned char ts_smem[];
-    float4 *tiles = reinterpret_cast<float4 *>(ts_smem);          // TS_WARPS tiles of TS_CAP candidates
+    float4 *tiles = reinterpret_cast<float4 *>(ts_smem);          // K_WARPS tiles of K_CAP candidates
     __shared__ PairState st;                                      // this CTA's copy of the pair state (all CTAs of a group agree bit for bit)
     __shared__ float4 hist[PS_HIST][3];                           // float poses (three rows) of the last PS_HIST iterations (ring)
-    __shared__ long long wrow[TS_WARPS][S3D_ROW];                 // every warp's own (hi, lo) sums of this iteration (no 64-bit shared atomics:
+    __shared__ long long wrow[K_WARPS][S3D_ROW];                 // every warp's own (hi, lo) sums of this iteration (no 64-bit shared atomics:
                                                                   // they are compare-and-swap loops and 16 warps meet on the same 58 words)
     __shared__ long long ctot[S3D_ROW];                           // the CTA's (hi, lo) sums of this iteration
     __shared__ double total[S3D_NACC];                            // the pair's 29 sums as doubles, input of the solve
@@ -687,12 +692,12 @@ __global__ void __launch_bounds__(TS_BLOCK, 1) icp_persist_kernel(const PersistA
     __shared__ int pend_count, pend_next;                         // pending list of this CTA: entries appended / handed out
     __shared__ int full_next;                                     // the next iteration skips the streaming pass (big pose update)
 #ifdef TS_USE_TMA
-    __shared__ __align__(8) uint64_t tile_bar[TS_WARPS];         // one mbarrier per warp: completion of its TMA row copies
+    __shared__ __align__(8) uint64_t tile_bar[K_WARPS];         // one mbarrier per warp: completion of its TMA row copies
 #endif
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int group = blockIdx.x / a.group_ctas, rank = blockIdx.x - group * a.group_ctas;
-    float4 *buf = tiles + warp * TS_CAP;
+    float4 *buf = tiles + warp * K_CAP;
     const uint32_t sbuf = ts_smem_u32(buf);
 #ifdef TS_USE_TMA
     uint64_t *bar_w = &tile_bar[warp];
@@ -717,7 +722,7 @@ __global__ void __launch_bounds__(TS_BLOCK, 1) icp_persist_kernel(const PersistA
         if (threadIdx.x == 0) {
             st = a.states[pair];
             fxs = s3d_fx_make(s3d_icp_bound(*d.src_absmax, *d.tgt_absmax, EST == S3D_ESTIMATOR_POINT_TO_PLANE ? d.tgt_absmax[1] : 1.0f, st.T));
-            pend_count = 0; pend_next = 0; full_next = 1;
+            pend_count = 0; pend_next = 0; full_next = st.iterations == 0 ? 1 : 0;      // (a pair taken over from the search-only instance streams)
             cfg[1].gp = *d.grid; cfg[1].cell_start = d.cell_start; cfg[1].pts = d.sorted_pts;
             cfg[1].slack = a.slack_cells * cfg[1].gp.cell; cfg[1].gate_r = gate_r;
             cfg[0] = cfg[1];
@@ -728,7 +733,14 @@ __global__ void __launch_bounds__(TS_BLOCK, 1) icp_persist_kernel(const PersistA
         }
         if (threadIdx.x < S3D_ROW) ctot[threadIdx.x] = 0;
         __syncthreads();
-        if (threadIdx.x < 3) hist[0][threadIdx.x] = make_float4(st.Tf[4 * threadIdx.x], st.Tf[4 * threadIdx.x + 1], st.Tf[4 * threadIdx.x + 2], st.Tf[4 * threadIdx.x + 3]);
+        // the pose ring: the current pose and (a pair taken over after it_begin iterations: every query was last searched in
+        // iteration it_begin - 1) the pose of the iteration before
+        const int it_begin = st.iterations;
+        if (threadIdx.x < 3) hist[it_begin & (PS_HIST - 1)][threadIdx.x] = make_float4(st.Tf[4 * threadIdx.x], st.Tf[4 * threadIdx.x + 1], st.Tf[4 * threadIdx.x + 2], st.Tf[4 * threadIdx.x + 3]);
+        else if (threadIdx.x < 6 && it_begin > 0) {
+            const int k = threadIdx.x - 3;
+            hist[(it_begin - 1) & (PS_HIST - 1)][k] = make_float4(st.Tf_prev[4 * k], st.Tf_prev[4 * k + 1], st.Tf_prev[4 * k + 2], st.Tf_prev[4 * k + 3]);
+        }
         const float cell = cfg[1].gp.cell, slack = cfg[1].slack, ccell = cfg[0].gp.cell;
         float4 *my_cq = a.cq + (size_t)pair * a.nn_stride;
         float4 *my_cn = a.cn + (size_t)pair * a.nn_stride;
@@ -736,17 +748,17 @@ __global__ void __launch_bounds__(TS_BLOCK, 1) icp_persist_kernel(const PersistA
         uint8_t *my_fl = a.flags + (size_t)pair * a.nn_stride;
         // Octet u belongs to CTA (u mod group_ctas): every CTA samples the whole cloud evenly (the search cost varies smoothly
         // with depth).  The CTA's octets are m = 0 .. cta_units-1 (u = rank + group_ctas * m); in pass 1 chunk c = four
-        // consecutive local octets 4c .. 4c+3 (one per 8 lanes) and warp w walks chunks w, w + TS_WARPS, ...
+        // consecutive local octets 4c .. 4c+3 (one per 8 lanes) and warp w walks chunks w, w + K_WARPS, ...
         const int nunits = (d.n_src + 7) >> 3;
         const int cta_units = rank < nunits ? (nunits - rank + a.group_ctas - 1) / a.group_ctas : 0;
         const int cta_chunks = (cta_units + 3) >> 2;
         __syncthreads();
 
-        // stage PS_STAGE chunks of per-query state (49 B per query) into the warp's tile: every load in flight at once, no registers
+        // stage K_STAGE chunks of per-query state (49 B per query) into the warp's tile: every load in flight at once, no registers
 #define PS_STAGE_ROUND(c0_) do {                                                                                                      \
-            _Pragma("unroll") for (int s_ = 0; s_ < (int)PS_STAGE; ++s_) {                                                            \
-                if (4 * ((c0_) + s_ * TS_WARPS) >= cta_units) break;                               /* warp-uniform */                 \
-                const int m_ = 4 * ((c0_) + s_ * TS_WARPS) + (lane >> 3);                                                             \
+            _Pragma("unroll") for (int s_ = 0; s_ < K_STAGE; ++s_) {                                                            \
+                if (4 * ((c0_) + s_ * K_WARPS) >= cta_units) break;                               /* warp-uniform */                 \
+                const int m_ = 4 * ((c0_) + s_ * K_WARPS) + (lane >> 3);                                                             \
                 const int i_ = ((rank + a.group_ctas * m_) << 3) + (lane & 7);                                                        \
                 if (m_ < cta_units && i_ < d.n_src) {                                                                                 \
                     const uint32_t dst_ = sbuf + PS_CHUNK_BYTES * (uint32_t)s_ + 16u * (uint32_t)lane;                                \
@@ -759,8 +771,10 @@ __global__ void __launch_bounds__(TS_BLOCK, 1) icp_persist_kernel(const PersistA
             }                                                                                                                         \
         } while (0)
 
-        for (int it = 0; it < a.iterations; ++it) {
+        bool pre_staged = false;                  // the first staging round of the coming streaming pass is already in flight
+        for (int it = it_begin; it < a.iterations; ++it) {
             if (st.status != 0) break;            // failed pairs stop; every CTA of the group sees the same state
+            if (SEARCH_ONLY && it > 0 && !full_next) break;       // the first iteration that streams: the general instance takes over
             const float *T = st.Tf;               // the pose is read from shared memory where it is used
             const bool last = (it == a.iterations - 1);
             const unsigned long long mbits = fxs.mbits;
@@ -779,7 +793,7 @@ __global__ void __launch_bounds__(TS_BLOCK, 1) icp_persist_kernel(const PersistA
             wrow[warp][lane] = 0; wrow[warp][32 + lane] = 0;
             __syncwarp();
 #define PS_HAND_OVER() do {                                                                                               \
-                long long *tr_ = reinterpret_cast<long long *>(buf);          /* 29 x 33 int64 <= TS_CAP float4 */          \
+                long long *tr_ = reinterpret_cast<long long *>(buf);          /* 29 x 33 int64 <= K_CAP float4 */          \
                 __syncwarp();                                                                                             \
                 /* raw (wrapping) sums: the bias count * bits(M) of a slot is removed once, after the 32 lanes are added */ \
                 _Pragma("unroll") for (int k = 0; k < 28; ++k) tr_[k * 33 + lane] = acc[k];                               \
@@ -809,11 +823,12 @@ __global__ void __launch_bounds__(TS_BLOCK, 1) icp_persist_kernel(const PersistA
             // have passed returns the same exact answer).
             const bool full_search = it == 0 || full_next;
             if (full_search) { ts_cp_async_wait_all(); __syncwarp(); }      // a staging round issued ahead for nothing: the tile is the search's now
-            if (!full_search) {
+            if (!SEARCH_ONLY && !full_search) {
                 int since = 0;
-                for (int c0 = warp; c0 < cta_chunks; c0 += TS_WARPS * PS_STAGE) {
+                for (int c0 = warp; c0 < cta_chunks; c0 += K_WARPS * K_STAGE) {
 #ifndef PS_NO_PREFETCH
-                    if (c0 != warp) PS_STAGE_ROUND(c0);       // (the first round was issued before the previous iteration's barrier)
+                    if (c0 != warp || !pre_staged) PS_STAGE_ROUND(c0);       // (the first round was issued before the previous iteration's group sums,
+                                                                             //  unless this is the first iteration of a pair taken over)
 #else
                     PS_STAGE_ROUND(c0);
 #endif
@@ -822,9 +837,9 @@ __global__ void __launch_bounds__(TS_BLOCK, 1) icp_persist_kernel(const PersistA
                     __syncwarp();
                     constexpr int p1_unroll = PS_P1_UNROLL;
                     #pragma unroll p1_unroll
-                    for (int s = 0; s < PS_STAGE; ++s) {
-                        const int m = 4 * (c0 + s * TS_WARPS) + (lane >> 3);
-                        if (4 * (c0 + s * TS_WARPS) >= cta_units) break;                                  // warp-uniform
+                    for (int s = 0; s < K_STAGE; ++s) {
+                        const int m = 4 * (c0 + s * K_WARPS) + (lane >> 3);
+                        if (4 * (c0 + s * K_WARPS) >= cta_units) break;                                  // warp-uniform
                         const int i = ((rank + a.group_ctas * m) << 3) + (lane & 7);
                         const bool in = m < cta_units && i < d.n_src;
                         bool pending = false;
@@ -890,8 +905,8 @@ __global__ void __launch_bounds__(TS_BLOCK, 1) icp_persist_kernel(const PersistA
                         }
                     }
                     __syncwarp();
-                    since += PS_STAGE;
-                    if (since >= S3D_FX_SEGMENT - PS_STAGE) { PS_HAND_OVER(); since = 0; }      // warp-uniform
+                    since += K_STAGE;
+                    if (since >= S3D_FX_SEGMENT - K_STAGE) { PS_HAND_OVER(); since = 0; }      // warp-uniform
                 }
                 PHASE(14);
                 PS_HAND_OVER();
@@ -906,7 +921,7 @@ __global__ void __launch_bounds__(TS_BLOCK, 1) icp_persist_kernel(const PersistA
             {
                 const int n_items = full_search ? cta_units : pend_count;
                 // few octets left (late iterations): one per item, so that a lone search is not queued behind another one
-                const int item = n_items <= 2 * TS_WARPS ? 1 : a.item_octets;
+                const int item = n_items <= 2 * K_WARPS ? 1 : a.item_octets;
                 while (n_items > 0) {
                     int e0 = 0;
                     if (lane == 0) e0 = atomicAdd(&pend_next, item);
@@ -943,9 +958,9 @@ __global__ void __launch_bounds__(TS_BLOCK, 1) icp_persist_kernel(const PersistA
                     for (int level = (it == 0 && have_coarse) ? 0 : 1; level < 2; ++level) {
                         STAT(level ? 0 : 6, pending);
 #ifdef TS_USE_TMA
-                        b = tile_search(&cfg[level], x.x, x.y, x.z, level ? r : ccell, pending, buf, lane, level == 1 && it >= 4, bar_w, &parity TS_TM_PASS);
+                        b = tile_search<K_CAP>(&cfg[level], x.x, x.y, x.z, level ? r : ccell, pending, buf, lane, level == 1 && it >= 4, bar_w, &parity TS_TM_PASS);
 #else
-                        b = tile_search(&cfg[level], x.x, x.y, x.z, level ? r : ccell, pending, buf, lane, level == 1 && it >= 4 TS_TM_PASS);
+                        b = tile_search<K_CAP>(&cfg[level], x.x, x.y, x.z, level ? r : ccell, pending, buf, lane, level == 1 && it >= 4 TS_TM_PASS);
 #endif
                         if (level == 0 && pending && b.bd < INFINITY) r = sqrtf(b.bd) * 1.00001f + slack;
                     }
@@ -983,7 +998,8 @@ __global__ void __launch_bounds__(TS_BLOCK, 1) icp_persist_kernel(const PersistA
             // round of its streaming pass is issued now, so that its latency hides behind the group sum and the solve.  (Should the next
             // iteration skip the streaming pass after all, the copies are simply drained.)
 #ifndef PS_NO_PREFETCH
-            if (!last && warp < cta_chunks) PS_STAGE_ROUND(warp);
+            pre_staged = !SEARCH_ONLY && !last;
+            if (pre_staged && warp < cta_chunks) PS_STAGE_ROUND(warp);
 #endif
 #ifndef PS_BARRIER_CLASSIC
             // Self-validating group sums: there is no barrier.  Lane k of warp 0 owns slot k: it adds the CTA's (hi, lo) to the group's
@@ -998,7 +1014,7 @@ __global__ void __launch_bounds__(TS_BLOCK, 1) icp_persist_kernel(const PersistA
                 long long hi = 0, lo = 0;
                 if (lane < 29) {
                     #pragma unroll
-                    for (int w = 0; w < TS_WARPS; ++w) { hi += wrow[w][lane]; lo += wrow[w][32 + lane]; }
+                    for (int w = 0; w < K_WARPS; ++w) { hi += wrow[w][lane]; lo += wrow[w][32 + lane]; }
                     hi += lo >> 32; lo &= 0xffffffffll;
                 }
                 if (a.group_ctas > 1) {
@@ -1035,7 +1051,7 @@ __global__ void __launch_bounds__(TS_BLOCK, 1) icp_persist_kernel(const PersistA
             if (threadIdx.x < S3D_ROW) {
                 long long v = 0;
                 #pragma unroll
-                for (int w = 0; w < TS_WARPS; ++w) v += wrow[w][threadIdx.x];
+                for (int w = 0; w < K_WARPS; ++w) v += wrow[w][threadIdx.x];
                 ctot[threadIdx.x] = v;
             }
             if (a.group_ctas > 1) {
@@ -1097,6 +1113,19 @@ __global__ void __launch_bounds__(TS_BLOCK, 1) icp_persist_kernel(const PersistA
         __syncwarp();
         if (rank == 0 && threadIdx.x == 0) a.states[pair] = st;
     }
+}
+
+// the two instances: general (512 threads, 640-candidate tiles) and search-only (768 threads, 512-candidate tiles)
+#ifndef TS_SEARCH_BLOCK
+#define TS_SEARCH_BLOCK 768
+#endif
+#ifndef TS_SEARCH_CAP
+#define TS_SEARCH_CAP 512
+#endif
+template <int EST> static const void *persist_fn(bool search_only)
+{
+    return search_only ? (const void *)icp_persist_kernel<EST, TS_SEARCH_BLOCK, TS_SEARCH_CAP, true>
+                       : (const void *)icp_persist_kernel<EST, TS_BLOCK, TS_CAP, false>;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1188,15 +1217,20 @@ int s3d_register_issue(s3d_ctx *ctx, const s3d_cloud *const *src, const s3d_clou
     int ctas = std::max(1, std::min((n_max + rounds * ICP_BLOCK - 1) / (rounds * ICP_BLOCK), std::max(1, resident / n_pairs)));
     // persistent path: groups of CTAs, all co-resident (cooperative launch), one group per pair at a time
     int p_groups = 1, p_group_ctas = 1;
-    const size_t p_smem = sizeof(float4) * TS_CAP * TS_WARPS;
+    const size_t p_smem = sizeof(float4) * TS_CAP * TS_WARPS, p_smem_search = sizeof(float4) * TS_SEARCH_CAP * (TS_SEARCH_BLOCK / 32);
     if (persist) {
         if (ctx->persist_resident[plane ? 0 : 1] == 0) {
-            const void *fn = plane ? (const void *)icp_persist_kernel<S3D_ESTIMATOR_POINT_TO_PLANE> : (const void *)icp_persist_kernel<S3D_ESTIMATOR_SVD>;
-            S3D_CUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p_smem));
-            int per_sm = 0;
-            S3D_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, TS_BLOCK, p_smem));
-            if (per_sm < 1) return s3d_fail(ctx, S3D_E_CUDA, "icp_persist_kernel does not fit on an SM");
-            ctx->persist_resident[plane ? 0 : 1] = per_sm * ctx->sm_count;
+            int res = 1 << 30;
+            for (int so = 0; so < 2; ++so) {          // both instances must be co-resident with the same grid: one CTA per SM each
+                const void *fn = plane ? persist_fn<S3D_ESTIMATOR_POINT_TO_PLANE>(so != 0) : persist_fn<S3D_ESTIMATOR_SVD>(so != 0);
+                const size_t smem = so ? p_smem_search : p_smem;
+                S3D_CUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                int per_sm = 0;
+                S3D_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, so ? TS_SEARCH_BLOCK : TS_BLOCK, smem));
+                if (per_sm < 1) return s3d_fail(ctx, S3D_E_CUDA, "icp_persist_kernel does not fit on an SM");
+                res = std::min(res, per_sm * ctx->sm_count);
+            }
+            ctx->persist_resident[plane ? 0 : 1] = res;
         }
         const int p_res = ctx->persist_resident[plane ? 0 : 1];
         const int chunks_per_cta = 2 * TS_WARPS;      // at least two chunks of 32 queries per warp before a pair is spread wider
@@ -1323,7 +1357,17 @@ int s3d_register_issue(s3d_ctx *ctx, const s3d_cloud *const *src, const s3d_clou
         { static const char *e = getenv("S3D_SLACK_CELLS"); pa.slack_cells = e ? (float)atof(e) : 0.08f; }
         { static const char *e = getenv("S3D_ITEM_OCTETS"); const int v = e ? atoi(e) : 2; pa.item_octets = v >= 4 ? 4 : v >= 2 ? 2 : 1; }
         void *kargs[] = {&pa};
-        const void *fn = plane ? (const void *)icp_persist_kernel<S3D_ESTIMATOR_POINT_TO_PLANE> : (const void *)icp_persist_kernel<S3D_ESTIMATOR_SVD>;
+        // Two launches: the search-only instance (768 threads: the search gains from resident warps, and without the streaming
+        // pass its 58 accumulator registers do not have to stay live) runs every pair's leading full-search iterations, the
+        // general instance takes each pair over -- PairState + per-query arrays -- at its first streaming iteration.
+        static const bool split = []() { const char *e = getenv("S3D_SPLIT"); return !e || atoi(e) != 0; }();
+        if (split) {
+            const void *fs = plane ? persist_fn<S3D_ESTIMATOR_POINT_TO_PLANE>(true) : persist_fn<S3D_ESTIMATOR_SVD>(true);
+            S3D_CUDA(ctx, cudaLaunchCooperativeKernel(fs, dim3(p_groups * p_group_ctas), dim3(TS_SEARCH_BLOCK), kargs, p_smem_search, ctx->stream));
+            S3D_LAUNCHED(ctx); ++iter_launches;
+            S3D_CUDA(ctx, cudaMemsetAsync(ctx->d_partials, 0, sizeof(long long) * S3D_ROW * 3 * (size_t)p_groups, ctx->stream));
+        }
+        const void *fn = plane ? persist_fn<S3D_ESTIMATOR_POINT_TO_PLANE>(false) : persist_fn<S3D_ESTIMATOR_SVD>(false);
         S3D_CUDA(ctx, cudaLaunchCooperativeKernel(fn, dim3(p_groups * p_group_ctas), dim3(TS_BLOCK), kargs, p_smem, ctx->stream));
         S3D_LAUNCHED(ctx); ++iter_launches;
     }

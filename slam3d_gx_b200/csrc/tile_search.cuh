@@ -244,6 +244,7 @@ struct TileOut { float4 bq; float bd; float lb; float4 q2; float lb3; };     // 
 // NOT inlined on purpose: the caller keeps 29 double accumulators and a prefetched chunk in registers; as a real
 // call the search spills them only around itself (the rare path of a late iteration) instead of raising the
 // register pressure of the whole streaming loop.
+template <int CAP>
 __device__ __noinline__ TileOut tile_search(const TileCfg *cfg, float px, float py, float pz, float r, bool pending,
                                             float4 *__restrict__ buf, int lane, bool want2 TS_BAR_ARG TS_TM_ARG)
 {
@@ -333,7 +334,7 @@ __device__ __noinline__ TileOut tile_search(const TileCfg *cfg, float px, float 
                 if (lane >= o) incl += v;
             }
             const uint32_t total = __shfl_sync(full, incl, 31), excl = incl - cnt;
-            const uint32_t room = (uint32_t)(TS_CAP - fill);
+            const uint32_t room = (uint32_t)(CAP - fill);
             uint32_t take = cnt;
             if (total > room) take = excl >= room ? 0u : min(cnt, room - excl);
             const uint32_t moved_pts = min(total, room);

@@ -162,7 +162,7 @@ def test_enqueue_drain_matches_blocking_calls(ctx, small_cam, small_pair):
             assert r["status"] == 0 and np.array_equal(r["T"], ref[k]["T"]) and r["inliers"] == ref[k]["inliers"]
             assert r["fitness"] == ref[k]["fitness"] and r["norm"] == ref[k]["norm"] and r["iterations"] == 6
         assert res[2]["status"] == _abi.PAIR_FEW and np.array_equal(res[2]["T"], np.eye(4))
-        assert all(t["iterate_ms"] > 0 and t["index_ms"] > 0 and t["iter_launches"] == 1 for t in tms)
+        assert all(t["iterate_ms"] > 0 and t["index_ms"] > 0 and t["iter_launches"] >= 1 for t in tms)
         assert ctx.register_drain() == ([], [])
         # depth limit
         for _ in range(ASYNC_DEPTH):

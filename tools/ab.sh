@@ -34,6 +34,11 @@ if [ -n "$BENCH" ]; then
     L=""; [ -n "$lib" ] && L="S3D_LIBRARY=$PWD/slam3d_gx_b200/libslam3d_b200$lib.so"
     env $L python bench.py --no-cpu-baseline --no-batch-regime --steps 120 --warmup 30 2>/dev/null | python -c "
 import json,sys
-d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('  bench lib \'$lib\': value', round(d['value']), 'avg_launch_us', round(d['roofline']['avg_launch_us'],1), 'e2e', round(d['e2e']['value']), 'config4', round(d['config4']['iterations_per_s']) if d.get('config4') else None)"
+d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('  bench lib \'$lib\': value', round(d['value']), 'ms_per_step', round(d['ms_per_step'],4), 'e2e', round(d['e2e']['value']), 'config4', round(d['config4']['iterations_per_s']) if d.get('config4') else None)"
+  done
+  for e in $ENVS; do
+    env $e python bench.py --no-cpu-baseline --no-batch-regime --steps 120 --warmup 30 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('  bench env \'$e\': value', round(d['value']), 'ms_per_step', round(d['ms_per_step'],4), 'e2e', round(d['e2e']['value']), 'config4', round(d['config4']['iterations_per_s']) if d.get('config4') else None)"
   done
 fi
