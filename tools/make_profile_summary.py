@@ -30,7 +30,7 @@ with open(os.path.join(out_dir, f"{tag}_launches_summary.md"), "w") as f:
         # a registration = the search-only instance (template argument true) followed by the general instance
         regs = []
         for n, t in its:
-            if "(bool)1" in n or "true" in n or not regs: regs.append([t])
+            if n.rstrip().endswith(", 1>") or "(bool)1" in n or "true" in n or not regs: regs.append([t])
             else: regs[-1].append(t)
         f.write("\n`icp_persist_kernel` launches: one registration = 30 ICP iterations = the search-only instance (leading full-search "
                 "iterations) + the general instance; us per registration (search-only + general):\n\n`"
