@@ -646,17 +646,6 @@ struct PersistArgs {
     int item_octets;             // octets a warp takes from the pending list at a time (1, 2 or 4: one per 8 lanes)
 };
 
-__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p)
-{
-    unsigned v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void red_release_add_u32(unsigned *p, unsigned v)
-{
-    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-
 // How an iteration runs (one group of CTAs per pair; octet u = 8 consecutive source points belongs to CTA u mod group_ctas):
 //   pass 1  streaming: every warp walks its share of the CTA's octets once, 49 bytes per query (point, correspondence, normal + bound,
 //           flag byte; staged into the warp's tile by cp.async, all loads of up to PS_STAGE chunks in flight at once).  Skip test
@@ -668,8 +657,9 @@ __device__ __forceinline__ void red_release_add_u32(unsigned *p, unsigned v)
 //   pass 2  searching: warps take octets from the pending list (dynamically: search cost varies several-fold with depth and surface
 //           orientation), search them in a TMA-staged shared-memory tile (tile_search.cuh), write the new per-query state and add
 //           the terms of the searched queries.  In the first iteration every octet is pending and there is no pass 1.
-//   then    the CTA's sums (integers, smem atomics) go to the group as one row, group barrier (red.release / ld.acquire), every CTA
-//           adds the rows and solves redundantly in strict double: all CTAs hold bit-identical poses, no second barrier.
+//   then    the CTA's sums (integers) are added to the group's words with atomics that also count the CTAs that have added: a word
+//           whose count is complete holds the sum (no barrier); every CTA reads the 58 words and solves redundantly in strict
+//           double: all CTAs hold bit-identical poses.
 // Because the sums do not depend on the order of the additions, a query can be accumulated by whichever pass decides it.
 template <int EST, int BLOCK_, int CAP_, bool SEARCH_ONLY>
 __global__ void __launch_bounds__(BLOCK_, 1) icp_persist_kernel(const PersistArgs a)
@@ -707,9 +697,6 @@ __global__ void __launch_bounds__(BLOCK_, 1) icp_persist_kernel(const PersistArg
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-#endif
-#ifdef PS_BARRIER_CLASSIC
-    unsigned *bar = a.barriers + group;
 #endif
     unsigned epoch = 0;
     const float gate_r = a.max_d2 < INFINITY ? sqrtf(a.max_d2) : INFINITY;
@@ -1001,7 +988,6 @@ __global__ void __launch_bounds__(BLOCK_, 1) icp_persist_kernel(const PersistArg
             pre_staged = !SEARCH_ONLY && !last;
             if (pre_staged && warp < cta_chunks) PS_STAGE_ROUND(warp);
 #endif
-#ifndef PS_BARRIER_CLASSIC
             // Self-validating group sums: there is no barrier.  Lane k of warp 0 owns slot k: it adds the CTA's (hi, lo) to the group's
             // two words of the slot with ONE atomic each, and every atomic also carries +1 in bits 48.. of the word.  A word whose
             // count has reached the number of CTAs of the group holds the complete sum: the lane polls its own two words, nothing
@@ -1047,48 +1033,6 @@ __global__ void __launch_bounds__(BLOCK_, 1) icp_persist_kernel(const PersistArg
                 total[lane] = lane < 29 ? fx_total<EST>(hi, lo, lane, fxs.scale) : 0.0;
                 __syncwarp();
             } else if (a.group_ctas > 1) ++epoch;
-#else
-            if (threadIdx.x < S3D_ROW) {
-                long long v = 0;
-                #pragma unroll
-                for (int w = 0; w < K_WARPS; ++w) v += wrow[w][threadIdx.x];
-                ctot[threadIdx.x] = v;
-            }
-            if (a.group_ctas > 1) {
-                // the CTA's sums go to the group's accumulators (red.add.u64: integers, order free); then arrive at the barrier
-                long long *g = a.gacc + ((size_t)(epoch % 3u) * a.groups + group) * S3D_ROW;
-                if (threadIdx.x < S3D_ROW) {
-                    const long long v = ctot[threadIdx.x];
-                    if (v != 0) atomicAdd(reinterpret_cast<unsigned long long *>(&g[threadIdx.x]), (unsigned long long)v);
-                    ctot[threadIdx.x] = 0;
-                }
-                ++epoch;
-                __syncthreads();
-                if (warp == 0) {
-                    if (lane == 0) {
-                        // release (the CTA's atomics, issued by other threads before the __syncthreads above) -> arrive -> wait -> acquire
-                        red_release_add_u32(bar, 1u);
-                        const unsigned target = epoch * (unsigned)a.group_ctas;
-                        while (ld_acquire_u32(bar) < target) { }
-                    }
-                    __syncwarp();
-                    PHASE(10);
-                    const long long hi = __ldcg(&g[lane]), lo = __ldcg(&g[32 + lane]);
-                    total[lane] = lane < 29 ? fx_total<EST>(hi, lo, lane, fxs.scale) : 0.0;
-                    // the buffer read two epochs ago is free: every CTA is past the barrier that followed its reads.  It is added to
-                    // again only after the NEXT barrier, which this CTA (rank 0) reaches after these stores.
-                    if (rank == 0) {
-                        long long *gz = a.gacc + ((size_t)((epoch + 1u) % 3u) * a.groups + group) * S3D_ROW;
-                        __stcg(&gz[lane], 0ll); __stcg(&gz[32 + lane], 0ll);
-                    }
-                    __syncwarp();
-                }
-            } else {
-                __syncthreads();                  // (the 64 sums were written by two warps)
-                if (warp == 0) total[lane] = lane < 29 ? fx_total<EST>(ctot[lane], ctot[32 + lane], lane, fxs.scale) : 0.0;
-                __syncwarp();
-            }
-#endif
             PHASE(11);
             if (threadIdx.x == 0) {
                 solve_and_update<EST>(total, &st, a.min_corr, a.pivot_eps);
