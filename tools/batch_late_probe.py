@@ -1,4 +1,4 @@
-"""Scratch driver for ncu: a 16-pair batch started from the ground-truth poses, so that nearly every iteration is a
+"""Driver for ncu: a 16-pair batch started from the ground-truth poses, so that nearly every iteration is a
 streaming (late) iteration: the regime in which the registration kernel is bound by HBM bandwidth."""
 import sys, os
 import numpy as np

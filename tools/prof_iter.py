@@ -1,4 +1,4 @@
-"""Scratch driver for ncu: one single-pair registration (config 2 shape), optionally starting converged."""
+"""Driver for ncu: one single-pair registration (config 2 shape), optionally starting converged."""
 import sys, os
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))

@@ -1,4 +1,4 @@
-"""Scratch driver for compute-sanitizer: a small registration (all search modes), plane extraction, filters."""
+"""Driver for compute-sanitizer: a small registration (all search modes), plane extraction, filters."""
 import sys, os
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
