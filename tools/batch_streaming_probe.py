@@ -1,4 +1,4 @@
-"""the streaming (late-iteration) regime of a 64-pair batch, where the working set (64 x ~25 MB of per-query state and
+"""The streaming (late-iteration) regime of a 64-pair batch, where the working set (64 x ~25 MB of per-query state and
 clouds) does not fit L2: time per late iteration = (t(40 iterations) - t(10 iterations)) / 30, against the HBM roofline."""
 import sys, os, json
 import numpy as np

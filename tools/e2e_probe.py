@@ -1,4 +1,4 @@
-"""where the end-to-end step (host buffers -> pose) spends its time, blocking and pipelined upload.
+"""Where the end-to-end step (host buffers -> pose) spends its time, blocking and pipelined upload.
 argv: [npairs] [torch]  -- 'torch' runs the ctx on torch's current stream like bench.py does."""
 import sys, os, time
 import numpy as np

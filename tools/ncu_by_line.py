@@ -1,4 +1,4 @@
-"""attribute the per-SASS-instruction counters of an .ncu-rep to source lines, using nvdisasm line info of the
+"""Attribute the per-SASS-instruction counters of an .ncu-rep to source lines, using nvdisasm line info of the
 same build.  Usage: ncu_by_line.py file.ncu-rep lib.so kernel-mangled-name"""
 import csv, subprocess, sys, io, re, os, tempfile, collections, glob
 rep, lib, kname = sys.argv[1], sys.argv[2], sys.argv[3]

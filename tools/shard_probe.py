@@ -1,4 +1,4 @@
-"""device time of one rank's config-4 shard (64 pairs x 10 iterations, indices rebuilt) for several shards on ONE GPU:
+"""Device time of one rank's config-4 shard (64 pairs x 10 iterations, indices rebuilt) for several shards on ONE GPU:
 how much of the rank skew of the 8-GPU run is the workload itself.  Usage: python tools/shard_probe.py [rank ...]"""
 import sys, os, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
