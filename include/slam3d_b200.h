@@ -244,6 +244,10 @@ int  s3d_last_timing(const s3d_ctx *ctx, s3d_timing *out);
 int  s3d_register_enqueue(s3d_ctx *ctx, const s3d_cloud *src, const s3d_cloud *tgt, const double *guess /* 16 doubles or NULL */,
                           const s3d_icp_params *params);
 int  s3d_register_drain(s3d_ctx *ctx, s3d_result *results_out, s3d_timing *timing_out /* may be NULL */, int capacity, int *n_out);
+/* How s3d_register_batch spreads n_pairs pairs (largest source: n_points_max points) over resident_ctas co-resident CTAs of the
+ * registration kernel (one per SM: 148 on a B200): *groups_out pairs are in flight at a time, each on *group_ctas_out CTAs; the
+ * groups walk the batch in rounds.  Pure host arithmetic (no device needed): lets a host size its batches. */
+int  s3d_batch_shape(int n_pairs, int n_points_max, int resident_ctas, int *groups_out, int *group_ctas_out);
 int  s3d_segment_planes_enqueue(s3d_ctx *ctx, s3d_cloud *cloud, const s3d_plane_params *params);
 int  s3d_segment_planes_drain(s3d_ctx *ctx, s3d_plane *planes_out, int *n_planes_out, int capacity, int *n_out);
 void s3d_icp_params_default(s3d_icp_params *p);

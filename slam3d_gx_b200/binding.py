@@ -34,7 +34,7 @@ EXPORTS = [
     "s3d_last_correspondences", "s3d_last_timing", "s3d_icp_params_default", "s3d_plane_params_default",
     "s3d_planar_keypoints", "s3d_gather_results", "s3d_cloud_passthrough_z", "s3d_cloud_voxel_grid", "s3d_cloud_transform",
     "s3d_cloud_concat", "s3d_map_fuse", "s3d_cloud_from_depth_normals", "s3d_cloud_upload_async", "s3d_cloud_wait", "s3d_host_alloc", "s3d_host_free",
-    "s3d_memory_stats", "s3d_last_plane_timing", "s3d_comm_unique_id", "s3d_comm_create", "s3d_comm_destroy", "s3d_register_batch_gather", "s3d_register_enqueue", "s3d_register_drain", "s3d_segment_planes_enqueue", "s3d_segment_planes_drain", "s3d_cloud_release",
+    "s3d_memory_stats", "s3d_last_plane_timing", "s3d_comm_unique_id", "s3d_comm_create", "s3d_comm_destroy", "s3d_register_batch_gather", "s3d_register_enqueue", "s3d_register_drain", "s3d_segment_planes_enqueue", "s3d_segment_planes_drain", "s3d_cloud_release", "s3d_batch_shape",
 ]
 ASYNC_DEPTH = 64          # S3D_ASYNC_DEPTH
 MAX_PLANES = 16           # S3D_MAX_PLANES
@@ -80,6 +80,7 @@ def load_library():
     lib.s3d_cloud_free.restype = None
     lib.s3d_cloud_release.argtypes = [vp, vp]
     lib.s3d_cloud_release.restype = None
+    lib.s3d_batch_shape.argtypes = [ci, ci, ci, C.POINTER(ci), C.POINTER(ci)]
     lib.s3d_segment_planes.argtypes = [vp, vp, C.POINTER(_abi.PlaneParams), C.POINTER(_abi.Plane), C.POINTER(ci)]
     lib.s3d_register_batch.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), vp, ci, C.POINTER(_abi.IcpParams),
                                        C.POINTER(_abi.Result)]
@@ -202,6 +203,15 @@ class Cloud:
         if self.handle is not None:
             self.ctx.lib.s3d_cloud_release(self.ctx.h, self.handle)
             self.handle = None
+
+
+def batch_shape(n_pairs: int, n_points_max: int, resident_ctas: int = 148):
+    """(groups, CTAs per group) of a batch (s3d_batch_shape; no GPU needed)."""
+    g, c = C.c_int(0), C.c_int(0)
+    rc = load_library().s3d_batch_shape(n_pairs, n_points_max, resident_ctas, C.byref(g), C.byref(c))
+    if rc != 0:
+        raise S3DError(f"s3d_batch_shape rc={rc}")
+    return g.value, c.value
 
 
 class Context:

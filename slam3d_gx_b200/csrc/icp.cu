@@ -1075,6 +1075,24 @@ template <int EST> static const void *persist_fn(bool search_only)
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
+// How a batch is spread over the co-resident CTAs of the persistent kernel (pure host arithmetic, no CUDA call).
+// Up to 16 pairs: one group each, all at once.  Larger batches: 4 groups of a quarter of the chip each walk the batch in
+// rounds.  One small group per pair -- every pair at once -- made the launch as long as its most expensive pair and left
+// 148 mod n_pairs SMs idle: 54.1 / 64.5 ms for two 64-pair shards of config 4 against 38.6 / 40.0 ms with 4 groups of 37
+// CTAs (128 pairs: 75.5 / 75.8 / 73.6 ms with groups of 9 / 18 / 37).  Larger groups pay the per-iteration group sum +
+// solve on more SMs: for 16 pairs 9-CTA groups keep a late iteration at 87 us where 49-CTA groups need 129 us.
+extern "C" int s3d_batch_shape(int n_pairs, int n_points_max, int resident_ctas, int *groups_out, int *group_ctas_out)
+{
+    if (n_pairs <= 0 || n_points_max < 0 || resident_ctas <= 0 || !groups_out || !group_ctas_out) return S3D_E_ARG;
+    const int chunks_per_cta = 2 * TS_WARPS;      // at least two chunks of 32 queries per warp before a pair is spread wider
+    const int useful = std::max(1, (n_points_max + 32 * chunks_per_cta - 1) / (32 * chunks_per_cta));
+    const int max_groups = n_pairs <= 16 ? n_pairs : 4;
+    const int group_ctas = std::max(1, std::min(useful, resident_ctas / std::min(max_groups, resident_ctas)));
+    *group_ctas_out = group_ctas;
+    *groups_out = std::max(1, std::min(n_pairs, resident_ctas / group_ctas));
+    return S3D_OK;
+}
+
 extern "C" void s3d_icp_params_default(s3d_icp_params *p)
 {
     if (!p) return;
@@ -1177,17 +1195,16 @@ int s3d_register_issue(s3d_ctx *ctx, const s3d_cloud *const *src, const s3d_clou
             ctx->persist_resident[plane ? 0 : 1] = res;
         }
         const int p_res = ctx->persist_resident[plane ? 0 : 1];
-        const int chunks_per_cta = 2 * TS_WARPS;      // at least two chunks of 32 queries per warp before a pair is spread wider
-        const int useful = std::max(1, (n_max + 32 * chunks_per_cta - 1) / (32 * chunks_per_cta));
-        // Up to 16 pairs: one group each, all at once.  Larger batches: 4 groups of a quarter of the chip each walk the batch in
-        // rounds.  One small group per pair -- every pair at once -- made the launch as long as its most expensive pair and left
-        // 148 mod n_pairs SMs idle: 54.1 / 64.5 ms for two 64-pair shards of config 4 against 38.6 / 40.0 ms with 4 groups of 37
-        // CTAs (128 pairs: 75.5 / 75.8 / 73.6 ms with groups of 9 / 18 / 37).  Larger groups pay the per-iteration group sum +
-        // solve on more SMs: for 16 pairs 9-CTA groups keep a late iteration at 87 us where 49-CTA groups need 129 us.
-        const int max_groups = n_pairs <= 16 ? n_pairs : 4;
-        p_group_ctas = std::max(1, std::min(useful, p_res / std::min(max_groups, p_res)));
-        { static const char *e = getenv("S3D_GROUP_CTAS"); const int v = e ? atoi(e) : 0; if (v > 0) p_group_ctas = std::max(1, std::min(std::min(useful, p_res), v)); }
-        p_groups = std::max(1, std::min(n_pairs, p_res / p_group_ctas));
+        s3d_batch_shape(n_pairs, n_max, p_res, &p_groups, &p_group_ctas);
+        {
+            static const char *e = getenv("S3D_GROUP_CTAS");          // developer override of the group size (tools/group_probe.py)
+            const int v = e ? atoi(e) : 0;
+            if (v > 0) {
+                const int useful = std::max(1, (n_max + 64 * TS_WARPS - 1) / (64 * TS_WARPS));
+                p_group_ctas = std::max(1, std::min(std::min(useful, p_res), v));
+                p_groups = std::max(1, std::min(n_pairs, p_res / p_group_ctas));
+            }
+        }
         ctas = 3;                                     // d_partials doubles as the groups' accumulators: 3 epochs x groups (<= pairs) rows
     }
     int rc = ensure_batch(ctx, n_pairs, ctas);

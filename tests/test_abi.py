@@ -87,3 +87,25 @@ def test_only_the_checkers_touch_the_oracle():
                 if f.endswith((".py", ".cpp", ".h", ".hpp", ".c")):
                     txt = open(os.path.join(dirpath, f), errors="ignore").read()
                     assert "import oracle" not in txt and "from oracle" not in txt and "liboracle" not in txt, os.path.join(dirpath, f)
+
+
+def test_batch_shape_rule():
+    """s3d_batch_shape (host arithmetic of s3d_register_batch): a lone pair gets the whole chip, up to 16 pairs
+    run all at once on equal groups, larger batches on four groups that walk the list; small clouds are not spread wider than
+    two chunks of 32 queries per warp; the groups always fit the resident CTAs."""
+    n = 307200
+    assert binding.batch_shape(1, n) == (1, 148)
+    assert binding.batch_shape(2, n) == (2, 74)
+    assert binding.batch_shape(16, n) == (16, 9)
+    assert binding.batch_shape(17, n) == (4, 37)
+    assert binding.batch_shape(64, n) == (4, 37)
+    assert binding.batch_shape(512, n) == (4, 37)
+    assert binding.batch_shape(5, 1000) == (5, 1)            # a 1000-point cloud is one CTA's worth
+    assert binding.batch_shape(200, 1000) == (148, 1)        # ... and then every CTA takes pairs
+    for pairs in (1, 3, 16, 17, 100, 1000):
+        for pts in (0, 1, 5000, 307200, 2000000):
+            for res in (1, 7, 132, 148):
+                g, c = binding.batch_shape(pairs, pts, res)
+                assert 1 <= g <= pairs and c >= 1 and g * c <= max(res, 1)
+    with pytest.raises(s3d.S3DError):
+        binding.batch_shape(0, n)
